@@ -1,0 +1,200 @@
+"""Shared table of golden cases + deterministic input builders.
+
+Used by tools/make_golden.py (build container: runs the real reference on these inputs) and by
+the tests (any box: rebuild the same inputs, run oracle / CUDA path, compare with the stored
+reference outputs in tests/golden/<case>.json).
+"""
+import gzip
+import os
+import random
+
+import numpy as np
+
+from mcaller_b200 import refmark, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_SPEC3 = dict(seed=11, contigs=[("ctgA", 6000), ("ctgB", 5000), ("ctgC", 4500)], n_reads=60, len_min=300, len_max=900, header=True)
+_SPEC_A = dict(seed=12, contigs=[("c1", 1500), ("c2", 1500)], n_reads=10, len_min=150, len_max=300)
+_SPEC_G = dict(seed=13, contigs=[("chrG", 8000)], n_reads=40, len_min=300, len_max=700)
+_SPEC_P = dict(seed=14, contigs=[("p1", 5000), ("p2", 4000)], n_reads=40, len_min=300, len_max=800, header=True)
+
+R95 = "r95_twobase_model_NN_6_m6A.pkl"
+R94 = "r94_model_NN_6_m6A.pkl"
+CAAY_BARE = "CAAY_bare_model_6_m6A.pkl"
+
+CASES = {
+    # reference's own fixture (README.md:132 command) and the survey's extra regression run
+    "masonread1_p": dict(fixture="masonread1", positions="test_positions_m6A.txt", model=R95, base="A"),
+    "masonread1_gatc": dict(fixture="masonread1", motif="GATC", model=R95, base="A"),
+    "masonread1_gatc_s2": dict(fixture="masonread1", motif="GATC", model=R95, base="A", s=2),
+    # synthetic, three contigs + header line, methylation signal on half the sites
+    "gatc_s0": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, beds=[["-d", "1", "-t", "0.5"], ["-d", "3", "-t", "0.3"]]),
+    "gatc_s1": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1),
+    "gatc_s2": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=2, beds=[["-d", "2", "-t", "0.5"], ["-d", "2", "-t", "0.5", "--control"]]),
+    # dense multi-M windows (every A is a target), reads truncated so windows stay open across reads/contigs
+    "A_s0": dict(spec=_SPEC_A, motif="A", model=R95, base="A", post="truncate"),
+    "A_s2": dict(spec=_SPEC_A, motif="A", model=R95, base="A", s=2, post="truncate"),
+    "gaa_s1": dict(spec=_SPEC_G, motif="GAA", model=R95, base="A", s=1),
+    "gaa_s2": dict(spec=_SPEC_G, motif="GAA", model=R95, base="A", s=2),
+    # positions file on both strands
+    "pos_p": dict(spec=_SPEC_P, positions="random", model=R95, base="A", s=1),
+    # read-quality filter
+    "gatc_q": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, q=13.5),
+    # malformed / odd lines
+    "adversarial": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1, post="adversarial"),
+    # bare estimator pickles -> 'general' model path
+    "bare_r94": dict(spec=_SPEC3, motif="GATC", model=R94, base="A", meth=True),
+    "bare_caay_p": dict(spec=_SPEC_P, positions="random", model=CAAY_BARE, base="A"),
+    # cytosine targets
+    "cg_c": dict(spec=_SPEC_G, motif="CG", model=R94, base="C", s=1),
+}
+
+
+def _fixture_fasta(tsv_bytes, length, out_path):
+    """Rebuild the missing assembly FASTA: N everywhere except what TSV column 3 pins."""
+    seq = bytearray(b"N" * length)
+    for ln in tsv_bytes.split(b"\n"):
+        f = ln.split(b"\t")
+        if len(f) < 3:
+            continue
+        p = int(f[1])
+        seq[p:p + len(f[2])] = f[2]
+    with open(out_path, "w") as fh:
+        fh.write(">ecoli\n")
+        s = seq.decode()
+        fh.write("\n".join(s[i:i + 60] for i in range(0, length, 60)) + "\n")
+
+
+def _post_truncate(lines, seed):
+    """Cut each read at a random line so that windows are left open at read ends."""
+    rnd = random.Random(seed)
+    out, cur, cur_name = [], [], None
+    def flush():
+        if cur:
+            keep = rnd.randint(max(1, len(cur) // 2), len(cur))
+            out.extend(cur[:keep])
+    for ln in lines:
+        f = ln.split("\t")
+        nm = f[3] if len(f) > 3 else None
+        if nm != cur_name:
+            flush()
+            cur, cur_name = [], nm
+        cur.append(ln)
+    flush()
+    return out
+
+
+def _post_adversarial(lines, seed):
+    rnd = random.Random(seed)
+    out = []
+    for i, ln in enumerate(lines):
+        r = rnd.random()
+        f = ln.split("\t")
+        if len(f) < 13 or f[0] == "contig":
+            out.append(ln)
+            continue
+        if r < 0.01:
+            out.append("\t".join(f[:5]))                      # short line (<12 fields) -> dropped
+        elif r < 0.02:
+            out.append("\t".join(["ghost"] + f[1:]))          # unknown contig -> dropped, state untouched
+        elif r < 0.03:
+            out.append(ln + "\t1.5,2.5,3.5")                  # extra samples column
+        elif r < 0.04:
+            out.append(f[0] + "\t\t" + "\t".join(f[1:]))      # doubled tab collapses in str.split()
+        elif r < 0.05:
+            out.append(ln + " ")                              # trailing blank (a CR would hang the reference:
+                                                              # its char count never reaches the byte size, :144-148)
+        elif r < 0.055:
+            out.append("")                                    # empty line
+        elif r < 0.065:
+            out.append("\t".join(f[:12]))                     # exactly 12 fields (minimum accepted)
+        elif r < 0.075:
+            out.append("\t".join(f[:11]))                     # 11 fields -> dropped
+        elif r < 0.085:
+            continue                                          # line deleted (position gaps / event gaps)
+        out.append(ln)
+    return out
+
+
+POSTS = {"truncate": _post_truncate, "adversarial": _post_adversarial}
+
+
+def _random_positions(spec, genomes, seed, frac=0.04):
+    rnd = random.Random(seed)
+    rows = []
+    for ci, (nm, ln) in enumerate(spec.contigs):
+        g = genomes[ci]
+        for p in range(12, ln - 12):
+            if g[p] == 65 and rnd.random() < frac:
+                rows.append((nm, p, "+"))
+            elif g[p] == 84 and rnd.random() < frac:
+                rows.append((nm, p, "-"))
+    return rows
+
+
+def build_inputs(case, outdir, models_dir=None):
+    """Write tsv / fasta / fastq / (positions) for `case` into outdir; return dict of paths."""
+    models_dir = models_dir or os.path.join(GOLD, "models")
+    paths = {"tsv": os.path.join(outdir, "syn.eventalign.tsv"), "fasta": os.path.join(outdir, "ref.fasta"),
+             "fastq": os.path.join(outdir, "syn.fastq"), "model": os.path.join(models_dir, case["model"])}
+    if "fixture" in case:
+        fx = os.path.join(GOLD, case["fixture"])
+        tsv = gzip.open(os.path.join(fx, "masonread1.eventalign.tsv.gz"), "rb").read()
+        with open(paths["tsv"], "wb") as fh:
+            fh.write(tsv)
+        _fixture_fasta(tsv, 4734145, paths["fasta"])
+        with open(paths["fastq"], "w") as fh:
+            fh.write(open(os.path.join(fx, "masonread1.fastq")).read())
+        if case.get("positions"):
+            paths["positions"] = os.path.join(outdir, "positions.txt")
+            with open(paths["positions"], "w") as fh:
+                fh.write(open(os.path.join(fx, case["positions"])).read())
+        return paths
+    spec = synth.SynthSpec(**case["spec"])
+    genomes = [synth.genome(spec, ci) for ci in range(len(spec.contigs))]
+    base = case.get("base", "A")
+    if case.get("positions") == "random":
+        rows = _random_positions(spec, genomes, spec.seed + 1000)
+        paths["positions"] = os.path.join(outdir, "positions.txt")
+        with open(paths["positions"], "w") as fh:
+            for nm, p, st in rows:
+                fh.write("%s\t%d\t%s\tm6A\n" % (nm, p, st))
+    site_maps = None
+    if case.get("meth"):
+        site_maps = {}
+        for ci, (nm, ln) in enumerate(spec.contigs):
+            seq = genomes[ci].tobytes().decode()
+            fwd, rev = refmark.mark_reference(seq, base, motif=case.get("motif"), positions_file=paths.get("positions"), contig=nm)
+            site_maps[ci] = (synth.meth_sites(spec, ci, refmark.site_bitmap(fwd)),
+                             synth.meth_sites(spec, ci, refmark.site_bitmap(rev)))
+    tsv, fasta, fastq, _ = synth.generate(spec, site_maps)
+    if case.get("post"):
+        lines = tsv.decode().split("\n")
+        if lines and lines[-1] == "":
+            lines.pop()
+        lines = POSTS[case["post"]](lines, spec.seed + 77)
+        tsv = ("\n".join(lines) + "\n").encode()
+    with open(paths["tsv"], "wb") as fh:
+        fh.write(tsv)
+    with open(paths["fasta"], "w") as fh:
+        fh.write(fasta)
+    with open(paths["fastq"], "w") as fh:
+        fh.write(fastq)
+    return paths
+
+
+def cli_args(case, inputs):
+    """Argument vector of the reference CLI (mCaller.py:122-141) for this case."""
+    a = []
+    if case.get("positions"):
+        a += ["-p", inputs["positions"]]
+    else:
+        a += ["-m", case["motif"]]
+    a += ["-r", inputs["fasta"], "-e", inputs["tsv"], "-f", inputs["fastq"], "-d", inputs["model"],
+          "-b", case.get("base", "A"), "-n", str(case.get("k", 6))]
+    if case.get("s"):
+        a += ["-s", str(case["s"])]
+    if case.get("q"):
+        a += ["-q", str(case["q"])]
+    return a
