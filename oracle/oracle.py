@@ -1,0 +1,316 @@
+"""ctypes front-end of the CPU oracle (oracle/mcaller_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  It restates, on the CPU, what the reference's `extract_features`
+(extract_contexts.py:110-304) and `aggregate_by_pos` (make_bed.py:67-164) compute, and renders
+the same text rows, so outputs can be compared byte for byte with the golden vectors.
+
+Independent of the product package on purpose: it has its own FASTA/FASTQ readers, reference
+marking, model export and row formatting.
+"""
+import ctypes as C
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libmcoracle.so")
+MAXK = 16
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "mcaller_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-B"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class _Contig(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("fwd", C.c_char_p), ("rev", C.c_char_p), ("len", C.c_int64)]
+
+
+class _Qual(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("qual", C.c_double)]
+
+
+class _Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_in", C.c_int32), ("n_layers", C.c_int32), ("sizes", C.c_int32 * 8),
+                ("hidden_act", C.c_int32), ("weights", C.c_void_p), ("biases", C.c_void_p),
+                ("n_trees", C.c_int32), ("tree_off", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
+                ("feature", C.c_void_p), ("threshold", C.c_void_p), ("leaf_p1", C.c_void_p)]
+
+
+class _Call(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("chrom_cid", C.c_int32), ("win_cid", C.c_int32), ("rev", C.c_int32),
+                ("read_off", C.c_int64), ("read_len", C.c_int32), ("mpos", C.c_int32), ("n_empty", C.c_int32),
+                ("empty_mask", C.c_uint32), ("model_sel", C.c_int32), ("label", C.c_int32),
+                ("feat", C.c_double * (MAXK + 1)), ("prob", C.c_double), ("context", C.c_char * (2 * MAXK))]
+
+
+class _Locus(C.Structure):
+    _fields_ = [("key_off", C.c_int64 * 5), ("key_len", C.c_int32 * 5), ("depth", C.c_int64), ("meth", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_extract.restype = C.c_int64
+        _lib.orc_aggregate.restype = C.c_int64
+        _lib.orc_predict.restype = C.c_double
+        _lib.orc_np_mean.restype = C.c_double
+        _lib.orc_np_round.restype = C.c_double
+        _lib.orc_np_round.argtypes = [C.c_double, C.c_int]
+        assert _lib.orc_sizeof_call() == C.sizeof(_Call), (_lib.orc_sizeof_call(), C.sizeof(_Call))
+        assert _lib.orc_sizeof_locus() == C.sizeof(_Locus)
+    return _lib
+
+
+# ---- inputs -------------------------------------------------------------------------------------
+
+def read_fasta(path):
+    seqs, name, parts = {}, None, []
+    for ln in open(path):
+        if ln[:1] == ">":
+            if name is not None:
+                seqs[name] = "".join(parts).upper()
+            t = ln[1:].split()
+            name, parts = (t[0] if t else ""), []
+        elif name is not None:
+            parts.append(ln.strip())
+    if name is not None:
+        seqs[name] = "".join(parts).upper()
+    return seqs
+
+
+def read_fastq_quals(path):
+    """read_qual.py:6-19: {id.split(':')[0].split('_')[0]: mean phred}."""
+    import gzip
+    op = gzip.open if path.find(".gz") != -1 else open
+    out = {}
+    with op(path, "rt") as fh:
+        while True:
+            h = fh.readline()
+            if not h:
+                break
+            if not h.strip():
+                continue
+            fh.readline()
+            fh.readline()
+            q = fh.readline().rstrip("\n")
+            toks = h[1:].split()
+            rid = (toks[0] if toks else "").split(":")[0].split("_")[0]
+            out[rid] = float(np.mean([ord(c) - 33 for c in q]))
+    return out
+
+
+_CB = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N", "M": "M"}
+
+
+def _rc(s):
+    return "".join(_CB[c] for c in reversed(s))
+
+
+def mark(seq, base, motif=None, positions=None, contig=None):
+    """extract_contexts.py:33-73 in plain Python string operations."""
+    if not positions and motif:
+        f = seq.replace(motif, "M".join(motif.split(base)))
+        rm = _rc(motif)
+        r = seq.replace(rm, "M".join(rm.split(_CB[base])))
+        return f, r
+    rows = [x.split() for x in open(positions).read().split("\n")]
+    outs = []
+    for st, b in (("+", base), ("-", _CB[base])):
+        buf = list(seq)
+        for x in rows:
+            if len(x) > 1 and x[2] == st and x[0] == contig:
+                p = int(x[1])
+                if buf[p] != b and buf[p] != "M":
+                    raise ValueError("Base %d does not correspond to methylated base" % p)
+                buf[p] = "M"
+        outs.append("".join(buf))
+    return outs[0], outs[1]
+
+
+class _Aliasing(pickle.Unpickler):
+    _MAP = {"sklearn.neural_network.multilayer_perceptron": "sklearn.neural_network._multilayer_perceptron",
+            "sklearn.preprocessing.label": "sklearn.preprocessing._label",
+            "sklearn.ensemble.forest": "sklearn.ensemble._forest", "sklearn.tree.tree": "sklearn.tree._classes",
+            "sklearn.linear_model.logistic": "sklearn.linear_model._logistic"}
+
+    def find_class(self, module, name):
+        return super().find_class(self._MAP.get(module, module), name)
+
+
+def load_pickle(path):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with open(path, "rb") as fh:
+            return _Aliasing(fh, encoding="latin").load()
+
+
+_ACT = {"identity": 0, "logistic": 1, "tanh": 2, "relu": 3}
+
+
+def export_model(est):
+    """sklearn estimator -> (_Model, keepalive list)."""
+    m = _Model()
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    tn = type(est).__name__
+    if tn == "MLPClassifier":
+        m.kind = 0
+        sizes = [est.coefs_[0].shape[0]] + [c.shape[1] for c in est.coefs_]
+        assert sizes[-1] == 1 and est.out_activation_ == "logistic" and len(sizes) <= 8
+        m.n_in, m.n_layers = sizes[0], len(est.coefs_)
+        for i, s in enumerate(sizes):
+            m.sizes[i] = s
+        m.hidden_act = _ACT[est.activation]
+        m.weights = arr(np.concatenate([c.ravel() for c in est.coefs_]), np.float64)
+        m.biases = arr(np.concatenate([b.ravel() for b in est.intercepts_]), np.float64)
+    elif tn == "LogisticRegression":
+        m.kind, m.n_in = 1, est.coef_.shape[1]
+        m.weights, m.biases = arr(est.coef_.ravel(), np.float64), arr(est.intercept_.ravel(), np.float64)
+    elif tn == "GaussianNB":
+        m.kind, m.n_in = 2, est.theta_.shape[1]
+        var = est.var_ if hasattr(est, "var_") else est.sigma_
+        m.weights = arr(np.concatenate([est.theta_.ravel(), var.ravel()]), np.float64)
+        m.biases = arr(np.log(est.class_prior_), np.float64)
+    elif tn == "RandomForestClassifier":
+        m.kind, m.n_in, m.n_trees = 3, est.n_features_in_, len(est.estimators_)
+        off, L, R, F, T, P = [0], [], [], [], [], []
+        for t in est.estimators_:
+            tr = t.tree_
+            L.append(tr.children_left); R.append(tr.children_right); F.append(np.maximum(tr.feature, 0)); T.append(tr.threshold)
+            v = tr.value[:, 0, :]
+            P.append(v[:, 1] / v.sum(axis=1))
+            off.append(off[-1] + tr.node_count)
+        m.tree_off = arr(off, np.int32)
+        m.left, m.right, m.feature = arr(np.concatenate(L), np.int32), arr(np.concatenate(R), np.int32), arr(np.concatenate(F), np.int32)
+        m.threshold, m.leaf_p1 = arr(np.concatenate(T), np.float64), arr(np.concatenate(P), np.float64)
+    else:
+        raise TypeError("unsupported estimator " + tn)
+    return m, keep
+
+
+def predict(est, X):
+    m, keep = export_model(est)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    return np.array([lib().orc_predict(C.byref(m), X[i].ctypes.data_as(C.c_void_p)) for i in range(len(X))])
+
+
+# ---- extract_features ---------------------------------------------------------------------------------
+
+ERRORS = {-2: "output capacity", -3: "KeyError: read not in fastq", -4: "ValueError: numeric field", -5: "context / reference end",
+          -6: "KeyError: model key", -7: "n diffs off"}
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def fmt_float(x):
+    """str(np.float64(x)) -- shortest round-trip repr."""
+    return repr(float(x))
+
+
+def fmt_prob(p):
+    """str(np.round(p, 2)) (extract_contexts.py:207)."""
+    return repr(float(lib().orc_np_round(float(p), 2)))
+
+
+def extract(tsv_bytes, fasta, quals, k=6, skip_thresh=0, qual_thresh=0.0, model=None, base="A", motif=None,
+            positions=None, cap=None):
+    """Run the restated extract_features over a whole TSV (== reference with -t 1).
+
+    Returns dict(rows=[str...], calls=[...], counters={...}) where rows are the `.diffs.<k>` lines.
+    `model`: unpickled object (dict or bare estimator) or None (features only).
+    """
+    L = lib()
+    seqs = read_fasta(fasta) if isinstance(fasta, str) else fasta
+    names = list(seqs)
+    carr = (_Contig * len(names))()
+    keep = []
+    for i, nm in enumerate(names):
+        f, r = mark(seqs[nm], base, motif=motif, positions=positions, contig=nm)
+        fb, rb, nb = f.encode(), r.encode(), nm.encode()
+        keep += [fb, rb, nb]
+        carr[i].name, carr[i].fwd, carr[i].rev, carr[i].len = nb, fb, rb, len(fb)
+    qitems = sorted((kk.encode(), float(v)) for kk, v in quals.items())
+    qarr = (_Qual * max(len(qitems), 1))()
+    for i, (kk, v) in enumerate(qitems):
+        qarr[i].key, qarr[i].qual = kk, v
+    marr = (_Model * 2)()
+    two = 0
+    label_mod = "m6A" if base == "A" else "m" + base
+    if model is not None:
+        if isinstance(model, dict):
+            if base == "A":
+                m0, k0 = export_model(model["MH"]); m1, k1 = export_model(model["MG"]); two = 1
+                marr[0], marr[1] = m0, m1
+                keep += k0 + k1
+            else:
+                m0, k0 = export_model(model["general"]); marr[0] = m0; keep += k0
+        else:
+            m0, k0 = export_model(model); marr[0] = m0; keep += k0
+    cap = cap or max(1024, len(tsv_bytes) // 64)
+    calls = (_Call * cap)()
+    n = L.orc_extract(C.c_char_p(tsv_bytes), C.c_int64(len(tsv_bytes)), carr, C.c_int32(len(names)), qarr, C.c_int64(len(qitems)),
+                      C.c_int32(k), C.c_int32(skip_thresh), C.c_double(qual_thresh), marr, C.c_int32(two),
+                      C.c_int32(1 if model is not None else 0), calls, C.c_int64(cap))
+    if n < 0:
+        raise OracleError(ERRORS.get(n, str(n)))
+    rows, recs = [], []
+    pos_set, multi, wskips, toomany = set(), set(), set(), set()
+    for i in range(n):
+        c = calls[i]
+        read = tsv_bytes[c.read_off:c.read_off + c.read_len].decode()
+        if c.kind == 1:
+            toomany.add((read, c.mpos)); continue
+        if c.kind == 2:
+            multi.add((read, c.mpos)); continue
+        feats = ["0" if (c.empty_mask >> j) & 1 else fmt_float(c.feat[j]) for j in range(k)] + [fmt_float(c.feat[k])]
+        st = "-" if c.rev else "+"
+        row = [names[c.chrom_cid], read, str(c.mpos), c.context.decode(), ",".join(feats), st]
+        if model is not None:
+            row += [label_mod if c.label else base, fmt_prob(c.prob)]
+        rows.append("\t".join(row))
+        recs.append(dict(chrom=names[c.chrom_cid], win_contig=names[c.win_cid], read=read, mpos=c.mpos, rev=bool(c.rev),
+                         context=c.context.decode(), feat=[c.feat[j] for j in range(k + 1)], empty_mask=c.empty_mask,
+                         prob=c.prob, label=c.label, model_sel=c.model_sel, n_empty=c.n_empty))
+        pos_set.add(c.mpos)
+        if c.n_empty > 0:
+            wskips.add((read, c.mpos))
+    return dict(rows=rows, calls=recs, counters=dict(observations=len(rows), positions=len(pos_set), multi=len(multi),
+                                                     with_skips=len(wskips), too_many_skips=len(toomany)))
+
+
+def aggregate(diffs_text, depth_thresh=15, mod_thresh=0.5, control=False):
+    """make_bed.py aggregate_by_pos default mode -> list of BED row strings (first-seen order)."""
+    L = lib()
+    b = diffs_text.encode() if isinstance(diffs_text, str) else diffs_text
+    cap = b.count(b"\n") + 2
+    loci = (_Locus * cap)()
+    n = L.orc_aggregate(C.c_char_p(b), C.c_int64(len(b)), loci, C.c_int64(cap))
+    if n < 0:
+        raise OracleError("malformed diffs row")
+    out = []
+    for i in range(n):
+        lc = loci[i]
+        key = [b[lc.key_off[j]:lc.key_off[j] + lc.key_len[j]].decode() for j in range(4)]
+        frac = lc.meth / lc.depth          # np.mean of a 0/1 list: exact integer sum / n
+        if lc.depth >= depth_thresh and ((not control and frac >= mod_thresh) or (control and frac < mod_thresh)):
+            out.append("\t".join([key[0], key[1], str(int(key[1]) + 1), key[2], repr(float(frac)), key[3], str(lc.depth)]))
+    return out
