@@ -1,0 +1,280 @@
+/*
+ * mcaller_b200.h -- C ABI of libmcaller_b200.so: the B200-native (sm_100a) implementation of
+ * mCaller's data-parallel hot path.
+ *
+ * The reference (al-mcintyre/mCaller) is pure Python and exposes no FFI; its boundary for this
+ * path is the Python function extract_features() (extract_contexts.py:110) called from
+ * mCaller.py:53/58/60, and aggregate_by_pos() (make_bed.py:67) called from make_bed.py:200.
+ * The replacement modules mcaller_b200/extract_contexts.py and mcaller_b200/make_bed.py keep
+ * those signatures and drive the entry points below through ctypes (see INTEGRATION.md for
+ * the binding a maintainer would add).  Each entry point names the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MC_E* code otherwise; the text of the last
+ *     error of the calling thread is available from mc_last_error();
+ *   - all pointers named d_* are DEVICE pointers owned by the caller (the host side allocates
+ *     them as torch tensors); the library never allocates device memory and keeps no state;
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*); the only host
+ *     synchronisation is mc_read_u64();
+ *   - no torch / C++ types cross this boundary.
+ */
+#ifndef MCALLER_B200_H
+#define MCALLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+/* text tiles: one CTA tokenises MC_TILE_BYTES of TSV; the caller must keep MC_TEXT_PAD readable bytes,
+ * all '\n', after the last text byte (so a final line without newline and tile look-ahead are safe). */
+#define MC_TILE_BYTES 16384
+#define MC_TEXT_PAD 4096
+#define MC_MAXK 8            /* largest -n/--num_variables supported (reference default 6) */
+
+enum {
+    MC_OK = 0,
+    MC_EINVAL = -1,      /* bad argument */
+    MC_ECUDA = -2,       /* CUDA runtime error (see mc_last_error) */
+    MC_ECAPACITY = -3    /* an output buffer is too small */
+};
+
+/* ---- device-resident reference index (built once per run by the host from the marked reference,
+ *      replaces the per-contig meth_fwd/meth_rev strings of extract_contexts.py:154-160) --------------- */
+typedef struct mc_refindex {
+    int32_t n_contigs;
+    int32_t k;                     /* -n */
+    const uint8_t *d_names;        /* concatenated contig ids */
+    const int32_t *d_name_off;     /* [n_contigs+1] offsets into d_names */
+    const int64_t *d_base;         /* [n_contigs] first global coordinate of the contig (multiple of 64) */
+    const int32_t *d_len;          /* [n_contigs] contig length */
+    const uint32_t *d_site_fwd;    /* bit g: forward-strand copy holds 'M' at global coordinate g */
+    const uint32_t *d_site_rev;    /* same for the reverse-strand copy (forward coordinates) */
+    const uint32_t *d_cand;        /* bit g: some 'M' (either strand) inside [g, g+k) */
+    const uint32_t *d_rank_fwd;    /* per 32-bit word: number of forward sites before the word */
+    const uint32_t *d_rank_rev;    /* same for reverse sites, offset by the total number of forward sites */
+    const uint8_t *d_bases;        /* reference letters at global coordinates (upper case) */
+    int64_t total_bits;            /* size of the global coordinate space (multiple of 64) */
+} mc_refindex;
+
+/* ---- stage 1 output: one record per TSV line that can open, feed or close a window ------------------- */
+typedef struct mc_record {
+    uint32_t line_lo;      /* byte offset of the line inside the chunk, low 32 bits */
+    uint16_t line_hi;      /* high 16 bits */
+    uint16_t name_off;     /* offset of the read-name field (column 4) from the line start */
+    int32_t pos;           /* column 2, reference position */
+    int32_t event_idx;     /* column 6 */
+    double diff;           /* np.round(float(col7) - float(col11), 4), extract_contexts.py:286 */
+    uint16_t name_len;
+    uint16_t contig;       /* contig index */
+    uint8_t flags;         /* MC_RF_* */
+    uint8_t pad[3];
+} mc_record;               /* 32 bytes */
+
+#define MC_RF_EQ 1u        /* reference_kmer (col 3) == model_kmer (col 10) */
+#define MC_RF_CAND 2u      /* k-mer window touches a target on either strand */
+#define MC_RF_BADNUM 4u    /* event/model mean not a plain decimal (<= 18 digits) */
+#define MC_RF_BADIDX 8u    /* event index not a plain integer */
+
+/* counters written by mc_scan (uint64 each) */
+enum {
+    MC_C_LINES = 0,        /* lines owned by the scanned range */
+    MC_C_KEPT,             /* >= 12 fields, known contig, model_kmer != NNNNNN */
+    MC_C_RECORDS,          /* records appended (allocation cursor) */
+    MC_C_SHORT,            /* lines with < 12 whitespace separated fields (:149-152) */
+    MC_C_UNKNOWN_CONTIG,   /* contig not in the reference (:154-160) */
+    MC_C_NNN,              /* model_kmer == 'NNNNNN' (:167) */
+    MC_C_BADPOS,           /* column 2 not a non-negative integer on a known contig (reference: ValueError) */
+    MC_C_LONGLINE,         /* first 12 fields do not fit the tile look-ahead */
+    MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
+    MC_C_COUNT = 16
+};
+
+/* ---- stage 5 output: one row per closed window ----------------------------------------------------- */
+typedef struct mc_call {
+    int64_t read_off;      /* read name: byte offset inside the chunk ... */
+    double prob;           /* P(methylated), filled by mc_classify */
+    double feat[MC_MAXK + 1];   /* k column means in output order (5'->3' on the read strand) + read quality */
+    int32_t read_len;      /* ... and length */
+    int32_t mpos;          /* target position (column 3 of the .diffs row) */
+    int32_t site;          /* dense site slot (forward sites first, then reverse) for the histogram */
+    uint32_t close_rec;    /* ordered index of the record that closed the window; 0xFFFFFFFF = still open at the end of the chunk */
+    uint16_t win_contig;   /* contig of the window (context is cut from its marked copy, :194) */
+    uint16_t chrom_contig; /* contig of the closing line (column 1, :216); 0xFFFF while pending */
+    uint8_t kind;          /* MC_CALL / MC_TOO_MANY_SKIPS / MC_MULTI_M */
+    uint8_t rev;           /* strand: 1 = '-' */
+    uint8_t n_empty;       /* empty columns (skips) */
+    uint8_t empty_mask;    /* bit c: output feature c is an empty column (printed as integer 0) */
+    uint8_t model_sel;     /* 0 = 'MH' / 'general', 1 = 'MG' (base_models, :99-106) */
+    uint8_t label;         /* prob >= 0.5 */
+    uint8_t err;           /* MC_CE_* */
+    uint8_t pad0;
+    uint32_t seg;          /* read segment index inside the chunk */
+    uint32_t pad1;
+    uint32_t pad2;
+} mc_call;                 /* 128 bytes */
+
+enum { MC_CALL = 0, MC_TOO_MANY_SKIPS = 1, MC_MULTI_M = 2 };
+#define MC_CE_CONTEXT 1u   /* window within k of a contig end (reference: IndexError / sys.exit, :195, :224) */
+#define MC_CE_MODELKEY 2u  /* base after the target not in ACGTM (reference: KeyError -> sys.exit, :218-223) */
+#define MC_CE_BADNUM 4u    /* a fed line had an unsupported numeric field */
+#define MC_CE_COLUMN 8u    /* more than 128 events in one column (pairwise-sum block limit) */
+#define MC_CE_SPACING 16u  /* multi-M shift of 0 (reference: 'n diffs off' -> sys.exit, :257-266) */
+
+/* ---- classifier (host struct holding device pointers; layout mirrors sklearn's fitted attributes) ---- */
+enum { MC_MLP = 0, MC_LR = 1, MC_GNB = 2, MC_RF = 3 };
+enum { MC_ACT_IDENTITY = 0, MC_ACT_LOGISTIC = 1, MC_ACT_TANH = 2, MC_ACT_RELU = 3 };
+typedef struct mc_model {
+    int32_t kind;
+    int32_t n_in;
+    int32_t n_layers;          /* MLP: number of weight matrices */
+    int32_t hidden_act;
+    int32_t sizes[8];          /* MLP: layer widths, sizes[0] = n_in ... sizes[n_layers] = 1 */
+    const double *d_weights;   /* MLP: coefs_ concatenated (row-major [in][out]); LR: coef_; GNB: theta_[2][n] then var_[2][n] */
+    const double *d_biases;    /* MLP: intercepts_ concatenated; LR: intercept_; GNB: log class_prior_[2] */
+    int32_t n_trees;           /* RF */
+    int32_t max_nodes;         /* RF: largest tree (for shared-memory staging) */
+    const int32_t *d_tree_off; /* [n_trees+1] */
+    const int32_t *d_left;     /* child index inside the tree, -1 = leaf */
+    const int32_t *d_right;
+    const int32_t *d_feature;
+    const double *d_threshold;
+    const double *d_leaf_p1;   /* class-1 fraction of the node's value */
+} mc_model;
+
+/* read-quality table entry (open addressing, power-of-two size, key = FNV-1a of the read-name prefix) */
+typedef struct mc_qual_entry {
+    uint64_t hash;             /* 0 = empty slot */
+    uint32_t check;            /* second hash (different basis), guards against 64-bit collisions */
+    uint32_t len;              /* prefix length */
+    double qual;               /* mean phred (read_qual.py:13) */
+} mc_qual_entry;
+
+/* ---------------------------------------------------------------------------------------------------- */
+
+int mc_version(void);
+/* sizeof of the ABI structs: 0 mc_record, 1 mc_call, 2 mc_refindex, 3 mc_model, 4 mc_qual_entry, 5 mc_synth_spec, 6 mc_locus_entry */
+int mc_sizeof(int what);
+const char *mc_last_error(void);
+
+/* copy n uint64 from device to host and synchronise the stream */
+int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream);
+
+/*
+ * Stage 1 -- tokenise + filter.  Replaces the reader/tokeniser and the per-line filters of
+ * extract_contexts.py:140-176 (readlines, line.split()[:12], contig lookup, NNNNNN filter, k-mer
+ * 'has M' test).  One CTA per MC_TILE_BYTES tile; a line belongs to the tile holding its first byte.
+ * Emits a record for every kept line that is a candidate (k-mer window touches a target on either
+ * strand), that follows a candidate, or that is the first kept line of its tile; with dense != 0 for
+ * every kept line (needed with -q).  Records of one tile are contiguous and in line order; tiles
+ * allocate from d_counters[MC_C_RECORDS]; d_tile_tab[tile] = {first record, count}.
+ * d_counters (MC_C_COUNT uint64) must be zeroed by the caller.
+ */
+int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,
+            mc_record *d_rec, int64_t rec_cap, uint32_t *d_tile_tab /* [2*n_tiles] */,
+            uint64_t *d_counters, void *stream);
+
+/* number of tiles mc_scan uses for nbytes */
+int64_t mc_num_tiles(int64_t nbytes);
+
+/* bytes of scratch needed by the scan-based stages below for up to n items */
+int64_t mc_workspace_bytes(int64_t n);
+
+/* Stage 2 -- put the records into file order (exclusive scan of the tile table + gather). */
+int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t n_records,
+                     mc_record *d_rec_out, void *d_ws, void *stream);
+
+/*
+ * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the
+ * previous record's (extract_contexts.py:161, `read_name != last_read`).  Writes the first record index of
+ * each segment to d_seg_start (capacity n_records+1, terminated by n_records) and the segment count to
+ * d_nseg[0].
+ */
+int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, int64_t n_records,
+                     uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream);
+
+/*
+ * Stage 4 -- read quality per segment: read2qual[name] else read2qual[name.split(':')[0].split('_')[0]]
+ * (extract_contexts.py:163-166, read_qual.py:6-19).  Missing reads get NaN and are counted in d_err[0]
+ * (the reference raises KeyError).
+ */
+int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, int64_t n_seg,
+                       const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual, uint64_t *d_err, void *stream);
+
+/*
+ * Stage 5 -- window builder: the state machine of extract_contexts.py:169-291 (strand inference, window
+ * open/feed/close, skip filter, multi-M carry, orientation flip, np.mean of np.round(ev-model,4) per column in
+ * numpy's summation order) run per read segment.  Two passes (count, exclusive scan, write) so rows come out in
+ * file order.  d_ncalls[0] receives the number of rows (all kinds); rows beyond call_cap are dropped and
+ * d_ncalls[1] is set.  Segments whose quality is below qual_thresh are skipped entirely (:167).
+ */
+int mc_build_windows(const mc_record *d_rec, int64_t n_records, const uint32_t *d_seg_start, int64_t n_seg,
+                     const double *d_seg_qual, const mc_refindex *ref, int skip_thresh, double qual_thresh, int two_models,
+                     mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count, uint64_t *d_ncalls, void *d_ws, void *stream);
+
+/*
+ * Stage 6 -- classifier: model[key].predict_proba([x])[0][1] and the 0.5 label threshold
+ * (extract_contexts.py:195-207) for every MC_CALL row; float64 arithmetic.  models[0] = 'MH'/'general',
+ * models[1] = 'MG' (only read when a row has model_sel == 1).
+ */
+int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void *stream);
+
+/*
+ * Stage 7 -- per-position aggregation (make_bed.py:86-96): depth and methylated counts per site slot, plus the
+ * smallest global row index that touched the slot (first-seen order of make_bed.py:134).  d_depth/d_meth are
+ * uint32[n_sites], d_first uint64[n_sites] (initialise to ~0); row_base is added to the row index (chunk / rank
+ * offset).  Rows whose closing contig differs from the window contig (reference quirk, :216) or that are pending
+ * are skipped and counted in d_skipped[0]; the host handles them.
+ */
+int mc_hist_accumulate(const mc_call *d_calls, int64_t n_calls, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first,
+                       int64_t n_sites, uint64_t row_base, uint64_t *d_skipped, void *stream);
+
+/*
+ * make_bed drop-in: aggregate a `.diffs.<k>` text file (make_bed.py:75-98, default mode).  d_table is an open-addressing
+ * table (power-of-two entries; hash == 0 means empty, first_off must be initialised to ~0) keyed by the FNV-1a hash of
+ * "chrom\tpos\tcontext\tstrand"; first_off is the smallest byte offset of a row with that key (first-seen order, :134).
+ * d_counters[4]: rows, malformed rows (field count not 7/8), rows skipped by the centre-'M' test (:84), table-full drops.
+ */
+typedef struct mc_locus_entry {
+    unsigned long long hash;
+    unsigned long long first_off;
+    uint32_t depth;
+    uint32_t meth;
+} mc_locus_entry;
+int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_table, int64_t table_size,
+                       uint64_t *d_counters, void *stream);
+
+/* ---- synthetic eventalign generator (bench / test tooling; bit-identical to mcaller_b200/synth.py) ---- */
+typedef struct mc_synth_spec {
+    uint64_t seed;
+    int32_t n_contigs;
+    int32_t len_min, len_max, p_skip, p_nnn, margin;
+    int32_t meth;                  /* add METH_OFFSETS at methylated sites */
+    const uint8_t *d_names;        /* contig ids, concatenated */
+    const int32_t *d_name_off;     /* [n_contigs+1] */
+    const int32_t *d_contig_len;   /* [n_contigs] */
+    const int64_t *d_read_bounds;  /* [n_contigs+1] read index ranges per contig */
+    const int64_t *d_gbase;        /* [n_contigs] global coordinate base (as in mc_refindex) */
+    const uint8_t *d_genome;       /* letters at global coordinates */
+    const uint32_t *d_meth_fwd;    /* methylated-site bitmaps (global coordinates), may be NULL when !meth */
+    const uint32_t *d_meth_rev;
+    const int32_t *d_model_mean;   /* [4096] centi-pA */
+    const int32_t *d_model_sd;     /* [4096] */
+} mc_synth_spec;
+
+/* genome letters for all contigs (global coordinates) */
+int mc_synth_genome(const mc_synth_spec *spec, uint8_t *d_genome_out, int64_t total_bits, void *stream);
+/* pass 1: bytes of TSV text of reads [read0, read0+n) -> d_sizes[n] */
+int mc_synth_sizes(const mc_synth_spec *spec, int64_t read0, int64_t n, int64_t n_total_reads, uint64_t *d_sizes, void *stream);
+/* pass 2: write the text of each read at d_offsets[i] (exclusive scan of the sizes) */
+int mc_synth_write(const mc_synth_spec *spec, int64_t read0, int64_t n, int64_t n_total_reads, const uint64_t *d_offsets,
+                   uint8_t *d_text, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

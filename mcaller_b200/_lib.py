@@ -1,0 +1,121 @@
+"""ctypes binding of libmcaller_b200.so (C ABI in include/mcaller_b200.h).
+
+There is no CPU fallback: importing this module's `lib()` without the built library, or calling
+into it without a CUDA device, raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcaller_b200.so")
+
+MC_TILE_BYTES = 16384
+MC_TEXT_PAD = 4096
+MC_MAXK = 8
+MC_C_COUNT = 16
+COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow"]
+
+MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M = 0, 1, 2
+MC_CE_CONTEXT, MC_CE_MODELKEY, MC_CE_BADNUM, MC_CE_COLUMN, MC_CE_SPACING = 1, 2, 4, 8, 16
+MC_MLP, MC_LR, MC_GNB, MC_RF = 0, 1, 2, 3
+PENDING = 0xFFFFFFFF
+
+
+class RefIndex(C.Structure):
+    _fields_ = [("n_contigs", C.c_int32), ("k", C.c_int32), ("d_names", C.c_void_p), ("d_name_off", C.c_void_p),
+                ("d_base", C.c_void_p), ("d_len", C.c_void_p), ("d_site_fwd", C.c_void_p), ("d_site_rev", C.c_void_p),
+                ("d_cand", C.c_void_p), ("d_rank_fwd", C.c_void_p), ("d_rank_rev", C.c_void_p), ("d_bases", C.c_void_p),
+                ("total_bits", C.c_int64)]
+
+
+class Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_in", C.c_int32), ("n_layers", C.c_int32), ("hidden_act", C.c_int32),
+                ("sizes", C.c_int32 * 8), ("d_weights", C.c_void_p), ("d_biases", C.c_void_p), ("n_trees", C.c_int32),
+                ("max_nodes", C.c_int32), ("d_tree_off", C.c_void_p), ("d_left", C.c_void_p), ("d_right", C.c_void_p),
+                ("d_feature", C.c_void_p), ("d_threshold", C.c_void_p), ("d_leaf_p1", C.c_void_p)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_contigs", C.c_int32), ("len_min", C.c_int32), ("len_max", C.c_int32),
+                ("p_skip", C.c_int32), ("p_nnn", C.c_int32), ("margin", C.c_int32), ("meth", C.c_int32),
+                ("d_names", C.c_void_p), ("d_name_off", C.c_void_p), ("d_contig_len", C.c_void_p),
+                ("d_read_bounds", C.c_void_p), ("d_gbase", C.c_void_p), ("d_genome", C.c_void_p),
+                ("d_meth_fwd", C.c_void_p), ("d_meth_rev", C.c_void_p), ("d_model_mean", C.c_void_p),
+                ("d_model_sd", C.c_void_p)]
+
+
+RECORD_DTYPE = np.dtype([("line_lo", "<u4"), ("line_hi", "<u2"), ("name_off", "<u2"), ("pos", "<i4"), ("event_idx", "<i4"),
+                         ("diff", "<f8"), ("name_len", "<u2"), ("contig", "<u2"), ("flags", "u1"), ("pad", "u1", (3,))])
+assert RECORD_DTYPE.itemsize == 32
+
+CALL_DTYPE = np.dtype([("read_off", "<i8"), ("prob", "<f8"), ("feat", "<f8", (MC_MAXK + 1,)), ("read_len", "<i4"),
+                       ("mpos", "<i4"), ("site", "<i4"), ("close_rec", "<u4"), ("win_contig", "<u2"), ("chrom_contig", "<u2"),
+                       ("kind", "u1"), ("rev", "u1"), ("n_empty", "u1"), ("empty_mask", "u1"), ("model_sel", "u1"),
+                       ("label", "u1"), ("err", "u1"), ("pad0", "u1"), ("seg", "<u4"), ("pad1", "<u4"), ("pad2", "<u4")])
+assert CALL_DTYPE.itemsize == 128
+
+class LocusEntry(C.Structure):
+    _fields_ = [("hash", C.c_uint64), ("first_off", C.c_uint64), ("depth", C.c_uint32), ("meth", C.c_uint32)]
+
+
+QUAL_DTYPE = np.dtype([("hash", "<u8"), ("check", "<u4"), ("len", "<u4"), ("qual", "<f8")])
+assert QUAL_DTYPE.itemsize == 24
+
+
+class McallerCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_PROTOS = {
+    "mc_version": (C.c_int, []),
+    "mc_sizeof": (C.c_int, [C.c_int]),
+    "mc_last_error": (C.c_char_p, []),
+    "mc_read_u64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mc_scan": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RefIndex), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_num_tiles": (C.c_int64, [C.c_int64]),
+    "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_build_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RefIndex), C.c_int, C.c_double,
+                                   C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_classify": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Model), C.c_void_p]),
+    "mc_hist_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mc_synth_genome": (C.c_int, [C.POINTER(SynthSpec), C.c_void_p, C.c_int64, C.c_void_p]),
+    "mc_synth_sizes": (C.c_int, [C.POINTER(SynthSpec), C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mc_synth_write": (C.c_int, [C.POINTER(SynthSpec), C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_diffs_aggregate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+}
+
+# symbols every build must export (checked by the CPU test-suite against include/mcaller_b200.h)
+EXPORTS = sorted(_PROTOS)
+
+
+def load(path=LIB_PATH):
+    """dlopen the library and attach prototypes (no CUDA call is made)."""
+    if not os.path.exists(path):
+        raise McallerCudaError("libmcaller_b200.so is not built (%s); run `python -m mcaller_b200.build` -- there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load()
+        if _lib.mc_version() != 1:
+            raise McallerCudaError("ABI version mismatch")
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise McallerCudaError("libmcaller_b200: rc=%d %s" % (rc, lib().mc_last_error().decode(errors="replace")))

@@ -1,0 +1,228 @@
+// Stage 6 (K3): per-observation classifier -- model[key].predict_proba([x])[0][1] and the 0.5 label threshold of
+// the reference (extract_contexts.py:195-207) for the estimator types mCaller can be run with (-c NN/RF/LR/NBC;
+// the estimator type is whatever the pickle holds, mCaller.py:137).
+//
+// Arithmetic is float64 like scikit-learn's.  The work per call is ~1.6 kFLOP (MLP 7-100-1) and there is one call
+// per ~85 KB of TSV, so this stage is <1 % of the step; the layer widths (K=7, N=100) would leave a tcgen05 tile
+// >90 % padding and bf16/tf32 operands cannot meet the 1e-5 probability tolerance, so the MLP runs on the FP64
+// FMA pipe: one warp per call, lanes over hidden units, weights served from L1/L2 (7 KB per model).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_WIDTH = 512;     // widest MLP layer supported
+constexpr int WARPS = 4;
+
+__device__ __forceinline__ double expit(double x) { return x < 0.0 ? exp(x) / (1.0 + exp(x)) : 1.0 / (1.0 + exp(-x)); }
+
+__device__ __forceinline__ double activate(double v, int act) {
+    switch (act) {
+        case MC_ACT_TANH: return tanh(v);
+        case MC_ACT_LOGISTIC: return expit(v);
+        case MC_ACT_RELU: return v > 0.0 ? v : 0.0;
+        default: return v;
+    }
+}
+
+// sklearn MLPClassifier._forward_pass_fast (neural_network/_multilayer_perceptron.py) for a binary classifier:
+// hidden activations, logistic output, P(class 1) = expit(z)
+__global__ void __launch_bounds__(WARPS * 32)
+k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1) {
+    __shared__ double s_act[WARPS][2][MAX_WIDTH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * WARPS + warp;
+    if (i >= n) return;
+    mc_call &c = calls[i];
+    if (c.kind != MC_CALL) return;
+    const mc_model &m = c.model_sel ? m1 : m0;
+    double *a = s_act[warp][0], *b = s_act[warp][1];
+    if (lane < m.sizes[0]) a[lane] = c.feat[lane];
+    __syncwarp();
+    const double *w = m.d_weights, *bi = m.d_biases;
+    double out = 0.0;
+    for (int l = 0; l < m.n_layers; ++l) {
+        const int ni = m.sizes[l], no = m.sizes[l + 1];
+        const bool last = (l + 1 == m.n_layers);
+        if (no >= 8) {
+            for (int o = lane; o < no; o += 32) {
+                double acc = 0.0;
+                for (int k = 0; k < ni; ++k) acc = fma(a[k], __ldg(w + (size_t)k * no + o), acc);
+                acc += __ldg(bi + o);
+                b[o] = last ? acc : activate(acc, m.hidden_act);
+            }
+        } else {
+            for (int o = 0; o < no; ++o) {
+                double acc = 0.0;
+                for (int k = lane; k < ni; k += 32) acc = fma(a[k], __ldg(w + (size_t)k * no + o), acc);
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                acc += __ldg(bi + o);
+                if (lane == 0) b[o] = last ? acc : activate(acc, m.hidden_act);
+            }
+        }
+        __syncwarp();
+        double *t = a; a = b; b = t;
+        w += (size_t)ni * no;
+        bi += no;
+    }
+    out = expit(a[0]);
+    if (lane == 0) {
+        c.prob = out;
+        c.label = (uint8_t)(out >= 0.5);
+    }
+}
+
+// LogisticRegression.predict_proba (binary): expit(x.w + b); GaussianNB.predict_proba: exp(jll_1 - logsumexp(jll))
+__global__ void __launch_bounds__(256) k_linear(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mc_call &c = calls[i];
+    if (c.kind != MC_CALL) return;
+    const mc_model &m = c.model_sel ? m1 : m0;
+    double p;
+    if (m.kind == MC_LR) {
+        double z = __ldg(m.d_biases);
+        for (int k = 0; k < m.n_in; ++k) z += c.feat[k] * __ldg(m.d_weights + k);
+        p = expit(z);
+    } else {
+        const double *theta = m.d_weights, *var = m.d_weights + 2 * m.n_in;
+        double jll[2];
+        for (int cl = 0; cl < 2; ++cl) {
+            double nij = 0.0, s = 0.0;
+            for (int k = 0; k < m.n_in; ++k) nij += log(2.0 * 3.14159265358979323846 * __ldg(var + cl * m.n_in + k));
+            nij *= -0.5;
+            for (int k = 0; k < m.n_in; ++k) {
+                const double d = c.feat[k] - __ldg(theta + cl * m.n_in + k);
+                s += d * d / __ldg(var + cl * m.n_in + k);
+            }
+            jll[cl] = __ldg(m.d_biases + cl) + nij - 0.5 * s;
+        }
+        const double mx = jll[0] > jll[1] ? jll[0] : jll[1];
+        const double lse = mx + log(exp(jll[0] - mx) + exp(jll[1] - mx));
+        p = exp(jll[1] - lse);
+    }
+    c.prob = p;
+    c.label = (uint8_t)(p >= 0.5);
+}
+
+// RandomForestClassifier.predict_proba: mean over trees of the leaf class-1 fraction; the walk compares float32(x)
+// with the float64 threshold (sklearn tree/_tree.pyx).  A block owns 256 calls and streams the trees through shared
+// memory (node table of one tree at a time), so every node read in the walk is an smem read.
+struct RfNode {
+    double thr;
+    float p1f_unused;
+    int32_t left, right;   // absolute smem node index, -1 = leaf
+    int32_t feature;
+};
+
+__global__ void __launch_bounds__(256)
+k_rf(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int max_nodes) {
+    extern __shared__ __align__(16) uint8_t rf_smem[];
+    double *s_thr = reinterpret_cast<double *>(rf_smem);
+    double *s_p1 = s_thr + max_nodes;
+    int32_t *s_left = reinterpret_cast<int32_t *>(s_p1 + max_nodes);
+    int32_t *s_right = s_left + max_nodes;
+    int32_t *s_feat = s_right + max_nodes;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n && calls[i].kind == MC_CALL;
+    float x[MC_MAXK + 1];
+    int sel = 0;
+    if (active) {
+        sel = calls[i].model_sel;
+        for (int k = 0; k <= MC_MAXK; ++k) x[k] = (float)calls[i].feat[k];
+    }
+    double acc = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const mc_model &m = pass ? m1 : m0;
+        // skip a model nobody in the block uses
+        const int any = __syncthreads_or(active && sel == pass);
+        if (!any || m.n_trees == 0) continue;
+        for (int t = 0; t < m.n_trees; ++t) {
+            const int o0 = __ldg(m.d_tree_off + t), nn = __ldg(m.d_tree_off + t + 1) - o0;
+            __syncthreads();
+            for (int j = threadIdx.x; j < nn; j += blockDim.x) {
+                s_thr[j] = __ldg(m.d_threshold + o0 + j);
+                s_p1[j] = __ldg(m.d_leaf_p1 + o0 + j);
+                s_left[j] = __ldg(m.d_left + o0 + j);
+                s_right[j] = __ldg(m.d_right + o0 + j);
+                s_feat[j] = __ldg(m.d_feature + o0 + j);
+            }
+            __syncthreads();
+            if (active && sel == pass) {
+                int node = 0;
+                while (s_left[node] >= 0) node = ((double)x[s_feat[node]] <= s_thr[node]) ? s_left[node] : s_right[node];
+                acc += s_p1[node];
+            }
+        }
+    }
+    if (active) {
+        const mc_model &m = sel ? m1 : m0;
+        const double p = acc / (double)m.n_trees;
+        calls[i].prob = p;
+        calls[i].label = (uint8_t)(p >= 0.5);
+    }
+}
+
+// ---- stage 7 (K4): per-site histogram (make_bed.py:86-96) ----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_hist(const mc_call *__restrict__ calls, int64_t n, uint32_t *__restrict__ depth, uint32_t *__restrict__ meth,
+       unsigned long long *__restrict__ first, int64_t n_sites, unsigned long long row_base,
+       unsigned long long *__restrict__ d_skipped) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mc_call &c = calls[i];
+    if (c.kind != MC_CALL) return;
+    if (c.close_rec == 0xFFFFFFFFu || c.chrom_contig != c.win_contig || c.site < 0 || c.site >= n_sites || c.err) {
+        atomicAdd(d_skipped, 1ull);
+        return;
+    }
+    atomicAdd(depth + c.site, 1u);
+    if (c.label) atomicAdd(meth + c.site, 1u);
+    atomicMin(first + c.site, row_base + (unsigned long long)i);
+}
+
+}  // namespace
+
+extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void *stream) {
+    MC_REQUIRE(d_calls && models, "null pointer");
+    if (n_calls <= 0) return MC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const mc_model &m0 = models[0], &m1 = models[1];
+    MC_REQUIRE(m0.n_in >= 1 && m0.n_in <= MC_MAXK + 1, "model input width out of range");
+    switch (m0.kind) {
+        case MC_MLP: {
+            MC_REQUIRE(m0.n_layers >= 1 && m0.n_layers < 8, "MLP depth out of range");
+            for (int l = 0; l <= m0.n_layers; ++l) MC_REQUIRE(m0.sizes[l] >= 1 && m0.sizes[l] <= MAX_WIDTH, "MLP layer too wide");
+            MC_REQUIRE(m0.sizes[m0.n_layers] == 1, "MLP must have one logistic output");
+            k_mlp<<<(unsigned)((n_calls + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d_calls, n_calls, m0, m1);
+            break;
+        }
+        case MC_LR:
+        case MC_GNB:
+            k_linear<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(d_calls, n_calls, m0, m1);
+            break;
+        case MC_RF: {
+            int mx = m0.max_nodes > m1.max_nodes ? m0.max_nodes : m1.max_nodes;
+            MC_REQUIRE(mx >= 1, "RF max_nodes missing");
+            const size_t smem = (size_t)mx * (8 + 8 + 4 + 4 + 4);
+            MC_REQUIRE(smem <= 200 * 1024, "RF tree too large for shared-memory staging");
+            MC_CUDA_CHECK(cudaFuncSetAttribute(k_rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_rf<<<(unsigned)((n_calls + 255) / 256), 256, smem, st>>>(d_calls, n_calls, m0, m1, mx);
+            break;
+        }
+        default:
+            MC_REQUIRE(false, "unknown model kind");
+    }
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_hist_accumulate(const mc_call *d_calls, int64_t n_calls, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first,
+                                  int64_t n_sites, uint64_t row_base, uint64_t *d_skipped, void *stream) {
+    MC_REQUIRE(d_calls && d_depth && d_meth && d_first && d_skipped, "null pointer");
+    if (n_calls <= 0) return MC_OK;
+    k_hist<<<(unsigned)((n_calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_calls, n_calls, d_depth, d_meth, reinterpret_cast<unsigned long long *>(d_first), n_sites,
+        (unsigned long long)row_base, reinterpret_cast<unsigned long long *>(d_skipped));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}

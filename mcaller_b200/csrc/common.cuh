@@ -1,0 +1,71 @@
+// Shared helpers for libmcaller_b200 (sm_100a).  Device code only sees plain structs of device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mcaller_b200.h"
+
+void mc_set_error(const char *fmt, ...);
+
+#define MC_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            mc_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return MC_ECUDA;                                                                 \
+        }                                                                                    \
+    } while (0)
+
+#define MC_LAUNCH_CHECK() MC_CUDA_CHECK(cudaGetLastError())
+
+#define MC_REQUIRE(cond, msg)                       \
+    do {                                            \
+        if (!(cond)) {                              \
+            mc_set_error("%s: %s", __func__, msg);  \
+            return MC_EINVAL;                       \
+        }                                           \
+    } while (0)
+
+// ---- k-mer bit window over a site bitmap: bits [g, g+k) of the bitmap, LSB = position g ---------------
+__device__ __forceinline__ uint32_t mc_kmer_bits(const uint32_t *__restrict__ bm, int64_t g, int k) {
+    int64_t w = g >> 5;
+    int b = (int)(g & 31);
+    uint32_t lo = __ldg(bm + w), hi = __ldg(bm + w + 1);
+    uint32_t v = __funnelshift_r(lo, hi, b);
+    return v & ((1u << k) - 1u);
+}
+
+// ---- block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32) -------------
+template <int THREADS>
+__device__ __forceinline__ int mc_block_exscan(int v, int *s_warp /* [THREADS/32 + 1] */, int &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int x = (lane < THREADS / 32) ? s_warp[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) xi += t;
+        }
+        if (lane < THREADS / 32) s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[THREADS / 32] = xi;
+    }
+    __syncthreads();
+    total = s_warp[THREADS / 32];
+    int res = s_warp[wid] + inc - v;
+    __syncthreads();
+    return res;
+}
+
+// generic device exclusive scan (uint32 in -> uint32 out), see scan_util.cu
+int mc_exscan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total /* may be null */, void *d_ws,
+                  cudaStream_t st);
+int64_t mc_exscan_ws_bytes(int64_t n);

@@ -1,0 +1,258 @@
+// Stages 2-4: file-order gather of the stage-1 records, read segmentation, per-read quality lookup,
+// plus the generic exclusive scan they (and the window builder) share.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_IPT;
+
+// ---- generic exclusive scan over uint32 (input may be strided) -----------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ in, int64_t stride, int64_t n,
+                                                            unsigned long long *__restrict__ block_sums) {
+    __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+    unsigned long long acc = 0ull;
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) {
+        const int64_t i = base + (int64_t)j * SCAN_THREADS + threadIdx.x;
+        if (i < n) acc += in[i * stride];
+    }
+    // block reduce (64-bit)
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    __shared__ unsigned long long s_sum[SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0ull;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += s_sum[w];
+        block_sums[blockIdx.x] = t;
+    }
+    (void)s_warp;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long *__restrict__ block_sums, int64_t nb,
+                                                   unsigned long long *__restrict__ d_total) {
+    __shared__ unsigned long long s_w[33];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t c0 = 0; c0 < nb; c0 += 1024) {
+        const int64_t i = c0 + threadIdx.x;
+        const unsigned long long v = (i < nb) ? block_sums[i] : 0ull;
+        unsigned long long inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long x = s_w[lane], xi = x;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, xi, d);
+                if (lane >= d) xi += t;
+            }
+            s_w[lane] = xi - x;
+            if (lane == 31) s_w[32] = xi;
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (i < nb) block_sums[i] = carry + s_w[wid] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && d_total) *d_total = s_carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const uint32_t *__restrict__ in, int64_t stride, int64_t n,
+                                                          const unsigned long long *__restrict__ block_sums,
+                                                          uint32_t *__restrict__ out) {
+    __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    // thread owns SCAN_IPT consecutive items so the scan order is the index order
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_IPT;
+    uint32_t v[SCAN_IPT];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) {
+        const int64_t i = base + j;
+        v[j] = (i < n) ? in[i * stride] : 0u;
+        sum += (int)v[j];
+    }
+    int total;
+    int off = mc_block_exscan<SCAN_THREADS>(sum, s_warp, total);
+    uint32_t run = (uint32_t)block_sums[blockIdx.x] + (uint32_t)off;
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) {
+        const int64_t i = base + j;
+        if (i < n) out[i] = run;
+        run += v[j];
+    }
+}
+
+}  // namespace
+
+int64_t mc_exscan_ws_bytes(int64_t n) { return ((n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 8 + 256; }
+
+static int exscan_strided(const uint32_t *d_in, int64_t stride, uint32_t *d_out, int64_t n, uint64_t *d_total, void *d_ws,
+                          cudaStream_t st) {
+    if (n <= 0) {
+        if (d_total) MC_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 8, st));
+        return MC_OK;
+    }
+    const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(d_ws);
+    k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, sums);
+    MC_LAUNCH_CHECK();
+    k_scan_sums<<<1, 1024, 0, st>>>(sums, nb, reinterpret_cast<unsigned long long *>(d_total));
+    MC_LAUNCH_CHECK();
+    k_scan_down<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, sums, d_out);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+int mc_exscan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total, void *d_ws, cudaStream_t st) {
+    return exscan_strided(d_in, 1, d_out, n, d_total, d_ws, st);
+}
+
+// workspace layout used by the stages: [A: uint32 n][B: uint32 n][scan sums]
+extern "C" int64_t mc_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    const int64_t a = ((n * 4 + 255) / 256) * 256;
+    return 2 * a + mc_exscan_ws_bytes(n) + 256;
+}
+static inline uint32_t *ws_a(void *ws) { return reinterpret_cast<uint32_t *>(ws); }
+static inline uint32_t *ws_b(void *ws, int64_t n) { return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ws) + ((n * 4 + 255) / 256) * 256); }
+static inline void *ws_s(void *ws, int64_t n) { return reinterpret_cast<uint8_t *>(ws) + 2 * (((n * 4 + 255) / 256) * 256); }
+
+namespace {
+
+// ---- stage 2: gather records into file order ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_dst,
+                                               int64_t n_tiles, const mc_record *__restrict__ in, mc_record *__restrict__ out,
+                                               unsigned long long n_records) {
+    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long src = tile_tab[2 * tile], cnt = tile_tab[2 * tile + 1], dst = tile_dst[tile];
+    for (unsigned long long j = lane; j < cnt; j += 32) {
+        if (src + j >= n_records || dst + j >= n_records) break;   // records dropped by a capacity overflow
+        const uint4 *s = reinterpret_cast<const uint4 *>(in + src + j);
+        uint4 *d = reinterpret_cast<uint4 *>(out + dst + j);
+        const uint4 a = s[0], b = s[1];
+        d[0] = a;
+        d[1] = b;
+    }
+}
+
+// ---- stage 3: read segmentation ----------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
+
+__global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n,
+                                                  uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t f = 1u;
+    if (i > 0) {
+        const mc_record a = rec[i - 1], b = rec[i];
+        if (a.name_len == b.name_len) {
+            const uint8_t *pa = text + rec_line(a) + a.name_off, *pb = text + rec_line(b) + b.name_off;
+            int j = 0;
+            const int L = a.name_len;
+            while (j < L && __ldg(pa + j) == __ldg(pb + j)) ++j;
+            f = (j < L) ? 1u : 0u;
+        }
+    }
+    flags[i] = f;
+}
+
+__global__ void __launch_bounds__(256) k_seg_starts(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ excl, int64_t n,
+                                                   uint32_t *__restrict__ seg_start, const unsigned long long *__restrict__ d_nseg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) seg_start[excl[i]] = (uint32_t)i;
+    if (i == 0) seg_start[*d_nseg] = (uint32_t)n;
+}
+
+// ---- stage 4: quality lookup -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec,
+                                                    const uint32_t *__restrict__ seg_start, int64_t n_seg,
+                                                    const mc_qual_entry *__restrict__ table, unsigned long long mask,
+                                                    double *__restrict__ seg_qual, unsigned long long *__restrict__ d_err) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const mc_record r = rec[seg_start[s]];
+    const uint8_t *p = text + rec_line(r) + r.name_off;
+    // key = name.split(':')[0].split('_')[0]   (read_qual.py:11-12 / extract_contexts.py:166)
+    unsigned long long h = 14695981039346656037ull, h2 = 0x84222325cbf29ce4ull;
+    int len = 0;
+    for (; len < r.name_len; ++len) {
+        const unsigned c = __ldg(p + len);
+        if (c == ':' || c == '_') break;
+        h = (h ^ c) * 1099511628211ull;
+        h2 = (h2 ^ c) * 1099511628211ull;
+    }
+    if (h == 0ull) h = 1ull;
+    const uint32_t check = (uint32_t)(h2 >> 32);
+    double q = __longlong_as_double(0x7ff8000000000000ll);   // NaN = missing
+    unsigned long long slot = h & mask;
+    for (unsigned long long probe = 0; probe <= mask; ++probe) {
+        const mc_qual_entry e = table[slot];
+        if (e.hash == 0ull) break;
+        if (e.hash == h && e.check == check && e.len == (uint32_t)len) { q = e.qual; break; }
+        slot = (slot + 1) & mask;
+    }
+    if (q != q) atomicAdd(d_err, 1ull);
+    seg_qual[s] = q;
+}
+
+}  // namespace
+
+extern "C" int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t n_records,
+                                mc_record *d_rec_out, void *d_ws, void *stream) {
+    MC_REQUIRE(d_tile_tab && d_rec_in && d_rec_out && d_ws, "null pointer");
+    if (n_tiles <= 0 || n_records <= 0) return MC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *dst = ws_a(d_ws);
+    int rc = exscan_strided(d_tile_tab + 1, 2, dst, n_tiles, nullptr, ws_s(d_ws, n_tiles), st);
+    if (rc) return rc;
+    k_gather<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(d_tile_tab, dst, n_tiles, d_rec_in, d_rec_out,
+                                                            (unsigned long long)n_records);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, int64_t n_records, uint32_t *d_seg_start,
+                                uint64_t *d_nseg, void *d_ws, void *stream) {
+    MC_REQUIRE(d_text && d_rec && d_seg_start && d_nseg && d_ws, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_records <= 0) {
+        MC_CUDA_CHECK(cudaMemsetAsync(d_nseg, 0, 8, st));
+        MC_CUDA_CHECK(cudaMemsetAsync(d_seg_start, 0, 4, st));
+        return MC_OK;
+    }
+    uint32_t *flags = ws_a(d_ws), *excl = ws_b(d_ws, n_records);
+    const unsigned nb = (unsigned)((n_records + 255) / 256);
+    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, n_records, flags);
+    MC_LAUNCH_CHECK();
+    int rc = mc_exscan_u32(flags, excl, n_records, d_nseg, ws_s(d_ws, n_records), st);
+    if (rc) return rc;
+    k_seg_starts<<<nb, 256, 0, st>>>(flags, excl, n_records, d_seg_start, reinterpret_cast<const unsigned long long *>(d_nseg));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, int64_t n_seg,
+                                  const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual, uint64_t *d_err,
+                                  void *stream) {
+    MC_REQUIRE(d_text && d_rec && d_seg_start && d_table && d_seg_qual && d_err, "null pointer");
+    MC_REQUIRE(table_size > 0 && (table_size & (table_size - 1)) == 0, "table size must be a power of two");
+    if (n_seg <= 0) return MC_OK;
+    k_seg_quality<<<(unsigned)((n_seg + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_text, d_rec, d_seg_start, n_seg, d_table, (unsigned long long)(table_size - 1), d_seg_qual,
+        reinterpret_cast<unsigned long long *>(d_err));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}

@@ -1,0 +1,312 @@
+// Stage 5 (K2): context-window builder -- the state machine of the reference's extract_features
+// (extract_contexts.py:169-291) run per read segment over the stage-1 records.
+//
+// Why this is enough: a kept line whose k-mer holds no 'M' leaves the reference's state machine closed and
+// empty (:242-245 / :289-291), and stage 1 records every line that can hold an 'M' on either strand plus the
+// kept line that follows it (the line that closes an open window, :179).  Unrecorded lines are therefore no-ops
+// and the state machine can run on the records alone.  State never crosses a read boundary except for the one
+// still-open window of the previous read, which the first record of the next read closes (:179, `read_name !=
+// last_read`); that hand-off is resolved here by looking at the first record of the next segment.
+//
+// One thread per read segment, two passes (count rows / write rows) so rows land in file order.  Column sums are
+// accumulated in numpy's pairwise order (8 running lanes + sequential tail) so np.mean is reproduced bit for bit.
+#include "common.cuh"
+
+namespace {
+
+struct ColState {
+    double lane[MC_MAXK][8];
+    double pend[MC_MAXK][8];
+    int cnt[MC_MAXK];
+};
+
+__device__ __forceinline__ void col_push(ColState &C, int c, double v) {
+    const int n = C.cnt[c];
+    const int j = n & 7;
+    C.pend[c][j] = v;
+    C.cnt[c] = n + 1;
+    if (j == 7) {
+        if (n == 7) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) C.lane[c][i] = C.pend[c][i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) C.lane[c][i] = __dadd_rn(C.lane[c][i], C.pend[c][i]);
+        }
+    }
+}
+
+// numpy add.reduce pairwise order for n <= 128 (see oracle/mcaller_oracle.c np_pairwise), then / n
+__device__ __forceinline__ double col_mean(const ColState &C, int c) {
+    const int n = C.cnt[c];
+    double res;
+    if (n < 8) {
+        res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, C.pend[c][i]);
+    } else {
+        const double *r = C.lane[c];
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (int i = 0; i < (n & 7); ++i) res = __dadd_rn(res, C.pend[c][i]);
+    }
+    return __ddiv_rn(res, (double)n);
+}
+
+__device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
+
+__device__ __forceinline__ mc_record load_rec(const mc_record *p) {
+    mc_record r;
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint4 a = __ldg(s), b = __ldg(s + 1);
+    uint4 *d = reinterpret_cast<uint4 *>(&r);
+    d[0] = a;
+    d[1] = b;
+    return r;
+}
+
+__device__ __forceinline__ uint8_t comp_base(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T';
+        case 'C': return 'G';
+        case 'G': return 'C';
+        case 'T': return 'A';
+        case 'N': return 'N';
+        default: return 0;
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *__restrict__ seg_start, int64_t n_seg,
+          const double *__restrict__ seg_qual, mc_refindex R, int skip_thresh, double qual_thresh, int two_models,
+          mc_call *__restrict__ calls, unsigned long long call_cap, uint32_t *__restrict__ seg_count,
+          const uint32_t *__restrict__ seg_off, unsigned long long *__restrict__ d_ncalls) {
+    const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_seg) return;
+    const double myq = seg_qual[seg];
+    uint32_t n_out = 0;
+    if (myq < qual_thresh) {                       // whole read dropped (:167)
+        if (!WRITE) seg_count[seg] = 0;
+        return;
+    }
+    const int k = R.k;
+    const uint32_t b = seg_start[seg], e = seg_start[seg + 1];
+    uint32_t out_pos = WRITE ? seg_off[seg] : 0u;
+
+    alignas(16) ColState C;
+    int map[MC_MAXK];
+#pragma unroll
+    for (int c = 0; c < MC_MAXK; ++c) { C.cnt[c] = 0; map[c] = c; }
+    bool started = false;        // read_name == last_read  (this read already had a line with 'M')
+    bool has_mpos = false;
+    int mpos = 0, first_ind = 0, last_rev = 0, last_cid = 0;
+    uint32_t name_rec = b;
+    uint32_t sticky_err = 0u;
+
+#define MPOS_TRUTHY (has_mpos && mpos != 0)
+
+    // emits the row(s) for the open window; `close_idx` = ordered index of the closing record (or ~0u)
+    auto emit_window = [&](uint32_t close_idx, int chrom_cid) {
+        int n_empty = 0;
+        for (int c = 0; c < k; ++c) n_empty += (C.cnt[map[c]] == 0);
+        if (WRITE) {
+            if (out_pos < call_cap) {
+                mc_call &o = calls[out_pos];
+                const mc_record nr = load_rec(rec + name_rec);
+                o.read_off = rec_line(nr) + nr.name_off;
+                o.read_len = nr.name_len;
+                o.prob = 0.0;
+                o.mpos = mpos;
+                o.close_rec = close_idx;
+                o.win_contig = (uint16_t)last_cid;
+                o.chrom_contig = (uint16_t)(chrom_cid < 0 ? 0xFFFF : chrom_cid);
+                o.rev = (uint8_t)last_rev;
+                o.n_empty = (uint8_t)n_empty;
+                o.label = 0;
+                o.pad0 = 0;
+                o.seg = (uint32_t)seg;
+                o.pad1 = 0;
+                uint32_t err = sticky_err;
+                uint32_t empty_mask = 0u;
+                const int64_t g = __ldg(R.d_base + last_cid) + mpos;
+                // dense site slot = rank of the target among the strand's sites
+                {
+                    const uint32_t *bm = last_rev ? R.d_site_rev : R.d_site_fwd;
+                    const uint32_t *rk = last_rev ? R.d_rank_rev : R.d_rank_fwd;
+                    const uint32_t wbits = __ldg(bm + (g >> 5));
+                    o.site = (int32_t)(__ldg(rk + (g >> 5)) + __popc(wbits & ((1u << (g & 31)) - 1u)));
+                }
+                if (n_empty <= skip_thresh) {
+                    o.kind = MC_CALL;
+                    for (int c = 0; c < k; ++c) {                 // :186-188 (forward reads are flipped)
+                        const int src = map[last_rev ? c : (k - 1 - c)];
+                        if (C.cnt[src] == 0) { o.feat[c] = 0.0; empty_mask |= 1u << c; }
+                        else {
+                            if (C.cnt[src] > 128) err |= MC_CE_COLUMN;
+                            o.feat[c] = col_mean(C, src);
+                        }
+                    }
+                    o.feat[k] = myq;                              // :189-193
+                    for (int c = k + 1; c <= MC_MAXK; ++c) o.feat[c] = 0.0;
+                    // context bounds (:194-195) and base after the target (:197, base_models :99-106)
+                    const int clen = __ldg(R.d_len + last_cid);
+                    uint8_t nextb = 0;
+                    if (mpos - k + 1 < 0 || mpos + k > clen) err |= MC_CE_CONTEXT;
+                    else if (!last_rev) {
+                        const int64_t gn = g + 1;
+                        nextb = ((__ldg(R.d_site_fwd + (gn >> 5)) >> (gn & 31)) & 1u) ? 'M' : __ldg(R.d_bases + gn);
+                    } else {
+                        const int64_t gn = g - 1;
+                        nextb = ((__ldg(R.d_site_rev + (gn >> 5)) >> (gn & 31)) & 1u) ? 'M' : comp_base(__ldg(R.d_bases + gn));
+                    }
+                    if (!(err & MC_CE_CONTEXT) &&
+                        !(nextb == 'A' || nextb == 'C' || nextb == 'G' || nextb == 'T' || nextb == 'M'))
+                        err |= MC_CE_MODELKEY;
+                    o.model_sel = (uint8_t)((two_models && nextb == 'G') ? 1 : 0);
+                } else {
+                    o.kind = MC_TOO_MANY_SKIPS;                   // :238-239
+                    for (int c = 0; c <= MC_MAXK; ++c) o.feat[c] = 0.0;
+                    o.model_sel = 0;
+                }
+                o.empty_mask = (uint8_t)empty_mask;
+                o.err = (uint8_t)err;
+            }
+            ++out_pos;
+        }
+        ++n_out;
+    };
+    auto emit_multi = [&]() {
+        if (WRITE) {
+            if (out_pos < call_cap) {
+                mc_call &o = calls[out_pos];
+                const mc_record nr = load_rec(rec + name_rec);
+                o.read_off = rec_line(nr) + nr.name_off;
+                o.read_len = nr.name_len;
+                o.prob = 0.0;
+                for (int c = 0; c <= MC_MAXK; ++c) o.feat[c] = 0.0;
+                o.mpos = mpos;
+                o.site = -1;
+                o.close_rec = 0u;
+                o.win_contig = (uint16_t)last_cid;
+                o.chrom_contig = (uint16_t)last_cid;
+                o.kind = MC_MULTI_M;
+                o.rev = (uint8_t)last_rev;
+                o.n_empty = 0; o.empty_mask = 0; o.model_sel = 0; o.label = 0; o.err = 0; o.pad0 = 0;
+                o.seg = (uint32_t)seg;
+                o.pad1 = 0;
+            }
+            ++out_pos;
+        }
+        ++n_out;
+    };
+    auto reset_cols = [&]() {
+#pragma unroll
+        for (int c = 0; c < MC_MAXK; ++c) C.cnt[c] = 0;
+    };
+
+    for (uint32_t i = b; i < e; ++i) {
+        const mc_record r = load_rec(rec + i);
+        const bool same_read = started;
+        if (!same_read) {                                          // :161-162
+            first_ind = r.event_idx;
+            if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+        }
+        int rev;
+        if (!same_read) rev = !(r.flags & MC_RF_EQ);               // :169-174
+        else {
+            if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+            rev = !(r.event_idx > first_ind);
+        }
+        const int cid = r.contig, pos = r.pos;
+        uint32_t bits = 0u;                                        // 'M's of meth_ref[pos:pos+k] (:176)
+        if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, k);
+        const int first_m = bits ? (__ffs(bits) - 1) : -1;
+
+        if (MPOS_TRUTHY && pos >= mpos + 1 && same_read) {         // :179 (the other-read case is the segment hand-off below)
+            emit_window(i, cid);
+            if (first_m < 0 || pos > mpos + skip_thresh + 1) {     // :242-245
+                reset_cols();
+                has_mpos = false;
+            } else {                                               // :246-256 multi-M carry
+                if (first_m != 0) emit_multi();
+                const int last_mpos = mpos;
+                mpos = pos + first_m;
+                int sp = mpos - last_mpos;
+                if (sp > k) sp = k;
+                if (sp <= 0) { sticky_err |= MC_CE_SPACING; sp = k; }
+                int nm[MC_MAXK];
+                for (int c = 0; c < k; ++c) {
+                    if (c < sp) { nm[c] = map[k - sp + c]; C.cnt[nm[c]] = 0; }
+                    else nm[c] = map[c - sp];
+                }
+                for (int c = 0; c < k; ++c) map[c] = nm[c];
+            }
+        }
+        if (first_m >= 0) {                                        // :269-287
+            if (MPOS_TRUTHY && rev != last_rev) has_mpos = false;  // columns kept (:276-277)
+            if (!MPOS_TRUTHY) { has_mpos = true; mpos = pos + first_m; }
+            started = true;
+            last_rev = rev;
+            last_cid = cid;
+            name_rec = i;
+            if (r.flags & MC_RF_BADNUM) sticky_err |= MC_CE_BADNUM;
+            if (WRITE) col_push(C, map[first_m], r.diff);
+            else C.cnt[map[first_m]] += 1;
+        } else if (MPOS_TRUTHY) {                                  // :289-291
+            has_mpos = false;
+            reset_cols();
+        }
+    }
+    // hand-off: a window still open at the end of the read is closed by the next kept line of the file, i.e. the
+    // first record of the next segment that passes the quality filter (:179, read_name != last_read)
+    if (MPOS_TRUTHY) {
+        int64_t j = seg + 1;
+        while (j < n_seg && seg_qual[j] < qual_thresh) ++j;
+        if (j < n_seg) {
+            const uint32_t ci = seg_start[j];
+            const mc_record cr = load_rec(rec + ci);
+            emit_window(ci, cr.contig);
+        } else {
+            emit_window(0xFFFFFFFFu, -1);                          // pending: resolved by the next chunk, dropped at EOF
+        }
+    }
+    if (!WRITE) seg_count[seg] = n_out;
+    (void)n_records;
+    (void)d_ncalls;
+#undef MPOS_TRUTHY
+}
+
+__global__ void k_check_cap(const unsigned long long *d_ncalls, unsigned long long cap, unsigned long long *d_flag) {
+    if (d_ncalls[0] > cap) *d_flag = 1ull;
+}
+
+}  // namespace
+
+extern "C" int mc_build_windows(const mc_record *d_rec, int64_t n_records, const uint32_t *d_seg_start, int64_t n_seg,
+                                const double *d_seg_qual, const mc_refindex *ref, int skip_thresh, double qual_thresh,
+                                int two_models, mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count, uint64_t *d_ncalls,
+                                void *d_ws, void *stream) {
+    MC_REQUIRE(d_rec && d_seg_start && d_seg_qual && ref && d_calls && d_seg_count && d_ncalls && d_ws, "null pointer");
+    MC_REQUIRE(ref->k >= 1 && ref->k <= MC_MAXK, "k out of range");
+    MC_REQUIRE(skip_thresh >= 0, "skip_thresh must be >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    MC_CUDA_CHECK(cudaMemsetAsync(d_ncalls, 0, 16, st));
+    if (n_seg <= 0) return MC_OK;
+    const unsigned nb = (unsigned)((n_seg + 127) / 128);
+    uint32_t *seg_off = reinterpret_cast<uint32_t *>(d_ws);
+    void *scan_ws = reinterpret_cast<uint8_t *>(d_ws) + ((n_seg * 4 + 255) / 256) * 256;
+    k_windows<false><<<nb, 128, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, *ref, skip_thresh, qual_thresh,
+                                          two_models, d_calls, (unsigned long long)call_cap, d_seg_count, nullptr,
+                                          reinterpret_cast<unsigned long long *>(d_ncalls));
+    MC_LAUNCH_CHECK();
+    int rc = mc_exscan_u32(d_seg_count, seg_off, n_seg, d_ncalls, scan_ws, st);
+    if (rc) return rc;
+    k_windows<true><<<nb, 128, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, *ref, skip_thresh, qual_thresh,
+                                         two_models, d_calls, (unsigned long long)call_cap, d_seg_count, seg_off,
+                                         reinterpret_cast<unsigned long long *>(d_ncalls));
+    MC_LAUNCH_CHECK();
+    k_check_cap<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
+                                 reinterpret_cast<unsigned long long *>(d_ncalls) + 1);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}

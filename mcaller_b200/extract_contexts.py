@@ -1,0 +1,343 @@
+"""Drop-in replacement for the reference module `extract_contexts` (al-mcintyre/mCaller).
+
+Same public names and signatures as the reference file (extract_contexts.py:11-110), so the unmodified
+`mCaller.py` (`from extract_contexts import *`, mCaller.py:18) and `make_bed.py` (`from extract_contexts import
+revcomp`, make_bed.py:8) run on it when this directory precedes the reference on sys.path.
+`extract_features` keeps its contract -- it appends `.diffs.<k>` rows to `<tsv prefix>.diffs.<k>.tmp<startline>` and
+prints the five counters -- but the work is done by the CUDA pipeline in libmcaller_b200.so (engine.Engine); there is
+no CPU implementation behind it.
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import refmark
+from .refmark import comp, revcomp, strand  # noqa: F401  (re-exported, reference :14-29)
+
+base_comps = {"A": "T", "C": "G", "T": "A", "G": "C", "N": "N", "M": "M"}
+
+CHUNK_BYTES = int(os.environ.get("MCALLER_B200_CHUNK_BYTES", str(1 << 30)))
+
+
+class ReferenceAbort(RuntimeError):
+    """A condition on which the reference prints a diagnostic and calls sys.exit(0) or dies with an exception."""
+
+
+def methylate_motifs(ref_seq, motif, meth_base, meth_position=None):
+    """reference :33-41 (the meth_position branch of the reference is unreachable from its CLI and not mirrored)."""
+    return refmark.mark_motif(ref_seq, motif, meth_base)
+
+
+def methylate_positions(ref_seq, positions, meth_base):
+    """reference :45-56; raises where the reference prints and quits."""
+    return refmark.mark_positions(ref_seq, positions, meth_base)
+
+
+def methylate_references(ref_seq, base, motif=None, positions=None, train=False, contig=None):
+    """reference :60-73."""
+    if not positions and not motif:
+        print("no motifs or positions specified")
+        raise ReferenceAbort("no motifs or positions specified")
+    return refmark.mark_reference(ref_seq, base, motif=motif, positions_file=positions, contig=contig)
+
+
+def find_and_methylate(refname, contigname, base, motif, positions_list):
+    """reference :76-81 (returns None when the contig is absent)."""
+    seqs = refmark.read_fasta(refname)
+    if contigname in seqs:
+        return methylate_references(seqs[contigname], base, motif=motif, positions=positions_list, contig=contigname)
+    return None
+
+
+def writefi(data, fi):
+    """reference :83-86 (append mode)."""
+    with open(fi, "a") as outfi:
+        for entry in data:
+            outfi.write("\t".join(entry) + "\n")
+
+
+def base_models(base, twobase=False):
+    """reference :99-106: two-letter context after the target -> model key."""
+    if base == "A" and twobase:
+        table = {"M" + b: "MH" for b in "CATMH"}
+        table.update({"A" + b: "MH" for b in "TCAM"})
+        table["MG"] = "MG"
+        table["AG"] = "MG"
+        return table
+    return {f + b: "general" for f in "MAT" for b in "ACGTM"}
+
+
+# ---- helpers -------------------------------------------------------------------------------------------------------
+
+def _line_name(buf, start):
+    """4th whitespace-separated field of the line starting at `start` (bytes) or None."""
+    end = buf.find(b"\n", start)
+    if end < 0:
+        end = len(buf)
+    f = buf[start:end].split(None, 4)
+    return f[3] if len(f) > 3 else None
+
+
+def read_boundary_before(buf, limit=None):
+    """Largest start s of a complete line of buf such that a new read begins at s (its name differs from the previous
+    line's); 0 if there is none.  Everything from s on (the possibly incomplete last read and any partial last line) is
+    meant to be carried into the next chunk."""
+    end = buf.rfind(b"\n", 0, len(buf) if limit is None else limit) + 1       # end of the complete lines
+    if end <= 0:
+        return 0
+    cur = buf.rfind(b"\n", 0, end - 1) + 1                                     # start of the last complete line
+    while cur > 0:
+        prev = buf.rfind(b"\n", 0, cur - 1) + 1
+        if _line_name(buf, cur) != _line_name(buf, prev):
+            return cur
+        cur = prev
+    return 0
+
+
+def read_boundary_after(fh, offset, fsize, probe=1 << 22):
+    """Smallest file offset s >= offset at which a line starts that begins a new read (or s == 0), else fsize."""
+    if offset <= 0:
+        return 0
+    if offset >= fsize:
+        return fsize
+    back = min(offset, 1 << 16)
+    while True:
+        fh.seek(offset - back)
+        head = fh.read(back)
+        p = head.rfind(b"\n", 0, back - 1)       # newline before the line that holds byte offset-1
+        if p >= 0 or back == offset:
+            break
+        back = min(offset, back * 4)
+    base = offset - back + (p + 1)               # file offset of the start of the line holding byte offset-1
+    while True:
+        fh.seek(base)
+        buf = fh.read(probe)
+        if not buf:
+            return fsize
+        at_eof = base + len(buf) >= fsize
+        prev_name = _line_name(buf, 0)
+        e = buf.find(b"\n")
+        cur = e + 1 if e >= 0 else len(buf)
+        last_complete = 0
+        while cur < len(buf):
+            e = buf.find(b"\n", cur)
+            if e < 0 and not at_eof:
+                break                              # partial line: refill from the last complete line
+            nm = _line_name(buf, cur)
+            if base + cur >= offset and nm != prev_name:
+                return base + cur
+            prev_name = nm
+            last_complete = cur
+            cur = (e + 1) if e >= 0 else len(buf)
+        if at_eof:
+            return fsize
+        if last_complete == 0:
+            probe *= 4
+        else:
+            base += last_complete
+
+
+def _fmt(x):
+    return repr(float(x))
+
+
+class _RowFormatter(object):
+    """Turns device rows into the reference's `.diffs.<k>` text rows (writer :216) and keeps the counters (:295-301)."""
+
+    def __init__(self, refindex, k, base, train, pos_label, have_model):
+        self.ref, self.k, self.base = refindex, k, base
+        self.train, self.pos_label, self.have_model = train, pos_label, have_model
+        self.mod_label = "m6A" if base == "A" else "m" + base
+        self.n_obs = 0
+        self.pos_set, self.multi, self.wskips, self.toomany = set(), set(), set(), set()
+        self.signals, self.contexts = {}, {}
+        self.pending = None        # (call fields, read name, segment key) awaiting the contig of the next kept line
+        self.seg_base = 0
+
+    @staticmethod
+    def _check(err, mpos):
+        if err & 1:
+            raise ReferenceAbort("window at %d lies within k of a contig end (reference: IndexError / sys.exit at extract_contexts.py:195/:224)" % mpos)
+        if err & 2:
+            raise ReferenceAbort("base after target %d is not one of ACGTM (reference: KeyError -> sys.exit, :218-223)" % mpos)
+        if err & 4:
+            raise ValueError("unsupported numeric field in a line feeding the window at %d" % mpos)
+        if err & 8:
+            raise ReferenceAbort("more than 128 events in one column at %d" % mpos)
+        if err & 16:
+            raise ReferenceAbort("n diffs off (multi-M spacing 0) at %d" % mpos)
+
+    def _row(self, c, read, segkey, chrom_idx):
+        k = self.k
+        mpos = int(c["mpos"])
+        self._check(int(c["err"]), mpos)
+        rev = bool(c["rev"])
+        ctx = self.ref.context(int(c["win_contig"]), mpos, rev)
+        em = int(c["empty_mask"])
+        feat = c["feat"]
+        feats = ["0" if (em >> j) & 1 else _fmt(feat[j]) for j in range(k)] + [_fmt(feat[k])]
+        chrom = self.ref.names[chrom_idx]
+        row = [chrom, read.decode(), str(mpos), ctx, ",".join(feats), strand(rev)]
+        if self.train:
+            label = self.pos_label[(chrom, mpos, strand(rev))]
+            row.append(label)
+            self.signals.setdefault("general", {}).setdefault(label, []).append([float(x) for x in feat[:k + 1]])
+            self.contexts.setdefault("general", {}).setdefault(label, []).append(ctx)
+        elif self.have_model:
+            p = float(c["prob"])
+            row.append(self.mod_label if p >= 0.5 else self.base)
+            row.append(str(np.round(np.float64(p), 2)))
+        self.n_obs += 1
+        self.pos_set.add(mpos)
+        if int(c["n_empty"]) > 0:
+            self.wskips.add((segkey, mpos))
+        return row
+
+    def consume(self, calls, text, first_kept_contig, n_segments):
+        """Rows of one chunk (host structured array) -> list of row lists.  `first_kept_contig`: contig index of the
+        first kept line of this chunk (it closes a window left pending by the previous chunk), or None."""
+        out = []
+        if self.pending is not None and first_kept_contig is not None:
+            pc, pread, pkey = self.pending
+            if int(pc["kind"]) == 0:
+                out.append(self._row(pc, pread, pkey, first_kept_contig))
+            else:
+                self.toomany.add((pkey, int(pc["mpos"])))
+            self.pending = None
+        for c in calls:
+            kind = int(c["kind"])
+            segkey = self.seg_base + int(c["seg"])
+            if kind == 2:
+                self.multi.add((segkey, int(c["mpos"])))
+                continue
+            ro = int(c["read_off"])
+            read = bytes(text[ro:ro + int(c["read_len"])])
+            if int(c["close_rec"]) == 0xFFFFFFFF:
+                self.pending = (c.copy(), read, segkey)      # still open at the end of the chunk
+                continue
+            if kind == 1:
+                self.toomany.add((segkey, int(c["mpos"])))
+                continue
+            out.append(self._row(c, read, segkey, int(c["chrom_contig"])))
+        self.seg_base += n_segments
+        return out
+
+
+def _first_kept_contig(engine, res, qual_thresh):
+    """Contig index of the first kept line of the chunk just processed (first ordered record of a segment that
+    passes the quality filter), or None."""
+    if res.n_records == 0:
+        return None
+    if qual_thresh <= 0:
+        return int(engine.records(1)[0]["contig"])
+    import torch
+    nseg = res.n_segments
+    q = engine._bufs["seg_qual"][: 8 * nseg].view(torch.float64)
+    ok = (~(q < qual_thresh)).nonzero()
+    if ok.numel() == 0:
+        return None
+    s = int(ok[0])
+    start = int(engine._bufs["seg_start"][: 4 * (nseg + 1)].view(torch.int32)[s])
+    return int(engine.records(start + 1)[start]["contig"])
+
+
+def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thresh, modelfile, classifier, startline, endline=None,
+                     train=False, pos_label=None, base=None, motif=None, positions_list=None):
+    """GPU implementation behind the reference signature (extract_contexts.py:110).
+
+    startline/endline are byte offsets like the reference's (mCaller.py:58, :63-68); a worker owns the reads whose
+    first line starts inside [startline, endline) (ranges are snapped to read boundaries instead of the reference's
+    '-500 characters / 8 MB overrun' overlap), so concatenating the workers' files in offset order gives
+    exactly the -t 1 output.
+    """
+    from . import engine as _engine, models as _models, read_qual as _rq
+    from .refindex import ReferenceIndex
+    _engine.require_cuda()
+    k = int(k)
+    seqs = refmark.read_fasta(fasta_input)
+    try:
+        ref = ReferenceIndex(seqs, base, motif=motif, positions_file=positions_list, k=k)
+    except refmark.MarkError as e:
+        print(str(e) + " - quitting thread now")
+        raise ReferenceAbort(str(e))
+    dm, two = None, False
+    if not train:
+        tsv_output = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k) + ".tmp" + str(startline)
+        model = _models.load_model_file(modelfile)
+        e0, e1, two = _models.select_models(model, base)
+        dm = _models.DeviceModels(e0, e1)
+        if dm.n_in != k + 1:
+            raise ValueError("model expects %d inputs but -n %d gives %d" % (dm.n_in, k, k + 1))
+    else:
+        tsv_output = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k) + ".train.tmp" + str(startline)
+    qt = _rq.build_quality_table(read2qual)
+    eng = _engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=skip_thresh, qual_thresh=qual_thresh, two_models=two, histogram=False)
+    fmt = _RowFormatter(ref, k, base, train, pos_label, dm is not None)
+
+    fsize = os.path.getsize(tsv_input)
+    if endline is None:
+        endline = fsize
+    towrite_total = 0
+    with open(tsv_input, "rb") as fh:
+        lo = read_boundary_after(fh, startline, fsize)
+        hi = read_boundary_after(fh, min(endline, fsize), fsize)
+        pos = lo
+        carry = b""
+        open(tsv_output, "a").close()
+        while pos < hi or carry:
+            want = min(CHUNK_BYTES, hi - pos)
+            fh.seek(pos)
+            data = carry + fh.read(want)
+            pos += want
+            if pos < hi:
+                cut = read_boundary_before(data, len(data))
+                if cut == 0:            # a single read larger than the chunk: keep reading
+                    carry = data
+                    continue
+                carry, data = data[cut:], data[:cut]
+            else:
+                carry = b""
+            if not data:
+                continue
+            rows = _run_text(eng, fmt, data, qual_thresh)
+            writefi(rows, tsv_output)
+            towrite_total += len(rows)
+        # a window still open at the end of my range is closed by the first kept line after it (next worker's range)
+        if fmt.pending is not None and hi < fsize:
+            fh.seek(hi)
+            probe = fh.read(1 << 22)
+            cutp = probe.rfind(b"\n")
+            if cutp >= 0:
+                d_text = eng.upload(probe[:cutp + 1])
+                res = eng.run_chunk(d_text, cutp + 1)
+                _raise_on_counters(res)
+                fk = _first_kept_contig(eng, res, qual_thresh)
+                rows = fmt.consume(np.zeros(0, dtype=_engine.CALL_DTYPE), b"", fk, 0)
+                writefi(rows, tsv_output)
+    print("thread finished processing...:")
+    print("%d observations" % fmt.n_obs)
+    print("%d positions" % len(fmt.pos_set))
+    print("%d regions with multiple methylated bases" % len(fmt.multi))
+    print("%d observations with skips included" % len(fmt.wskips))
+    print("%d observations with too many skips" % len(fmt.toomany))
+    if train:
+        return fmt.signals, fmt.contexts
+
+
+def _raise_on_counters(res):
+    c = res.counters
+    if c["badpos"]:
+        raise ValueError("%d lines on known contigs have a non-integer position column" % c["badpos"])
+    if c["longline"]:
+        raise ReferenceAbort("%d lines do not fit the 2 KB tile look-ahead" % c["longline"])
+    if res.missing_quality:
+        raise KeyError("%d reads of the eventalign file are missing from the fastq" % res.missing_quality)
+
+
+def _run_text(eng, fmt, data, qual_thresh):
+    d_text = eng.upload(data)
+    res = eng.run_chunk(d_text, len(data))
+    _raise_on_counters(res)
+    fk = _first_kept_contig(eng, res, qual_thresh) if fmt.pending is not None else None
+    return fmt.consume(res.calls(), data, fk, res.n_segments)

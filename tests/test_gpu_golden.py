@@ -1,0 +1,98 @@
+"""GPU parity against the golden vectors produced by the unmodified reference (tools/make_golden.py) and against the
+CPU oracle, through the public drop-in API (extract_contexts.extract_features / make_bed.aggregate_by_pos, which call
+the C ABI of libmcaller_b200.so).  Bar: rows, keys, contexts, strands, feature text, labels, probability text, the five
+stdout counters and BED rows are all byte-identical to the reference's output."""
+import json
+import os
+
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+CASES = list(gc.CASES)
+
+
+def _run_case(name, tmp_path, capsys, chunk_bytes=None):
+    from mcaller_b200 import extract_contexts as ec, read_qual
+    case = gc.CASES[name]
+    gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    read2qual = read_qual.extract_read_quality(inp["fastq"])
+    base = case.get("base", "A")
+    motif = case.get("motif")
+    if motif and len(motif) == 1:
+        base = motif
+    out = ".".join(inp["tsv"].split(".")[:-1]) + ".diffs.6.tmp0"
+    if os.path.exists(out):
+        os.remove(out)
+    old = ec.CHUNK_BYTES
+    if chunk_bytes:
+        ec.CHUNK_BYTES = chunk_bytes
+    try:
+        ec.extract_features(inp["tsv"], inp["fasta"], read2qual, 6, case.get("s", 0), case.get("q", 0.0), inp["model"], "NN", 0,
+                            endline=os.path.getsize(inp["tsv"]), base=base, motif=motif, positions_list=inp.get("positions"))
+    finally:
+        ec.CHUNK_BYTES = old
+    stdout = capsys.readouterr().out
+    return gold, open(out).read(), stdout, out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_diffs_match_reference(name, tmp_path, capsys, cuda_lib):
+    gold, mine, stdout, _ = _run_case(name, tmp_path, capsys)
+    assert gold["diffs"] is not None
+    g_rows, m_rows = gold["diffs"].split("\n"), mine.split("\n")
+    assert len(g_rows) == len(m_rows)
+    for g, m in zip(g_rows, m_rows):
+        assert g == m
+    c = gold["counters"]
+    assert "%d observations\n" % c["observations"] in stdout
+    assert "%d positions\n" % c["positions"] in stdout
+    assert "%d regions with multiple methylated bases\n" % c["multi"] in stdout
+    assert "%d observations with skips included\n" % c["with_skips"] in stdout
+    assert "%d observations with too many skips\n" % c["too_many_skips"] in stdout
+
+
+@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q"])
+@pytest.mark.parametrize("chunk", [40000, 300000])
+def test_chunked_equals_whole(name, chunk, tmp_path, capsys, cuda_lib):
+    """Streaming in small read-aligned chunks (window hand-off across chunk edges) must not change a byte."""
+    gold, mine, _, _ = _run_case(name, tmp_path, capsys, chunk_bytes=chunk)
+    assert mine == gold["diffs"]
+
+
+@pytest.mark.parametrize("name", ["gatc_s0", "gatc_s2", "masonread1_p"])
+def test_bed_matches_reference(name, tmp_path, capsys, cuda_lib):
+    from mcaller_b200 import make_bed as mb
+    gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
+    diffs = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
+    with open(diffs, "w") as fh:
+        fh.write(gold["diffs"])
+    for b in gold["beds"]:
+        a = b["args"]
+        out = os.path.join(str(tmp_path), "o.bed")
+        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), None, "--control" in a, False, False,
+                            None, False, "x", False)
+        assert open(out).read() == b["bed"]
+
+
+def test_reference_fixture_bed(tmp_path, cuda_lib):
+    """The reference's own golden BED from its own golden diffs (make_bed.py -d 1 -t 0.5)."""
+    from mcaller_b200 import make_bed as mb
+    fx = os.path.join(gc.GOLD, "masonread1")
+    out = os.path.join(str(tmp_path), "o.bed")
+    mb.aggregate_by_pos(os.path.join(fx, "masonread1.eventalign.diffs.6"), out, 1, 0.5, None, False, False, False, None, False, "x", False)
+    assert open(out).read() == open(os.path.join(fx, "masonread1.methylation.summary.bed")).read()
+
+
+def test_reference_fixture_features(tmp_path, capsys, cuda_lib):
+    """masonread1.eventalign.diffs.6: windows, contexts, strands and the 7 feature strings are the reference's own golden
+    values (its probability column predates the shipped model)."""
+    _, mine, _, _ = _run_case("masonread1_p", tmp_path, capsys)
+    fx = open(os.path.join(gc.GOLD, "masonread1", "masonread1.eventalign.diffs.6")).read().strip().split("\n")
+    rows = mine.strip().split("\n")
+    assert len(rows) == len(fx) == 9
+    for a, b in zip(rows, fx):
+        assert a.split("\t")[:6] == b.split("\t")[:6]
