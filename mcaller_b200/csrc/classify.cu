@@ -107,13 +107,6 @@ __global__ void __launch_bounds__(256) k_linear(mc_call *__restrict__ calls, int
 // RandomForestClassifier.predict_proba: mean over trees of the leaf class-1 fraction; the walk compares float32(x)
 // with the float64 threshold (sklearn tree/_tree.pyx).  A block owns 256 calls and streams the trees through shared
 // memory (node table of one tree at a time), so every node read in the walk is an smem read.
-struct RfNode {
-    double thr;
-    float p1f_unused;
-    int32_t left, right;   // absolute smem node index, -1 = leaf
-    int32_t feature;
-};
-
 __global__ void __launch_bounds__(256)
 k_rf(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int max_nodes) {
     extern __shared__ __align__(16) uint8_t rf_smem[];
@@ -180,7 +173,36 @@ k_hist(const mc_call *__restrict__ calls, int64_t n, uint32_t *__restrict__ dept
     atomicMin(first + c.site, row_base + (unsigned long long)i);
 }
 
+// row statistics without a D2H copy of the rows: [0] calls closed in this chunk, [1] calls still pending,
+// [2] too-many-skips events, [3] multi-M events, [4] rows with an error flag, [5] calls labelled methylated
+__global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__ calls, int64_t n, unsigned long long *__restrict__ out) {
+    __shared__ unsigned int s[6];
+    if (threadIdx.x < 6) s[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const mc_call &c = calls[i];
+        if (c.kind == MC_CALL) {
+            atomicAdd(&s[c.close_rec == 0xFFFFFFFFu ? 1 : 0], 1u);
+            if (c.label) atomicAdd(&s[5], 1u);
+        } else if (c.kind == MC_TOO_MANY_SKIPS) atomicAdd(&s[2], 1u);
+        else atomicAdd(&s[3], 1u);
+        if (c.err) atomicAdd(&s[4], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && s[threadIdx.x]) atomicAdd(out + threadIdx.x, (unsigned long long)s[threadIdx.x]);
+}
+
 }  // namespace
+
+extern "C" int mc_count_calls(const mc_call *d_calls, int64_t n_calls, uint64_t *d_out, void *stream) {
+    MC_REQUIRE(d_calls && d_out, "null pointer");
+    if (n_calls <= 0) return MC_OK;
+    k_count_calls<<<(unsigned)((n_calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_calls, n_calls,
+                                                                                       reinterpret_cast<unsigned long long *>(d_out));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
 
 extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void *stream) {
     MC_REQUIRE(d_calls && models, "null pointer");

@@ -52,12 +52,13 @@ class Engine(object):
         ns = max(refindex.n_sites, 1)
         self.d_depth = torch.zeros(ns, dtype=torch.int32, device=self.device)
         self.d_meth = torch.zeros(ns, dtype=torch.int32, device=self.device)
-        self.d_first = torch.full((ns,), -1, dtype=torch.int64, device=self.device)   # 0xFFFF... as uint64
+        self.d_first = torch.full((ns,), 2 ** 63 - 1, dtype=torch.int64, device=self.device)   # 'never seen'
         self.row_base = 0
         self._bufs = {}
         self.d_small = torch.zeros(64, dtype=torch.int64, device=self.device)       # counters / scalars
         self.h_small = np.zeros(64, dtype=np.uint64)
         self.launches = 0
+        self.scan_events = None          # set to [] to collect (start, end) CUDA events around the scan kernel
 
     # ---- buffers -----------------------------------------------------------------------------------------------
     def _buf(self, name, nbytes):
@@ -103,8 +104,14 @@ class Engine(object):
         while True:
             rec_a = self._buf("rec_a", 32 * rec_cap)
             self.d_small.zero_()
+            if self.scan_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             check(L.mc_scan(C.c_void_p(d_text.data_ptr()), nbytes, self.ref.ref(), 1 if self.dense else 0, C.c_void_p(rec_a.data_ptr()),
                             rec_cap, C.c_void_p(tile_tab.data_ptr()), C.c_void_p(self.d_small.data_ptr()), st))
+            if self.scan_events is not None:
+                e1.record()
+                self.scan_events.append((e0, e1))
             self.launches += 1
             cnt = self._read_small(0, MC_C_COUNT)
             if cnt[C_OVERFLOW] == 0 and cnt[C_RECORDS] <= rec_cap:
@@ -127,7 +134,7 @@ class Engine(object):
         seg_start = self._buf("seg_start", 4 * (n_rec + 2))
         check(L.mc_segment_reads(C.c_void_p(d_text.data_ptr()), C.c_void_p(rec_b.data_ptr()), n_rec, C.c_void_p(seg_start.data_ptr()),
                                  C.c_void_p(self.d_small.data_ptr() + 8 * 16), C.c_void_p(ws.data_ptr()), st))
-        self.launches += 7
+        self.launches += 4 + 5                       # order: 3 scan kernels + gather; segmentation: flags + 3 + starts
         n_seg = int(self._read_small(16, 1)[0])
         res.n_segments = n_seg
         seg_qual = self._buf("seg_qual", 8 * n_seg)
@@ -135,6 +142,7 @@ class Engine(object):
         check(L.mc_segment_quality(C.c_void_p(d_text.data_ptr()), C.c_void_p(rec_b.data_ptr()), C.c_void_p(seg_start.data_ptr()), n_seg,
                                    C.c_void_p(self.d_qual.data_ptr()), self.qual_table_size, C.c_void_p(seg_qual.data_ptr()),
                                    C.c_void_p(self.d_small.data_ptr() + 8 * 17), st))
+        self.launches += 1
         if call_cap is None:
             call_cap = n_rec // 4 + 1024
         while True:
@@ -143,7 +151,7 @@ class Engine(object):
                                      C.c_void_p(seg_qual.data_ptr()), self.ref.ref(), self.skip_thresh, self.qual_thresh, self.two_models,
                                      C.c_void_p(calls.data_ptr()), call_cap, C.c_void_p(seg_count.data_ptr()),
                                      C.c_void_p(self.d_small.data_ptr() + 8 * 18), C.c_void_p(ws.data_ptr()), st))
-            self.launches += 7
+            self.launches += 6                       # 2 window passes + 3 scan kernels + capacity check
             v = self._read_small(17, 3)
             res.missing_quality = int(v[0])
             n_calls = int(v[1])
@@ -163,6 +171,15 @@ class Engine(object):
             self.row_base += n_calls
         return res
 
+    def count_rows(self, res):
+        """Device-side row statistics of a chunk -> dict (one tiny kernel + 48-byte read-back)."""
+        self.d_small[24:30].zero_()
+        if res.n_calls:
+            check(self.L.mc_count_calls(C.c_void_p(res.calls_dev.data_ptr()), res.n_calls, C.c_void_p(self.d_small.data_ptr() + 8 * 24), self._sptr()))
+            self.launches += 1
+        v = self._read_small(24, 6)
+        return dict(calls=int(v[0]), pending=int(v[1]), too_many_skips=int(v[2]), multi=int(v[3]), errors=int(v[4]), methylated=int(v[5]))
+
     def records(self, n_rec):
         """Ordered stage-1 records of the last chunk (host copy; test helper)."""
         return self._bufs["rec_b"][: n_rec * 32].cpu().numpy().view(RECORD_DTYPE)
@@ -174,5 +191,5 @@ class Engine(object):
     def reset_histogram(self):
         self.d_depth.zero_()
         self.d_meth.zero_()
-        self.d_first.fill_(-1)
+        self.d_first.fill_(2 ** 63 - 1)
         self.row_base = 0

@@ -1,0 +1,210 @@
+"""Stage-level GPU tests through the C ABI: tokeniser records vs a Python split of the same bytes, device generator vs
+the numpy generator, classifiers vs the oracle / scikit-learn, histogram vs the oracle's aggregation, and a larger
+device-generated workload checked against the CPU oracle plus size-independent properties."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case_name, tmp_path, k=6):
+    import torch
+    from mcaller_b200 import engine, models, read_qual, refmark
+    from mcaller_b200.refindex import ReferenceIndex
+    case = gc.CASES[case_name]
+    inp = gc.build_inputs(case, str(tmp_path))
+    seqs = refmark.read_fasta(inp["fasta"])
+    base = case.get("base", "A")
+    ref = ReferenceIndex(seqs, base, motif=case.get("motif"), positions_file=inp.get("positions"), k=k)
+    model = models.load_model_file(inp["model"])
+    e0, e1, two = models.select_models(model, base)
+    dm = models.DeviceModels(e0, e1)
+    qt = read_qual.build_quality_table(read_qual.extract_read_quality(inp["fastq"]))
+    return case, inp, ref, dm, two, qt
+
+
+def test_scan_records_match_python_split(tmp_path, cuda_lib):
+    """Dense mode: one record per kept line, every parsed field equal to what Python's split/int/float give."""
+    from mcaller_b200 import engine
+    case, inp, ref, dm, two, qt = _setup("adversarial", tmp_path)
+    data = open(inp["tsv"], "rb").read()
+    eng = engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=1, two_models=two, dense=True)
+    res = eng.run_chunk(eng.upload(data), len(data))
+    rec = eng.records(res.n_records)
+    want = []
+    off = 0
+    n_lines = n_short = n_unknown = n_nnn = 0
+    for ln in data.split(b"\n")[:-1]:
+        n_lines += 1
+        f = ln.split()
+        if len(f) < 12:
+            n_short += 1
+        elif f[0].decode() not in ref.names:
+            n_unknown += 1
+        elif f[9] == b"NNNNNN":
+            n_nnn += 1
+        else:
+            d = float(np.round(float(f[6]) - float(f[10]), 4))
+            want.append((off, int(f[1]), int(f[5]), d, f[2] == f[9], ref.names.index(f[0].decode()), f[3], ln.find(f[3])))
+        off += len(ln) + 1
+    assert res.counters["lines"] == n_lines and res.counters["short"] == n_short
+    assert res.counters["unknown_contig"] == n_unknown and res.counters["nnn"] == n_nnn
+    assert res.counters["kept"] == len(want) == res.n_records
+    for r, w in zip(rec, want):
+        line = int(r["line_lo"]) | (int(r["line_hi"]) << 32)
+        assert (line, int(r["pos"]), int(r["event_idx"]), float(r["diff"]), bool(r["flags"] & 1), int(r["contig"])) == w[:6]
+        assert data[line + int(r["name_off"]):line + int(r["name_off"]) + int(r["name_len"])] == w[6] and int(r["name_off"]) == w[7]
+        assert not (r["flags"] & 12)
+
+
+def test_sparse_records_are_subset_with_same_calls(tmp_path, cuda_lib):
+    """Sparse mode (candidates + closers only) must give exactly the rows of dense mode."""
+    from mcaller_b200 import engine
+    case, inp, ref, dm, two, qt = _setup("gatc_s1", tmp_path)
+    data = open(inp["tsv"], "rb").read()
+    outs = []
+    for dense in (False, True):
+        eng = engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=1, two_models=two, dense=dense)
+        res = eng.run_chunk(eng.upload(data), len(data))
+        c = res.calls()
+        outs.append((res.n_records, c[["mpos", "kind", "rev", "n_empty", "label"]].tolist(), c["feat"].tolist(), c["prob"].tolist()))
+    assert outs[0][0] < outs[1][0] * 0.5
+    assert outs[0][1:] == outs[1][1:]
+
+
+def test_device_generator_matches_numpy_generator(cuda_lib):
+    import torch
+    from mcaller_b200 import synth, synth_device
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=5, contigs=[("zeta", 9000), ("alpha", 7000)], n_reads=14, len_min=150, len_max=600)
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    meth = {}
+    for ci, (nm, ln) in enumerate(spec.contigs):
+        b0 = int(ref.contig_base[ref.names.index(nm)])
+        meth[ci] = (synth.meth_sites(spec, ci, ref.site_fwd_bits[b0:b0 + ln]), synth.meth_sites(spec, ci, ref.site_rev_bits[b0:b0 + ln]))
+    gen = synth_device.DeviceSynth(spec, ref, meth)
+    d_text, n, offs = gen.generate(0, spec.n_reads)
+    dev_bytes = d_text[:n].cpu().numpy().tobytes()
+    host_bytes, _, _, _ = synth.generate(spec, meth)
+    assert dev_bytes == host_bytes
+    assert bytes(d_text[n:n + 64].cpu().numpy()) == b"\n" * 64
+    g = gen.genome_check().cpu().numpy()
+    for ci, (nm, ln) in enumerate(spec.contigs):
+        b0 = int(ref.contig_base[ref.names.index(nm)])
+        assert g[b0:b0 + ln].tobytes().decode() == seqs[nm]
+    # a slice in the middle equals the corresponding slice of the whole
+    d2, n2, _ = gen.generate(3, 5)
+    o = offs.cpu().numpy()
+    assert d2[:n2].cpu().numpy().tobytes() == host_bytes[int(o[3]):int(o[8])]
+
+
+@pytest.mark.parametrize("kind,tol", [("RF", 1e-12), ("LR", 1e-12), ("NBC", 1e-10), ("NN", 1e-12)])
+def test_classifiers_match_sklearn(kind, tol, cuda_lib, oracle):
+    """mc_classify on synthetic feature rows vs scikit-learn predict_proba (float64 on both sides)."""
+    import torch
+    from mcaller_b200 import _lib, models
+    from test_oracle_numerics import _X, _fit_alt
+    if kind == "NN":
+        m = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+        est0, est1 = m["MH"], m["MG"]
+    else:
+        est0 = est1 = _fit_alt(kind)
+    dm = models.DeviceModels(est0, est1)
+    X = _X(777, 13)
+    calls = np.zeros(len(X), dtype=_lib.CALL_DTYPE)
+    calls["feat"][:, :7] = X
+    calls["model_sel"] = np.arange(len(X)) % 2
+    calls["kind"][::50] = 1                       # non-call rows must be left untouched
+    d = torch.from_numpy(calls.view(np.uint8).reshape(-1).copy()).cuda()
+    _lib.check(cuda_lib.mc_classify(C.c_void_p(d.data_ptr()), len(X), dm.array, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    out = d.cpu().numpy().view(_lib.CALL_DTYPE)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        w0, w1 = est0.predict_proba(X)[:, 1], est1.predict_proba(X)[:, 1]
+    want = np.where(np.arange(len(X)) % 2 == 1, w1, w0)
+    live = calls["kind"] == 0
+    assert np.max(np.abs(out["prob"][live] - want[live])) < tol
+    assert np.array_equal(out["label"][live], (want[live] >= 0.5).astype(np.uint8))
+    assert np.all(out["prob"][~live] == 0)
+
+
+def test_histogram_matches_oracle_aggregation(tmp_path, cuda_lib, oracle):
+    """Device histogram (stage 7) == make_bed counts computed by the oracle from the rows of the same run."""
+    import json
+    from mcaller_b200 import engine
+    case, inp, ref, dm, two, qt = _setup("gatc_s2", tmp_path)
+    data = open(inp["tsv"], "rb").read()
+    eng = engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=2, two_models=two)
+    res = eng.run_chunk(eng.upload(data), len(data))
+    depth, meth, first = eng.histogram_host()
+    gold = json.load(open(os.path.join(gc.GOLD, "gatc_s2.json")))
+    rows = oracle.aggregate(gold["diffs"], 1, 0.0, False)
+    want = {}
+    for r in rows:
+        f = r.split("\t")
+        want[(f[0], int(f[1]), f[5])] = (int(f[6]), float(f[4]))
+    got = {}
+    order = np.argsort(first, kind="stable")
+    seen = []
+    for s in order:
+        if depth[s]:
+            key = (ref.names[ref.site_contig[s]], int(ref.site_pos[s]), "-" if ref.site_rev[s] else "+")
+            got[key] = (int(depth[s]), meth[s] / depth[s])
+            seen.append(key)
+    assert got == want
+    assert seen == [(r.split("\t")[0], int(r.split("\t")[1]), r.split("\t")[5]) for r in rows]     # first-seen order
+    assert int(depth.sum()) == eng.count_rows(res)["calls"]
+
+
+def test_device_workload_against_oracle_and_properties(cuda_lib, oracle):
+    """~120 MB of device-generated TSV: CUDA rows == oracle rows (keys exact, features and probabilities bit-equal), the
+    same workload streamed in chunks through pinned host memory gives the same totals, and histogram mass == calls."""
+    import torch
+    from mcaller_b200 import engine, models, read_qual, stream, synth, synth_device
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=9, contigs=[("ecoli", 400000)], n_reads=260, len_min=500, len_max=1500)
+    seqs = {"ecoli": synth.genome(spec, 0).tobytes().decode()}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    meth = {0: (synth.meth_sites(spec, 0, ref.site_fwd_bits[:400000]), synth.meth_sites(spec, 0, ref.site_rev_bits[:400000]))}
+    gen = synth_device.DeviceSynth(spec, ref, meth)
+    d_text, n, offs = gen.generate(0, spec.n_reads)
+    keys, q = synth_device.quality_table_for(spec)
+    quals = dict(zip(keys, q.tolist()))
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=1, two_models=True)
+    res = eng.run_chunk(d_text, n)
+    calls = res.calls()
+    host = d_text[:n].cpu().numpy().tobytes()
+    want = oracle.extract(host, seqs, quals, k=6, skip_thresh=1, model=model, base="A", motif="GATC", cap=200000)
+    mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
+    assert len(mine) == len(want["calls"]) > 1000
+    for c, w in zip(mine, want["calls"]):
+        assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"] and int(c["empty_mask"]) == w["empty_mask"]
+        assert host[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
+        assert [float(x) for x in c["feat"][:7]] == w["feat"]                 # bit-equal float64 features
+        assert abs(float(c["prob"]) - w["prob"]) < 1e-12 and int(c["label"]) == w["label"]
+    st = eng.count_rows(res)
+    assert st["calls"] == len(mine) and st["errors"] == 0
+    depth, _, _ = eng.histogram_host()
+    assert int(depth.sum()) == st["calls"]
+    assert st["too_many_skips"] == want["counters"]["too_many_skips"]
+    # the same bytes streamed from pinned host memory in read-aligned chunks
+    eng.reset_histogram()
+    hbuf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hbuf.copy_(d_text[:n])
+    torch.cuda.synchronize()
+    hs = stream.HostStreamer(eng, chunk_bytes=8 << 20)
+    cuts = stream.plan_chunks(offs.cpu().numpy(), n, hs.chunk_bytes)
+    assert len(cuts) > 5
+    tot = hs.run(hbuf, cuts)
+    assert tot["calls"] == st["calls"] + st["pending"] * 0 and tot["too_many_skips"] + 0 >= st["too_many_skips"] - 1
+    d2, _, _ = eng.histogram_host()
+    assert int(d2.sum()) + tot["pending_resolved"] == tot["calls"]
