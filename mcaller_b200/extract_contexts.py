@@ -71,27 +71,44 @@ def base_models(base, twobase=False):
 # ---- helpers -------------------------------------------------------------------------------------------------------
 
 def _line_name(buf, start):
-    """4th whitespace-separated field of the line starting at `start` (bytes) or None."""
+    """Read name (4th whitespace-separated field) of the line starting at `start`, or None for lines with fewer than
+    12 fields -- those are dropped by the tokeniser (:149-152) and must not look like read boundaries."""
     end = buf.find(b"\n", start)
     if end < 0:
         end = len(buf)
-    f = buf[start:end].split(None, 4)
-    return f[3] if len(f) > 3 else None
+    f = buf[start:end].split(None, 12)
+    return f[3] if len(f) >= 12 else None
 
 
 def read_boundary_before(buf, limit=None):
-    """Largest start s of a complete line of buf such that a new read begins at s (its name differs from the previous
-    line's); 0 if there is none.  Everything from s on (the possibly incomplete last read and any partial last line) is
-    meant to be carried into the next chunk."""
+    """Largest start s of a complete line of buf at which a new read begins (its name differs from the previous
+    well-formed line's); 0 if there is none.  Everything from s on (the possibly incomplete last read and any partial
+    last line) is meant to be carried into the next chunk."""
     end = buf.rfind(b"\n", 0, len(buf) if limit is None else limit) + 1       # end of the complete lines
     if end <= 0:
         return 0
     cur = buf.rfind(b"\n", 0, end - 1) + 1                                     # start of the last complete line
+    cur_name = _line_name(buf, cur)
     while cur > 0:
         prev = buf.rfind(b"\n", 0, cur - 1) + 1
-        if _line_name(buf, cur) != _line_name(buf, prev):
+        prev_name = _line_name(buf, prev)
+        if cur_name is None:                       # malformed line: transparent
+            cur, cur_name = prev, prev_name
+            continue
+        if prev_name is None:                      # skip malformed predecessors
+            p2 = prev
+            while p2 > 0 and prev_name is None:
+                p2 = buf.rfind(b"\n", 0, p2 - 1) + 1
+                prev_name = _line_name(buf, p2)
+            if prev_name is None:
+                return 0
+            if prev_name != cur_name:
+                return cur
+            cur, cur_name = p2, prev_name
+            continue
+        if cur_name != prev_name:
             return cur
-        cur = prev
+        cur, cur_name = prev, prev_name
     return 0
 
 
@@ -101,41 +118,58 @@ def read_boundary_after(fh, offset, fsize, probe=1 << 22):
         return 0
     if offset >= fsize:
         return fsize
+    # start far enough back to know the name of the last well-formed line before `offset`
     back = min(offset, 1 << 16)
     while True:
         fh.seek(offset - back)
         head = fh.read(back)
-        p = head.rfind(b"\n", 0, back - 1)       # newline before the line that holds byte offset-1
-        if p >= 0 or back == offset:
+        p = head.find(b"\n")
+        names = []
+        if p >= 0:
+            q = p + 1
+            while q < len(head):
+                e = head.find(b"\n", q)
+                if e < 0:
+                    break
+                nm = _line_name(head, q)
+                if nm is not None:
+                    names.append(nm)
+                q = e + 1
+        if names or back == offset:
             break
         back = min(offset, back * 4)
-    base = offset - back + (p + 1)               # file offset of the start of the line holding byte offset-1
+    if back == offset:
+        base, prev_name = 0, None
+    else:
+        # restart the scan at the first complete line of `head`
+        base, prev_name = offset - back + p + 1, None
     while True:
         fh.seek(base)
         buf = fh.read(probe)
         if not buf:
             return fsize
         at_eof = base + len(buf) >= fsize
-        prev_name = _line_name(buf, 0)
-        e = buf.find(b"\n")
-        cur = e + 1 if e >= 0 else len(buf)
-        last_complete = 0
+        cur = 0
+        last_complete = -1
         while cur < len(buf):
             e = buf.find(b"\n", cur)
             if e < 0 and not at_eof:
-                break                              # partial line: refill from the last complete line
+                break                              # partial line: refill starting at it
             nm = _line_name(buf, cur)
-            if base + cur >= offset and nm != prev_name:
-                return base + cur
-            prev_name = nm
+            if nm is not None:
+                if base + cur >= offset and prev_name is not None and nm != prev_name:
+                    return base + cur
+                if base + cur >= offset and prev_name is None and base + cur == 0:
+                    return 0
+                prev_name = nm
             last_complete = cur
             cur = (e + 1) if e >= 0 else len(buf)
         if at_eof:
             return fsize
-        if last_complete == 0:
+        if last_complete < 0:
             probe *= 4
         else:
-            base += last_complete
+            base += cur
 
 
 def _fmt(x):

@@ -51,7 +51,7 @@ def test_base_models_table():
     assert ec.base_models("A", False)["MG"] == "general"
 
 
-def _mk_tsv(n_reads, rnd):
+def _mk_tsv(n_reads, rnd, junk=False):
     lines, starts = [], []
     off = 0
     for r in range(n_reads):
@@ -60,12 +60,17 @@ def _mk_tsv(n_reads, rnd):
             ln = "ctg\t%d\tACGTAC\tread%04d_x\tt\t%d\t80.00\t1.0\t0.001\tACGTAC\t81.00\t1.5\t0.1\n" % (100 + j, r, j)
             lines.append(ln)
             off += len(ln)
+            if junk and rnd.random() < 0.3:          # malformed lines inside a read must not look like read boundaries
+                jl = rnd.choice(["\n", "ctg\t5\tAAA\tother\tt\n", "x y z\n"])
+                lines.append(jl)
+                off += len(jl)
     return "".join(lines).encode(), starts
 
 
-def test_read_boundary_helpers(tmp_path):
+@pytest.mark.parametrize("junk", [False, True])
+def test_read_boundary_helpers(tmp_path, junk):
     rnd = random.Random(5)
-    data, starts = _mk_tsv(40, rnd)
+    data, starts = _mk_tsv(40, rnd, junk)
     path = tmp_path / "x.tsv"
     path.write_bytes(data)
     sset = sorted(starts)
@@ -76,8 +81,8 @@ def test_read_boundary_helpers(tmp_path):
     for lim in [len(data), len(data) - 3, starts[7] + 5, starts[1] + 1, 10]:
         buf = data[:lim]
         comp_end = buf.rfind(b"\n") + 1
-        last_line = buf.rfind(b"\n", 0, comp_end - 1) + 1 if comp_end > 0 else 0
-        want = max([s for s in sset if s <= last_line and s < comp_end] + [0])
+        good = [i for i in range(comp_end) if (i == 0 or buf[i - 1:i] == b"\n") and len(buf[i:buf.find(b"\n", i)].split()) >= 12]
+        want = max([s for s in sset if good and s <= good[-1]] + [0])
         assert ec.read_boundary_before(buf) == want, lim
 
 
