@@ -30,9 +30,9 @@ extern "C" {
 
 #define MC_ABI_VERSION 1
 
-/* text tiles: one CTA tokenises MC_TILE_BYTES of TSV; the caller must keep MC_TEXT_PAD readable bytes,
+/* text chunks: one warp tokenises MC_TILE_BYTES of TSV; the caller must keep MC_TEXT_PAD readable bytes,
  * all '\n', after the last text byte (so a final line without newline and tile look-ahead are safe). */
-#define MC_TILE_BYTES 16384
+#define MC_TILE_BYTES 3712
 #define MC_TEXT_PAD 4096
 #define MC_MAXK 8            /* largest -n/--num_variables supported (reference default 6) */
 
@@ -84,12 +84,12 @@ typedef struct mc_record {
 enum {
     MC_C_LINES = 0,        /* lines owned by the scanned range */
     MC_C_KEPT,             /* >= 12 fields, known contig, model_kmer != NNNNNN */
-    MC_C_RECORDS,          /* records appended (allocation cursor) */
+    MC_C_RECORDS,          /* record slots reserved (allocation cursor, >= records written) */
     MC_C_SHORT,            /* lines with < 12 whitespace separated fields (:149-152) */
     MC_C_UNKNOWN_CONTIG,   /* contig not in the reference (:154-160) */
     MC_C_NNN,              /* model_kmer == 'NNNNNN' (:167) */
     MC_C_BADPOS,           /* column 2 not a non-negative integer on a known contig (reference: ValueError) */
-    MC_C_LONGLINE,         /* first 12 fields do not fit the tile look-ahead */
+    MC_C_LONGLINE,         /* lines whose first 12 columns outran the look-ahead and took the byte-wise slow path (informational) */
     MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
     MC_C_COUNT = 16
 };
@@ -170,8 +170,9 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * 'has M' test).  One CTA per MC_TILE_BYTES tile; a line belongs to the tile holding its first byte.
  * Emits a record for every kept line that is a candidate (k-mer window touches a target on either
  * strand), that follows a candidate, or that is the first kept line of its tile; with dense != 0 for
- * every kept line (needed with -q).  Records of one tile are contiguous and in line order; tiles
- * allocate from d_counters[MC_C_RECORDS]; d_tile_tab[tile] = {first record, count}.
+ * every kept line (needed with -q).  Records of one chunk are contiguous and in line order; warps reserve slots in
+ * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
+ * holes); d_tile_tab[chunk] = {first record slot, count}.
  * d_counters (MC_C_COUNT uint64) must be zeroed by the caller.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,
@@ -184,9 +185,11 @@ int64_t mc_num_tiles(int64_t nbytes);
 /* bytes of scratch needed by the scan-based stages below for up to n items */
 int64_t mc_workspace_bytes(int64_t n);
 
-/* Stage 2 -- put the records into file order (exclusive scan of the tile table + gather). */
-int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t n_records,
-                     mc_record *d_rec_out, void *d_ws, void *stream);
+/* Stage 2 -- put the records into file order (exclusive scan of the chunk table + gather).  d_rec_in is the stage-1
+ * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
+ * records, which land densely in d_rec_out (rec_out_cap slots; d_counters[MC_C_RECORDS] is an upper bound). */
+int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t rec_in_cap,
+                     mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the

@@ -132,14 +132,14 @@ namespace {
 
 // ---- stage 2: gather records into file order ----------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_dst,
-                                               int64_t n_tiles, const mc_record *__restrict__ in, mc_record *__restrict__ out,
-                                               unsigned long long n_records) {
+                                               int64_t n_tiles, const mc_record *__restrict__ in, unsigned long long in_cap,
+                                               mc_record *__restrict__ out, unsigned long long out_cap) {
     const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long src = tile_tab[2 * tile], cnt = tile_tab[2 * tile + 1], dst = tile_dst[tile];
     for (unsigned long long j = lane; j < cnt; j += 32) {
-        if (src + j >= n_records || dst + j >= n_records) break;   // records dropped by a capacity overflow
+        if (src + j >= in_cap || dst + j >= out_cap) break;          // records dropped by a capacity overflow
         const uint4 *s = reinterpret_cast<const uint4 *>(in + src + j);
         uint4 *d = reinterpret_cast<uint4 *>(out + dst + j);
         const uint4 a = s[0], b = s[1];
@@ -210,16 +210,19 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 
 }  // namespace
 
-extern "C" int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t n_records,
-                                mc_record *d_rec_out, void *d_ws, void *stream) {
-    MC_REQUIRE(d_tile_tab && d_rec_in && d_rec_out && d_ws, "null pointer");
-    if (n_tiles <= 0 || n_records <= 0) return MC_OK;
+extern "C" int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t rec_in_cap,
+                                mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
+    MC_REQUIRE(d_tile_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (n_tiles <= 0) {
+        MC_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, 8, st));
+        return MC_OK;
+    }
     uint32_t *dst = ws_a(d_ws);
-    int rc = exscan_strided(d_tile_tab + 1, 2, dst, n_tiles, nullptr, ws_s(d_ws, n_tiles), st);
+    int rc = exscan_strided(d_tile_tab + 1, 2, dst, n_tiles, d_n_out, ws_s(d_ws, n_tiles), st);
     if (rc) return rc;
-    k_gather<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(d_tile_tab, dst, n_tiles, d_rec_in, d_rec_out,
-                                                            (unsigned long long)n_records);
+    k_gather<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(d_tile_tab, dst, n_tiles, d_rec_in, (unsigned long long)rec_in_cap,
+                                                            d_rec_out, (unsigned long long)rec_out_cap);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

@@ -100,7 +100,10 @@ class Engine(object):
         n_tiles = L.mc_num_tiles(nbytes)
         tile_tab = self._buf("tile_tab", 8 * max(n_tiles, 1))
         if rec_cap is None:
-            rec_cap = (nbytes // 24 + 1024) if self.dense else (nbytes // 256 + n_tiles + 4096)
+            # sparse mode: ~3 records per 29-line chunk plus the 64-slot reservation blocks of the resident warps
+            slack = 256 * min(n_tiles, 8192) + 4096
+            rec_cap = (nbytes // 24 + slack) if self.dense else (nbytes // 1024 + 2 * n_tiles + slack)
+        rec_cap = min(rec_cap, 2 ** 32 - 2)
         while True:
             rec_a = self._buf("rec_a", 32 * rec_cap)
             self.d_small.zero_()
@@ -116,25 +119,33 @@ class Engine(object):
             cnt = self._read_small(0, MC_C_COUNT)
             if cnt[C_OVERFLOW] == 0 and cnt[C_RECORDS] <= rec_cap:
                 break
-            rec_cap = int(cnt[C_RECORDS]) + 1024          # exact size known now: redo the scan once
+            if rec_cap >= 2 ** 32 - 2:
+                raise _lib.McallerCudaError("chunk produces more than 2^32 records; use smaller chunks")
+            rec_cap = min(int(cnt[C_RECORDS]) + 256 * min(n_tiles, 8192) + 4096, 2 ** 32 - 2)      # demand known now: redo the scan once
         res.counters = {nm: int(cnt[i]) for i, nm in enumerate(_lib.COUNTER_NAMES)}
-        n_rec = int(cnt[C_RECORDS])
-        res.n_records = n_rec
+        reserved = int(cnt[C_RECORDS])
+        res.n_records = 0
         res.n_calls = 0
         res.n_segments = 0
         res.missing_quality = 0
         res.hist_skipped = 0
         res.calls_dev = None
+        if reserved == 0:
+            return res
+        ws = self._buf("ws", L.mc_workspace_bytes(max(reserved, n_tiles)))
+        rec_b = self._buf("rec_b", 32 * reserved)
+        check(L.mc_order_records(C.c_void_p(tile_tab.data_ptr()), n_tiles, C.c_void_p(rec_a.data_ptr()), rec_cap,
+                                 C.c_void_p(rec_b.data_ptr()), reserved, C.c_void_p(self.d_small.data_ptr() + 8 * 21),
+                                 C.c_void_p(ws.data_ptr()), st))
+        self.launches += 4                           # 3 scan kernels + gather
+        n_rec = int(self._read_small(21, 1)[0])
+        res.n_records = n_rec
         if n_rec == 0:
             return res
-        ws = self._buf("ws", L.mc_workspace_bytes(max(n_rec, n_tiles)))
-        rec_b = self._buf("rec_b", 32 * n_rec)
-        check(L.mc_order_records(C.c_void_p(tile_tab.data_ptr()), n_tiles, C.c_void_p(rec_a.data_ptr()), n_rec,
-                                 C.c_void_p(rec_b.data_ptr()), C.c_void_p(ws.data_ptr()), st))
         seg_start = self._buf("seg_start", 4 * (n_rec + 2))
         check(L.mc_segment_reads(C.c_void_p(d_text.data_ptr()), C.c_void_p(rec_b.data_ptr()), n_rec, C.c_void_p(seg_start.data_ptr()),
                                  C.c_void_p(self.d_small.data_ptr() + 8 * 16), C.c_void_p(ws.data_ptr()), st))
-        self.launches += 4 + 5                       # order: 3 scan kernels + gather; segmentation: flags + 3 + starts
+        self.launches += 5                           # segmentation: flags + 3 scan kernels + starts
         n_seg = int(self._read_small(16, 1)[0])
         res.n_segments = n_seg
         seg_qual = self._buf("seg_qual", 8 * n_seg)

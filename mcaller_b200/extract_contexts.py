@@ -363,8 +363,6 @@ def _raise_on_counters(res):
     c = res.counters
     if c["badpos"]:
         raise ValueError("%d lines on known contigs have a non-integer position column" % c["badpos"])
-    if c["longline"]:
-        raise ReferenceAbort("%d lines do not fit the 2 KB tile look-ahead" % c["longline"])
     if res.missing_quality:
         raise KeyError("%d reads of the eventalign file are missing from the fastq" % res.missing_quality)
 

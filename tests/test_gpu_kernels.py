@@ -185,7 +185,7 @@ def test_device_workload_against_oracle_and_properties(cuda_lib, oracle):
     host = d_text[:n].cpu().numpy().tobytes()
     want = oracle.extract(host, seqs, quals, k=6, skip_thresh=1, model=model, base="A", motif="GATC", cap=200000)
     mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
-    assert len(mine) == len(want["calls"]) > 1000
+    assert len(mine) == len(want["calls"]) > 500
     for c, w in zip(mine, want["calls"]):
         assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"] and int(c["empty_mask"]) == w["empty_mask"]
         assert host[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
