@@ -79,6 +79,7 @@ typedef struct mc_record {
 #define MC_RF_CAND 2u      /* k-mer window touches a target on either strand */
 #define MC_RF_BADNUM 4u    /* event/model mean not a plain decimal (<= 18 digits) */
 #define MC_RF_BADIDX 8u    /* event index not a plain integer */
+#define MC_RF_RAW 16u      /* stage-1 form: event_idx/diff still hold column offsets; cleared by mc_order_records */
 
 /* counters written by mc_scan (uint64 each) */
 enum {
@@ -172,7 +173,8 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * strand), that follows a candidate, or that is the first kept line of its tile; with dense != 0 for
  * every kept line (needed with -q).  Records of one chunk are contiguous and in line order; warps reserve slots in
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
- * holes); d_tile_tab[chunk] = {first record slot, count}.
+ * holes); d_tile_tab[chunk] = {first record slot, count | flags} (flags are consumed by mc_order_records, which also
+ * drops the chunk-first records whose predecessor line turns out not to be a candidate).
  * d_counters (MC_C_COUNT uint64) must be zeroed by the caller.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,
@@ -187,9 +189,12 @@ int64_t mc_workspace_bytes(int64_t n);
 
 /* Stage 2 -- put the records into file order (exclusive scan of the chunk table + gather).  d_rec_in is the stage-1
  * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
- * records, which land densely in d_rec_out (rec_out_cap slots; d_counters[MC_C_RECORDS] is an upper bound). */
-int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t rec_in_cap,
-                     mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
+ * records, which land densely in d_rec_out (rec_out_cap slots; d_counters[MC_C_RECORDS] is an upper bound).  Records arrive
+ * in raw form (column offsets, MC_RF_RAW) and are finished here, one thread per record: event index, the float64
+ * np.round(event_mean - model_mean, 4) from exact decimal parsing, and the k-mer equality flag (extract_contexts.py:150,
+ * :169, :286). */
+int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in,
+                     int64_t rec_in_cap, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the

@@ -78,7 +78,8 @@ _PROTOS = {
     "mc_scan": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RefIndex), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_num_tiles": (C.c_int64, [C.c_int64]),
     "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
-    "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
     "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_build_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RefIndex), C.c_int, C.c_double,

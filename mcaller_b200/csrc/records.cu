@@ -1,6 +1,6 @@
 // Stages 2-4: file-order gather of the stage-1 records, read segmentation, per-read quality lookup,
 // plus the generic exclusive scan they (and the window builder) share.
-#include "common.cuh"
+#include "parse.cuh"
 
 namespace {
 
@@ -131,14 +131,34 @@ static inline void *ws_s(void *ws, int64_t n) { return reinterpret_cast<uint8_t 
 namespace {
 
 // ---- stage 2: gather records into file order ----------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_dst,
-                                               int64_t n_tiles, const mc_record *__restrict__ in, unsigned long long in_cap,
-                                               mc_record *__restrict__ out, unsigned long long out_cap) {
-    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+// Stage 1 always records the first kept line of a chunk because the line before it belongs to another warp.  With all
+// chunks done the predecessor is known: the record is dropped unless the previous kept line was a candidate (or there
+// is none, so the first kept line of the text stays: it may close a window handed over by the caller).
+__global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ tile_tab, int64_t n_tiles, uint32_t *__restrict__ cnt_clean) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_tiles) return;
+    const uint32_t v = tile_tab[2 * c + 1];
+    uint32_t count = v & 0xFFFFu;
+    if ((v >> 16) & 1u) {
+        int64_t p = c - 1;
+        uint32_t st = 0u;
+        while (p >= 0 && (st = (tile_tab[2 * p + 1] >> 17) & 3u) == 0u) --p;
+        if (p >= 0 && st == 1u && count > 0u) {
+            tile_tab[2 * c] += 1u;           // skip the filler (it is the chunk's first record)
+            --count;
+        }
+    }
+    cnt_clean[c] = count;
+}
+
+__global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_cnt,
+                                               const uint32_t *__restrict__ tile_dst, int64_t n_tiles, const mc_record *__restrict__ in,
+                                               unsigned long long in_cap, mc_record *__restrict__ out, unsigned long long out_cap) {
+    // one thread per chunk: chunks hold a handful of records in sparse mode
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= n_tiles) return;
-    const int lane = threadIdx.x & 31;
-    const unsigned long long src = tile_tab[2 * tile], cnt = tile_tab[2 * tile + 1], dst = tile_dst[tile];
-    for (unsigned long long j = lane; j < cnt; j += 32) {
+    const unsigned long long src = tile_tab[2 * tile], cnt = tile_cnt[tile], dst = tile_dst[tile];
+    for (unsigned long long j = 0; j < cnt; ++j) {
         if (src + j >= in_cap || dst + j >= out_cap) break;          // records dropped by a capacity overflow
         const uint4 *s = reinterpret_cast<const uint4 *>(in + src + j);
         uint4 *d = reinterpret_cast<uint4 *>(out + dst + j);
@@ -146,6 +166,57 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ til
         d[0] = a;
         d[1] = b;
     }
+}
+
+// finish raw records in place (one thread per record): walk the line's columns in the text and parse what the window
+// builder needs -- read-name span (column 4), event index (6), np.round(event_mean - model_mean, 4) (7, 11) and the
+// k-mer equality flag (3 vs 10).  Columns split on runs of bytes <= 0x20 like str.split() (extract_contexts.py:150).
+__global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
+                                                       const unsigned long long *__restrict__ d_n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *d_n) return;
+    alignas(16) mc_record r = rec[i];
+    if (!(r.flags & MC_RF_RAW)) return;
+    const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
+    const GlobalBytes t{text + line, limit - line};
+    int nf = 0, f2 = 0, f3 = 0, name_end = 0, f5 = 0, f6 = 0, f9 = 0, f10 = 0;
+    bool in_tok = false;
+    for (int j = 0; j < (1 << 20); ++j) {
+        const int c = t[j];
+        if (c == 0x0a) { if (in_tok && nf == 4) name_end = j; break; }
+        const bool ws = c <= 0x20;
+        if (!ws && !in_tok) {
+            switch (nf) {
+                case 2: f2 = j; break;
+                case 3: f3 = j; break;
+                case 5: f5 = j; break;
+                case 6: f6 = j; break;
+                case 9: f9 = j; break;
+                case 10: f10 = j; break;
+                default: break;
+            }
+            ++nf;
+            in_tok = true;
+            if (nf == 11) break;
+        } else if (ws && in_tok) {
+            in_tok = false;
+            if (nf == 4) name_end = j;
+        }
+    }
+    uint32_t fl = r.flags & ~MC_RF_RAW;
+    int ev_idx = 0;
+    double diff = 0.0;
+    if (nf < 11 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;      // cannot happen for a kept line
+    else parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+    r.name_off = (uint16_t)f3;
+    r.name_len = (uint16_t)(name_end - f3);
+    r.event_idx = ev_idx;
+    r.diff = diff;
+    r.flags = (uint8_t)fl;
+    uint4 *dst = reinterpret_cast<uint4 *>(rec + i);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+    dst[0] = src[0];
+    dst[1] = src[1];
 }
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
@@ -210,19 +281,27 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 
 }  // namespace
 
-extern "C" int mc_order_records(const uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in, int64_t rec_in_cap,
-                                mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
-    MC_REQUIRE(d_tile_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
+extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles,
+                                const mc_record *d_rec_in, int64_t rec_in_cap, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out,
+                                void *d_ws, void *stream) {
+    MC_REQUIRE(d_text && d_tile_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles <= 0) {
         MC_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, 8, st));
         return MC_OK;
     }
-    uint32_t *dst = ws_a(d_ws);
-    int rc = exscan_strided(d_tile_tab + 1, 2, dst, n_tiles, d_n_out, ws_s(d_ws, n_tiles), st);
+    uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_tiles);
+    const unsigned nb = (unsigned)((n_tiles + 255) / 256);
+    k_resolve_fillers<<<nb, 256, 0, st>>>(d_tile_tab, n_tiles, cnt);
+    MC_LAUNCH_CHECK();
+    int rc = mc_exscan_u32(cnt, dst, n_tiles, d_n_out, ws_s(d_ws, n_tiles), st);
     if (rc) return rc;
-    k_gather<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(d_tile_tab, dst, n_tiles, d_rec_in, (unsigned long long)rec_in_cap,
-                                                            d_rec_out, (unsigned long long)rec_out_cap);
+    k_gather<<<nb, 256, 0, st>>>(d_tile_tab, cnt, dst, n_tiles, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
+                                 (unsigned long long)rec_out_cap);
+    MC_LAUNCH_CHECK();
+    // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
+    k_finish_records<<<(unsigned)((rec_out_cap + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
+                                                                            reinterpret_cast<const unsigned long long *>(d_n_out));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

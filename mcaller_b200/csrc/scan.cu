@@ -1,4 +1,5 @@
-// Stage 1 (K1): eventalign TSV tokeniser + line filter.  One WARP per 3712-byte text chunk, no block barriers.
+// Stage 1 (K1): eventalign TSV tokeniser + line filter.  One WARP per 3712-byte text chunk, no block barriers,
+// text staged by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the parse.
 //
 // Replaces the reader / tokeniser / per-line filters of the reference's extract_features
 // (extract_contexts.py:140-176): readlines + line.split()[:12], the '<12 fields' drop (:149-152),
@@ -6,20 +7,23 @@
 // test that gates everything after (:176, :242, :269).
 //
 // Per chunk (persistent warps stride over the chunks of the text):
-//   1. each lane pulls 4 x 32 B of the chunk (+32 B look-behind, +352 B look-ahead) with 16 B loads, classifies
-//      the bytes in registers (SWAR compare + IDP.4A bit packing) into two bit maps -- non-whitespace (byte > 0x20)
-//      and newline (byte == 0x0a) -- and parks text and bit maps in the warp's private shared-memory slice;
-//   2. field starts = nonws & ~(nonws << 1); line starts inside the chunk are compacted into a list with one warp scan;
-//   3. one lane per line: popcount-select on the field-start bits finds columns 2, 10 and 12 without touching the
-//      bytes in between (the ~58 B read name is never walked), the contig is resolved against a warp-uniform hint,
-//      column 2 is parsed and the per-position candidate bitmap (L1/L2 resident) is tested;
+//   0. lane 0 has already asked the TMA engine for the 4096 staged bytes of this chunk (32 B look-behind, the
+//      3712-byte chunk, 352 B look-ahead) while the previous chunk was being parsed; it now issues the copy of the
+//      warp's next chunk into the other buffer and the warp waits on this buffer's mbarrier;
+//   1. each lane classifies 4 x 32 B in registers (SWAR compare + IDP.4A bit packing) into two bit maps --
+//      non-whitespace (byte > 0x20) and newline (byte == 0x0a); field starts = nonws & ~(nonws << 1);
+//   2. line starts inside the chunk are compacted into a list with one warp scan, which also yields the running count
+//      of field starts per 32-byte word;
+//   3. one lane per line: rank/select on the field-start bits finds columns 1, 2, 10 and 12 without touching the bytes
+//      in between (the ~58 B read name is never walked); the contig is compared in registers against a warp-uniform
+//      hint, column 2 is parsed and the per-position candidate bitmap (L1/L2 resident) is tested;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the chunk, or
-//      every kept line in dense mode); only those are fully parsed (event index, currents as exact decimals ->
-//      float64 diff rounded like np.round(x, 4), k-mer equality, read-name span) into 32-byte records.  Record slots
-//      are reserved in blocks of 64 per warp, so the global allocation counter sees ~1 atomic per 20 chunks.
-// Lines whose first 12 columns do not fit the look-ahead take a byte-wise slow path straight from global memory.
-// Algorithmic HBM traffic: the text itself (once) + 32 B per record (~3 B per line in sparse mode).
-#include "common.cuh"
+//      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags}.  Their
+//      values (event index, currents, k-mer equality, read-name span) are parsed in stage 2 at full lane occupancy.
+//      Record slots are reserved per warp in blocks, so the global allocation counter sees ~1 atomic per 80 chunks.
+// Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
+// Algorithmic HBM traffic: the text itself (once) + 32 B per record (~2 B per line in sparse mode).
+#include "parse.cuh"
 
 namespace {
 
@@ -28,35 +32,66 @@ constexpr int LOOKB = 32;
 constexpr int LOOKA = 352;
 constexpr int WB = LOOKB + CHUNK + LOOKA;     // 4096 bytes staged per chunk
 constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
-constexpr int WARPS = 8;
-constexpr int THREADS = WARPS * 32;
-constexpr int LCAP = 64;                      // line-list capacity per pass
-constexpr int ECAP = 192;                     // queued record lines per chunk (a chunk holds <= 3712/23 keepable lines)
+#ifndef MC_SCAN_WARPS
+#define MC_SCAN_WARPS 7
+#endif
 #ifndef MC_SCAN_MIN_CTAS
 #define MC_SCAN_MIN_CTAS 3
 #endif
-constexpr int RESERVE = 256;                   // record slots reserved per global atomic
+constexpr int WARPS = MC_SCAN_WARPS;
+constexpr int THREADS = WARPS * 32;
+constexpr int LCAP = 32;                      // lines per pass (one per lane)
+constexpr int RESERVE = 256;                  // record slots reserved per global atomic
 static_assert(WB == 4096 && NW == 128, "chunk geometry");
 static_assert(CHUNK % 16 == 0, "chunks must keep 16-byte alignment");
 static_assert(MC_TEXT_PAD >= LOOKA + 64, "text padding must cover the look-ahead");
 
-__constant__ double c_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
-
 struct WarpSmem {
-    alignas(16) uint8_t text[WB + 16];
-    uint32_t nonws[NW + 4];
-    uint32_t fs[NW + 4];
-    uint32_t nl[NW + 4];
-    uint32_t ls[NW + 4];
-    uint16_t lstart[LCAP + 2];
+    alignas(128) uint8_t text[2][WB];    // double-buffered staged bytes (TMA destination)
+    alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
+    uint32_t nl[NW + 4];                 // newline bits
+    uint32_t ls[NW + 4];                 // line-start bits (owned range only)
+    uint16_t fcnt[NW + 4];               // field starts before each word (exclusive prefix over fs)
+    uint16_t lstart[LCAP + 4];
+    alignas(8) unsigned long long bar[2];
 };
+
+// ---- TMA / mbarrier wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: returns false if the phase never completes (reported through the overflow counter instead of hanging)
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
 
 // ---- byte classification ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t gt20_msb(uint32_t w) { return (((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u; }
 __device__ __forceinline__ uint32_t eq0a_msb(uint32_t w) {
-    const uint32_t x = w ^ 0x0a0a0a0au;
-    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    // low 7 bits of (byte ^ 0x0a) are zero and bit 7 of the byte is clear  <=>  byte == 0x0a
+    const uint32_t t = ((w ^ 0x0a0a0a0au) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | w) & 0x80808080u;
 }
 // 8 msb-form words (0x80 per flagged byte) -> 32 flag bits in byte order.  IDP.4A sums 0x80 * weight per byte: two
 // words fill bits 7..14 of one accumulator.
@@ -70,110 +105,16 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
     return (a >> 7) + b * 2u + c * 512u + d * 131072u;
 }
 
-// ---- byte sources: warp-private shared memory (fast path) or global memory (slow path) ---------------------------------
-struct SmemBytes {
-    const uint8_t *p;
-    __device__ __forceinline__ int operator[](int i) const { return p[i]; }
-};
-struct GlobalBytes {
-    const uint8_t *p;
-    int64_t limit;     // bytes readable from p
-    __device__ __forceinline__ int operator[](int64_t i) const { return i < limit ? __ldg(p + i) : 0x0a; }
-};
-
-template <class B>
-__device__ __forceinline__ bool contig_match(const B &t, int q, const mc_refindex &R, int cid) {
-    const int o0 = __ldg(R.d_name_off + cid), L = __ldg(R.d_name_off + cid + 1) - o0;
-    for (int j = 0; j < L; ++j)
-        if (t[q + j] != __ldg(R.d_names + o0 + j)) return false;
-    return t[q + L] <= 0x20;
+// ---- rank / select on the field-start bits -----------------------------------------------------------------------------------
+// position of the field start with rank n (0-based over the staged bytes), searching forward from word w;
+// NW*32 when it lies beyond the staged bytes
+__device__ __forceinline__ int select_fs(const WarpSmem &S, int &w, int n) {
+    while (w < NW && (int)S.fcnt[w + 1] <= n) ++w;
+    if (w >= NW) return NW * 32;
+    uint32_t m = S.fs[w];
+    for (int j = n - (int)S.fcnt[w]; j > 0; --j) m &= m - 1u;
+    return (w << 5) + __ffs(m) - 1;
 }
-template <class B>
-__device__ __forceinline__ int contig_cmp(const B &t, int q, const mc_refindex &R, int cid) {
-    const int o0 = __ldg(R.d_name_off + cid), L = __ldg(R.d_name_off + cid + 1) - o0;
-    for (int j = 0; j < L; ++j) {
-        const int a = t[q + j], b = __ldg(R.d_names + o0 + j);
-        if (a <= 0x20) return -1;
-        if (a != b) return a - b;
-    }
-    return t[q + L] <= 0x20 ? 0 : 1;
-}
-// contigs are sorted by name on the host: hint first, then binary search
-template <class B>
-__device__ __forceinline__ int contig_lookup(const B &t, int q, const mc_refindex &R, int hint) {
-    if (contig_match(t, q, R, hint)) return hint;
-    int lo = 0, hi = R.n_contigs - 1;
-    while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        const int c = contig_cmp(t, q, R, mid);
-        if (c == 0) return mid;
-        if (c < 0) hi = mid - 1; else lo = mid + 1;
-    }
-    return -1;
-}
-template <class B>
-__device__ __forceinline__ bool parse_uint(const B &t, int q, int &out) {
-    int v = 0, nd = 0, c;
-    while ((c = t[q]) >= '0' && c <= '9') { v = v * 10 + (c - '0'); ++nd; ++q; if (nd > 9) return false; }
-    if (nd == 0 || c > 0x20) return false;
-    out = v;
-    return true;
-}
-template <class B>
-__device__ __forceinline__ bool parse_int(const B &t, int q, int &out) {
-    bool neg = false;
-    if (t[q] == '-') { neg = true; ++q; } else if (t[q] == '+') ++q;
-    int v;
-    if (!parse_uint(t, q, v)) return false;
-    out = neg ? -v : v;
-    return true;
-}
-// plain decimal -> correctly rounded double (mantissa <= 2^53, <= 18 digits: one exact division)
-template <class B>
-__device__ __forceinline__ bool parse_decimal(const B &t, int q, double &out) {
-    bool neg = false;
-    int c = t[q];
-    if (c == '-') { neg = true; ++q; } else if (c == '+') ++q;
-    unsigned long long m = 0;
-    int nd = 0, nfrac = 0;
-    while ((c = t[q]) >= '0' && c <= '9') { m = m * 10ull + (unsigned)(c - '0'); ++nd; ++q; if (nd > 18) return false; }
-    if (c == '.') {
-        ++q;
-        while ((c = t[q]) >= '0' && c <= '9') { m = m * 10ull + (unsigned)(c - '0'); ++nd; ++nfrac; ++q; if (nd > 18) return false; }
-    }
-    if (nd == 0 || c > 0x20 || m > (1ull << 53)) return false;
-    const double v = __ddiv_rn((double)m, c_pow10[nfrac]);
-    out = neg ? -v : v;
-    return true;
-}
-template <class B>
-__device__ __forceinline__ bool is_nnnnnn(const B &t, int q) {
-    if (t[q] != 'N') return false;
-    return t[q + 1] == 'N' && t[q + 2] == 'N' && t[q + 3] == 'N' && t[q + 4] == 'N' && t[q + 5] == 'N' && t[q + 6] <= 0x20;
-}
-
-// ---- field location on the field-start bit map --------------------------------------------------------------------------
-struct FsCursor {
-    const uint32_t *fs;
-    int w;          // current word
-    uint32_t m;     // unconsumed bits of the current word
-    int before;     // field starts consumed in earlier words
-    __device__ __forceinline__ void init(const uint32_t *fs_, int s) { fs = fs_; w = s >> 5; m = fs[w] & (0xFFFFFFFFu << (s & 31)); before = 0; }
-    // position of the n-th (0-based, counted from the line start) field start; n must not decrease.  NW*32 if it lies
-    // beyond the staged bytes.
-    __device__ __forceinline__ int find(int n) {
-        int c = __popc(m);
-        while (before + c <= n) {
-            before += c;
-            if (++w >= NW) { m = 0u; return NW * 32; }
-            m = fs[w];
-            c = __popc(m);
-        }
-        uint32_t t = m;
-        for (int j = n - before; j > 0; --j) t &= t - 1u;
-        return (w << 5) + __ffs(t) - 1;
-    }
-};
 __device__ __forceinline__ int next_bit(const uint32_t *m, int q) {
     int w = q >> 5;
     uint32_t v = m[w] & (0xFFFFFFFFu << (q & 31));
@@ -183,97 +124,40 @@ __device__ __forceinline__ int next_bit(const uint32_t *m, int q) {
     }
     return (w << 5) + __ffs(v) - 1;
 }
-__device__ __forceinline__ int token_end(const uint32_t *nonws, int q) {
-    int w = q >> 5;
-    uint32_t v = ~nonws[w] & (0xFFFFFFFFu << (q & 31));
-    while (v == 0u) {
-        if (++w >= NW) return NW * 32;
-        v = ~nonws[w];
-    }
-    return (w << 5) + __ffs(v) - 1;
-}
 
-// result of the structural parse of one line
-struct LineHead {
-    int cid, pos;
-    uint32_t status;     // ST_*
-};
-enum { ST_KEPT = 1u, ST_CAND = 2u, ST_SHORT = 4u, ST_UNKNOWN = 8u, ST_NNN = 16u, ST_BADPOS = 32u, ST_SLOW = 64u };
-
-template <class B>
-__device__ __forceinline__ void classify_line(const B &t, int f0, int f1, int f9, const mc_refindex &R, int hint, int64_t hint_base,
-                                              int hint_len, LineHead &L) {
-    L.cid = contig_lookup(t, f0, R, hint);
-    if (L.cid < 0) { L.status = ST_UNKNOWN; return; }
-    if (is_nnnnnn(t, f9)) { L.status = ST_NNN; return; }
-    if (!parse_uint(t, f1, L.pos)) { L.status = ST_BADPOS; return; }
-    L.status = ST_KEPT;
-    const int len = (L.cid == hint) ? hint_len : __ldg(R.d_len + L.cid);
-    if (L.pos < len) {
-        const int64_t g = ((L.cid == hint) ? hint_base : __ldg(R.d_base + L.cid)) + L.pos;
-        if ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) L.status |= ST_CAND;
-    }
-}
-
-// full parse of an emitted line into a record; F[] = starts of fields 2,3,5,6,9,10, name_end = end of field 3
-template <class B>
-__device__ __forceinline__ void fill_record(const B &t, int64_t line_goff, int s, int f2, int f3, int name_end, int f5, int f6, int f9,
-                                            int f10, const LineHead &L, mc_record &r) {
-    r.line_lo = (uint32_t)(line_goff & 0xFFFFFFFFll);
-    r.line_hi = (uint16_t)(line_goff >> 32);
-    r.name_off = (uint16_t)(f3 - s);
-    r.name_len = (uint16_t)(name_end - f3);
-    r.pos = L.pos;
-    r.contig = (uint16_t)L.cid;
-    uint32_t fl = (L.status & ST_CAND) ? MC_RF_CAND : 0u;
-    int ev_idx = 0;
-    if (!parse_int(t, f5, ev_idx)) fl |= MC_RF_BADIDX;
-    r.event_idx = ev_idx;
-    double ev = 0.0, md = 0.0;
-    if (!parse_decimal(t, f6, ev) || !parse_decimal(t, f10, md)) { fl |= MC_RF_BADNUM; r.diff = 0.0; }
-    else r.diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);          // np.round(ev - model, 4)
-    {   // reference_kmer (col 3) == model_kmer (col 10)
-        int a = f2, b = f9;
-        bool eq = true;
-        for (;;) {
-            const int ca = t[a++], cb = t[b++];
-            const bool ea = ca <= 0x20, eb = cb <= 0x20;
-            if (ea || eb) { eq = ea && eb; break; }
-            if (ca != cb) { eq = false; break; }
-        }
-        if (eq) fl |= MC_RF_EQ;
-    }
-    r.flags = (uint8_t)fl;
-    r.pad[0] = r.pad[1] = r.pad[2] = 0;
-}
-
-// byte-wise field finder for the slow path: starts of fields 0..11 of the line at t[0..), -1 when the line ends first
-__device__ __noinline__ int slow_fields(const GlobalBytes &t, int64_t *f, int64_t *name_end) {
-    int nf = 0;
-    bool in_tok = false;
-    for (int64_t i = 0;; ++i) {
-        const int c = t[i];
-        if (c == 0x0a) { if (in_tok && nf == 4) *name_end = i; break; }
-        const bool ws = c <= 0x20;
-        if (!ws && !in_tok) { if (nf < 12) f[nf] = i; ++nf; in_tok = true; if (nf >= 13) break; }
-        else if (ws && in_tok) { in_tok = false; if (nf == 4) *name_end = i; if (nf >= 12) break; }
-    }
-    return nf;
-}
-
-// starts of the first 12 fields of the line at smem offset s, from the field-start bit map (NW*32 where the staged
-// bytes end first)
-__device__ __forceinline__ void extract_fields(const uint32_t *fs, int s, int (&F)[12]) {
-    int w = s >> 5;
-    uint32_t m = fs[w] & (0xFFFFFFFFu << (s & 31));
-    bool dead = false;
+// ---- field location: 160-bit window of field-start bits aligned at the line start, branch-free rank/select -------------
+__device__ __forceinline__ int nth_bit(uint32_t m, int j) {     // position of the j-th (0-based) set bit, j < popc(m)
 #pragma unroll
-    for (int f = 0; f < 12; ++f) {
-        while (m == 0u && !dead) {
-            if (++w >= NW) dead = true; else m = fs[w];
-        }
-        if (dead) F[f] = NW * 32;
-        else { F[f] = (w << 5) + __ffs(m) - 1; m &= m - 1u; }
+    for (int t = 0; t < 6; ++t)
+        if (j > t) m &= m - 1u;
+    for (int t = 6; t < j; ++t) m &= m - 1u;                     // words with more than 7 field starts: rare
+    return __ffs(m) - 1;
+}
+__device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11) {
+    const int w0 = s >> 5, sh = s & 31;
+    const uint32_t a0 = S.fs[w0], a1 = S.fs[w0 + 1], a2 = S.fs[w0 + 2], a3 = S.fs[w0 + 3], a4 = S.fs[w0 + 4], a5 = S.fs[w0 + 5];
+    const uint32_t W0 = __funnelshift_r(a0, a1, sh), W1 = __funnelshift_r(a1, a2, sh), W2 = __funnelshift_r(a2, a3, sh),
+                   W3 = __funnelshift_r(a3, a4, sh), W4 = __funnelshift_r(a4, a5, sh);
+    const int c0 = __popc(W0), c1 = c0 + __popc(W1), c2 = c1 + __popc(W2), c3 = c2 + __popc(W3), c4 = c3 + __popc(W4);
+    if (c4 >= 12) {
+        auto sel = [&](int k) {
+            const int wi = (k >= c0) + (k >= c1) + (k >= c2) + (k >= c3);
+            const uint32_t m = wi == 0 ? W0 : wi == 1 ? W1 : wi == 2 ? W2 : wi == 3 ? W3 : W4;
+            const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : wi == 3 ? c2 : c3;
+            return s + 32 * wi + nth_bit(m, k - base);
+        };
+        f0 = sel(0);
+        f1 = sel(1);
+        f9 = sel(9);
+        f11 = sel(11);
+    } else {
+        // fewer than 12 field starts within 160 bytes: short line or unusually wide columns -> generic walk
+        int w = w0;
+        const int k0 = (int)S.fcnt[w] + __popc(S.fs[w] & ((1u << sh) - 1u));
+        f0 = select_fs(S, w, k0);
+        f1 = select_fs(S, w, k0 + 1);
+        f9 = select_fs(S, w, k0 + 9);
+        f11 = select_fs(S, w, k0 + 11);
     }
 }
 
@@ -286,24 +170,51 @@ __device__ __forceinline__ unsigned long long load8(const uint8_t *text, int q) 
     return ((unsigned long long)hi << 32) | lo;
 }
 
-// the whole line handled from global memory (first 12 columns outran the staged look-ahead): status + record
-__device__ __noinline__ void line_from_global(const uint8_t *d_text, int64_t nbytes, int64_t goff, const mc_refindex &R, int hint,
-                                              int64_t hint_base, int hint_len, LineHead &L, mc_record &rec) {
-    const GlobalBytes GB{d_text + goff, nbytes + MC_TEXT_PAD - 64 - goff};
-    int64_t sf[12], name_end = 0;
-    const int nf = slow_fields(GB, sf, &name_end);
-    if (nf < 12) { L.status = ST_SHORT; return; }
-    classify_line(GB, (int)sf[0], (int)sf[1], (int)sf[9], R, hint, hint_base, hint_len, L);
-    if (L.status & ST_KEPT)
-        fill_record(GB, goff, 0, (int)sf[2], (int)sf[3], (int)name_end, (int)sf[5], (int)sf[6], (int)sf[9], (int)sf[10], L, rec);
-    L.status |= ST_SLOW;
+enum { ST_KEPT = 1u, ST_CAND = 2u, ST_SHORT = 4u, ST_UNKNOWN = 8u, ST_NNN = 16u, ST_BADPOS = 32u };
+
+// contig / NNNNNN / position / candidate test of one line whose columns 1, 2, 10 start at f0, f1, f9
+template <class B>
+__device__ __forceinline__ uint32_t classify_line(const B &t, int f0, int f1, int f9, const mc_refindex &R, int hint, int64_t hint_base,
+                                                  int hint_len, int known_cid, int &cid, int &pos) {
+    cid = known_cid >= 0 ? known_cid : contig_lookup(t, f0, R, hint);
+    if (cid < 0) return ST_UNKNOWN;
+    if (is_nnnnnn(t, f9)) return ST_NNN;
+    if (!parse_uint(t, f1, pos)) return ST_BADPOS;
+    uint32_t st = ST_KEPT;
+    const int len = (cid == hint) ? hint_len : __ldg(R.d_len + cid);
+    if (pos < len) {
+        const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
+        if ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) st |= ST_CAND;
+    }
+    return st;
+}
+
+// a line whose first 12 columns outran the staged look-ahead: byte-wise from global memory
+__device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int64_t limit, int64_t goff, const mc_refindex &R, int hint,
+                                                      int64_t hint_base, int hint_len, int &cid, int &pos) {
+    const GlobalBytes t{d_text + goff, limit - goff};
+    int nf = 0, f0 = 0, f1 = 0, f9 = 0;
+    bool in_tok = false;
+    for (int i = 0; i < (1 << 20); ++i) {
+        const int c = t[i];
+        if (c == 0x0a) break;
+        const bool ws = c <= 0x20;
+        if (!ws && !in_tok) {
+            if (nf == 0) f0 = i; else if (nf == 1) f1 = i; else if (nf == 9) f9 = i;
+            ++nf;
+            in_tok = true;
+            if (nf >= 12) break;
+        } else if (ws) in_tok = false;
+    }
+    if (nf < 12) return ST_SHORT;
+    return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, cid, pos);
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
 k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks, mc_refindex R, int dense,
        mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
        unsigned long long *__restrict__ d_counters) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
     const int64_t warp_global = (int64_t)blockIdx.x * WARPS + wib;
@@ -327,78 +238,113 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     };
     set_hint(0);
     unsigned long long slot_cur = 0ull, slot_end = 0ull;          // reserved record slots [cur, end)
-    // per-lane counters, reduced once at the end
     unsigned c_lines = 0, c_kept = 0, c_short = 0, c_unknown = 0, c_nnn = 0, c_badpos = 0, c_slow = 0, c_overflow = 0;
 
-    const SmemBytes T{S.text};
+    if (lane == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    uint32_t phase0 = 0u, phase1 = 0u;
+    const int64_t limit = nbytes + MC_TEXT_PAD - 64;              // bytes the slow path may read
 
-    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
-        const int64_t G0 = chunk * (int64_t)CHUNK - LOOKB;        // global offset of smem byte 0
-        const bool interior = G0 >= 0 && G0 + WB <= text_limit16 && G0 + WB <= nbytes;
-        __syncwarp();
-        // ---- 1. load + classify: lane owns words lane, lane+32, lane+64, lane+96 -----------------------------------
-        uint32_t prev_nonws_top = 0u, prev_nl_top = 0u;           // top bits of word 32r-1 (lane 31 of the previous round)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint4 va[2], vb[2];
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = 2 * half + rr;
-                const int64_t g = G0 + 32 * (32 * r + lane);
-                if (interior) {
-                    va[rr] = __ldcs(reinterpret_cast<const uint4 *>(d_text + g));
-                    vb[rr] = __ldcs(reinterpret_cast<const uint4 *>(d_text + g + 16));
-                } else {
-                    const uint4 nlv = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-                    va[rr] = (g >= 0 && g < text_limit16) ? __ldcs(reinterpret_cast<const uint4 *>(d_text + g)) : nlv;
-                    vb[rr] = (g + 16 >= 0 && g + 16 < text_limit16) ? __ldcs(reinterpret_cast<const uint4 *>(d_text + g + 16)) : nlv;
-                }
+    // stage a chunk: interior chunks by one TMA bulk copy (asynchronous), edge chunks by guarded loads (synchronous)
+    auto stage = [&](int64_t c, int b) -> bool {
+        const int64_t g0 = c * (int64_t)CHUNK - LOOKB;
+        if (g0 >= 0 && g0 + WB <= text_limit16) {
+            if (lane == 0) {
+                fence_proxy_async();                               // earlier generic reads of this buffer are done (__syncwarp)
+                tma_load_1d(S.text[b], d_text + g0, WB, &S.bar[b]);
             }
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = 2 * half + rr;
-                const int w = 32 * r + lane;
-                *reinterpret_cast<uint4 *>(S.text + 32 * w) = va[rr];
-                *reinterpret_cast<uint4 *>(S.text + 32 * w + 16) = vb[rr];
-                const uint32_t nonws = pack32(gt20_msb(va[rr].x), gt20_msb(va[rr].y), gt20_msb(va[rr].z), gt20_msb(va[rr].w),
-                                              gt20_msb(vb[rr].x), gt20_msb(vb[rr].y), gt20_msb(vb[rr].z), gt20_msb(vb[rr].w));
-                const uint32_t nl = pack32(eq0a_msb(va[rr].x), eq0a_msb(va[rr].y), eq0a_msb(va[rr].z), eq0a_msb(va[rr].w),
-                                           eq0a_msb(vb[rr].x), eq0a_msb(vb[rr].y), eq0a_msb(vb[rr].z), eq0a_msb(vb[rr].w));
-                // top bits of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
-                uint32_t pn = __shfl_up_sync(0xffffffffu, nonws >> 31, 1);
-                uint32_t pl = __shfl_up_sync(0xffffffffu, nl >> 31, 1);
-                if (lane == 0) { pn = prev_nonws_top; pl = prev_nl_top; }
-                prev_nonws_top = __shfl_sync(0xffffffffu, nonws >> 31, 31);
-                prev_nl_top = __shfl_sync(0xffffffffu, nl >> 31, 31);
-                S.nonws[w] = nonws;
-                S.nl[w] = nl;
-                S.fs[w] = nonws & ~((nonws << 1) | pn);
-                // line starts: byte p starts a line iff byte p-1 is '\n'; owned range LOOKB <= p < LOOKB+CHUNK, global p < nbytes
-                uint32_t ls = (nl << 1) | pl;
-                const int p0 = 32 * w;
-                if (p0 < LOOKB || p0 >= LOOKB + CHUNK) ls = 0u;   // LOOKB and CHUNK are multiples of 32: whole words
-                else if (!interior) {
-                    const int64_t room = nbytes - (G0 + p0);
-                    if (room <= 0) ls = 0u;
-                    else if (room < 32) ls &= (1u << room) - 1u;
-                }
-                S.ls[w] = ls;
-            }
+            return true;
         }
-        if (lane == 0) { S.nonws[NW] = 0u; S.fs[NW] = 0u; S.nl[NW] = 0xFFFFFFFFu; }
+        for (int i = lane; i < WB / 16; i += 32) {
+            const int64_t g = g0 + 16 * i;
+            uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+            if (g >= 0 && g < text_limit16) v = __ldg(reinterpret_cast<const uint4 *>(d_text + g));
+            *reinterpret_cast<uint4 *>(S.text[b] + 16 * i) = v;
+        }
+        return false;
+    };
+
+    int buf = 0;
+    bool cur_async = false;
+    if (warp_global < n_chunks) cur_async = stage(warp_global, 0);
+
+    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride, buf ^= 1) {
+        const int64_t G0 = chunk * (int64_t)CHUNK - LOOKB;        // global offset of staged byte 0
+        const bool tail = G0 + WB > nbytes;                       // chunk touches the end of the text
+        __syncwarp();
+        // ---- 0. prefetch the next chunk, wait for this one ----------------------------------------------------------------
+        const int64_t next = chunk + warp_stride;
+        bool next_async = false;
+        if (next < n_chunks) next_async = stage(next, buf ^ 1);
+        if (cur_async) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            if (!mbar_wait(&S.bar[buf], ph)) ++c_overflow;
+            if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+        }
+        __syncwarp();
+        const uint8_t *text = S.text[buf];
+        const SmemBytes T{text};
+
+        // ---- 1. classify: lane owns words lane, lane+32, lane+64, lane+96 ---------------------------------------------------
+        uint32_t prev_tops = 0u;                                  // top bits (nonws | nl << 1) of word 32r-1
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int w = 32 * r + lane;
+            const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
+            const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
+            const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x), gt20_msb(vb.y),
+                                          gt20_msb(vb.z), gt20_msb(vb.w));
+            const uint32_t nl = pack32(eq0a_msb(va.x), eq0a_msb(va.y), eq0a_msb(va.z), eq0a_msb(va.w), eq0a_msb(vb.x), eq0a_msb(vb.y),
+                                       eq0a_msb(vb.z), eq0a_msb(vb.w));
+            // top bits of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
+            const uint32_t tops = (nonws >> 31) | ((nl >> 31) << 1);
+            uint32_t pt = __shfl_up_sync(0xffffffffu, tops, 1);
+            if (lane == 0) pt = prev_tops;
+            prev_tops = __shfl_sync(0xffffffffu, tops, 31);
+            S.nl[w] = nl;
+            S.fs[w] = nonws & ~((nonws << 1) | (pt & 1u));
+            // line starts: byte p starts a line iff byte p-1 is '\n'; owned range LOOKB <= p < LOOKB+CHUNK, global p < nbytes
+            uint32_t ls = (nl << 1) | (pt >> 1);
+            const int p0 = 32 * w;
+            if (p0 < LOOKB || p0 >= LOOKB + CHUNK) ls = 0u;       // LOOKB and CHUNK are multiples of 32: whole words
+            else if (tail) {
+                const int64_t room = nbytes - (G0 + p0);
+                if (room <= 0) ls = 0u;
+                else if (room < 32) ls &= (1u << room) - 1u;
+            }
+            S.ls[w] = ls;
+        }
+        if (lane < 8) S.fs[NW + lane] = 0u;
+        if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
 
-        // ---- 2. ordered line list: lane owns words 4*lane .. 4*lane+3 -------------------------------------------------
+        // ---- 2. line list + field-start prefix counts: lane owns words 4*lane .. 4*lane+3 -------------------------------------
         const uint4 lsv = *reinterpret_cast<const uint4 *>(&S.ls[4 * lane]);
+        const uint4 fsv = *reinterpret_cast<const uint4 *>(&S.fs[4 * lane]);
+        const int pf0 = __popc(fsv.x), pf1 = __popc(fsv.y), pf2 = __popc(fsv.z), pf3 = __popc(fsv.w);
         const int my_cnt = __popc(lsv.x) + __popc(lsv.y) + __popc(lsv.z) + __popc(lsv.w);
-        int incl = my_cnt;
+        const int my_fs = pf0 + pf1 + pf2 + pf3;
+        int incl = my_cnt | (my_fs << 16);                         // both scans in one: lines low half, field starts high half
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int tt = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += tt;
         }
-        const int total_lines = __shfl_sync(0xffffffffu, incl, 31);
-        const int my_first = incl - my_cnt;
+        const int totals = __shfl_sync(0xffffffffu, incl, 31);
+        const int total_lines = totals & 0xFFFF;
+        const int my_first = (incl & 0xFFFF) - my_cnt;
+        const int my_first_fs = (incl >> 16) - my_fs;
+        {
+            // fcnt[w] = field starts before word w
+            const uint32_t a = (uint32_t)my_first_fs | ((uint32_t)(my_first_fs + pf0) << 16);
+            const uint32_t b = (uint32_t)(my_first_fs + pf0 + pf1) | ((uint32_t)(my_first_fs + pf0 + pf1 + pf2) << 16);
+            *reinterpret_cast<uint2 *>(&S.fcnt[4 * lane]) = make_uint2(a, b);
+            if (lane == 31) S.fcnt[NW] = (uint16_t)(my_first_fs + my_fs);
+        }
         c_lines += (lane == 0) ? (unsigned)total_lines : 0u;
 
         // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
@@ -412,6 +358,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         const unsigned long long chunk_base = slot_cur;
 
         int prev_state = -1;       // -1: no kept line yet in this chunk, 0: last kept line not a candidate, 1: candidate
+        uint32_t filler = 0u;      // the chunk's first record exists only because its predecessor line is in another chunk
         for (int pass0 = 0; pass0 < total_lines; pass0 += 32) {
             // list entries [pass0, pass0+33) (one extra so every lane knows where its line ends)
             {
@@ -431,72 +378,70 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             __syncwarp();
             const int n_pass = min(32, total_lines - pass0);
             // ---- 3. structural parse, one lane per line --------------------------------------------------------------
-            LineHead L;
-            L.cid = -1; L.pos = 0; L.status = 0u;
-            int s = 0;
-            int F[12];
-            alignas(16) mc_record rec;
+            uint32_t status = 0u;
+            int cid = -1, pos = 0, s = 0;
             if (lane < n_pass) {
                 s = S.lstart[lane];
                 const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : next_bit(S.nl, s);
-                extract_fields(S.fs, s, F);
-                if (F[11] < e) {
+                // columns 1, 2, 10, 12 from a 160-bit window of the field-start bits aligned at the line start
+                int f0, f1, f9, f11;
+                line_fields(S, s, f0, f1, f9, f11);
+                if (f11 < e) {
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
-                    const unsigned long long k8 = load8(S.text, F[0]);
-                    if (hint_keymask && (k8 & hint_keymask) == hint_key && ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull) L.cid = hint;
-                    else L.cid = contig_lookup(T, F[0], R, hint);
-                    if (L.cid < 0) L.status = ST_UNKNOWN;
-                    else if (is_nnnnnn(T, F[9])) L.status = ST_NNN;
-                    else if (!parse_uint(T, F[1], L.pos)) L.status = ST_BADPOS;
-                    else {
-                        L.status = ST_KEPT;
-                        const int len = (L.cid == hint) ? hint_len : __ldg(R.d_len + L.cid);
-                        if (L.pos < len) {
-                            const int64_t g = ((L.cid == hint) ? hint_base : __ldg(R.d_base + L.cid)) + L.pos;
-                            if ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) L.status |= ST_CAND;
-                        }
-                    }
-                } else if (e >= NW * 32 || F[11] >= NW * 32) {
-                    line_from_global(d_text, nbytes, G0 + s, R, hint, hint_base, hint_len, L, rec);
+                    const unsigned long long k8 = load8(text, f0);
+                    const bool hit = hint_keymask && (k8 & hint_keymask) == hint_key && ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull;
+                    status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, cid, pos);
+                } else if (e >= NW * 32 || f11 >= NW * 32) {
+                    status = classify_from_global(d_text, limit, G0 + s, R, hint, hint_base, hint_len, cid, pos);
                     ++c_slow;
                 } else {
-                    L.status = ST_SHORT;
+                    status = ST_SHORT;
                 }
             }
-            c_kept += (L.status & ST_KEPT) ? 1u : 0u;
-            c_short += (L.status & ST_SHORT) ? 1u : 0u;
-            c_unknown += (L.status & ST_UNKNOWN) ? 1u : 0u;
-            c_nnn += (L.status & ST_NNN) ? 1u : 0u;
-            c_badpos += (L.status & ST_BADPOS) ? 1u : 0u;
+            c_kept += (status & ST_KEPT) ? 1u : 0u;
+            c_short += (status & ST_SHORT) ? 1u : 0u;
+            c_unknown += (status & ST_UNKNOWN) ? 1u : 0u;
+            c_nnn += (status & ST_NNN) ? 1u : 0u;
+            c_badpos += (status & ST_BADPOS) ? 1u : 0u;
 
             // ---- 4. which lines matter: ballots over the 32 lines of this pass -----------------------------------------
-            const uint32_t kept_m = __ballot_sync(0xffffffffu, (L.status & ST_KEPT) != 0u);
-            const uint32_t cand_m = __ballot_sync(0xffffffffu, (L.status & ST_CAND) != 0u);
-            bool emit = false;
-            if (L.status & ST_KEPT) {
-                if (dense || (L.status & ST_CAND)) emit = true;
+            const uint32_t kept_m = __ballot_sync(0xffffffffu, (status & ST_KEPT) != 0u);
+            const uint32_t cand_m = __ballot_sync(0xffffffffu, (status & ST_CAND) != 0u);
+            bool emit = false, filler_lane = false;
+            if (status & ST_KEPT) {
+                if (dense || (status & ST_CAND)) emit = true;
                 else {
                     const uint32_t below = kept_m & lt_mask;
                     const int st = below ? (int)((cand_m >> (31 - __clz(below))) & 1u) : prev_state;
                     emit = (st != 0);            // predecessor is a candidate, or this is the first kept line of the chunk
+                    if (st < 0) filler_lane = true;
                 }
             }
             const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
+            if (__ballot_sync(0xffffffffu, filler_lane)) filler = 1u;
             if (kept_m) {
                 const int top = 31 - __clz(kept_m);
                 prev_state = (int)((cand_m >> top) & 1u);
-                const int new_hint = __shfl_sync(0xffffffffu, L.cid, top);     // contig hint follows the last kept line
+                const int new_hint = __shfl_sync(0xffffffffu, cid, top);       // contig hint follows the last kept line
                 if (new_hint != hint) set_hint(new_hint);
             }
-            // ---- 5. records: the emitting lanes finish the parse (values) and store ---------------------------------------
+            // ---- 5. raw records ------------------------------------------------------------------------------------------
             if (emit) {
-                if (!(L.status & ST_SLOW)) fill_record(T, G0 + s, s, F[2], F[3], token_end(S.nonws, F[3]), F[5], F[6], F[9], F[10], L, rec);
                 const unsigned long long slot = slot_cur + __popc(emit_m & lt_mask);
                 if (slot < rec_cap) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+                    const int64_t goff = G0 + s;
+                    const uint32_t fl = ((status & ST_CAND) ? MC_RF_CAND : 0u) | MC_RF_RAW;
+                    uint4 a, b;
+                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                   // line_lo
+                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                  // line_hi | name_off (0)
+                    a.z = (uint32_t)pos;                                     // pos
+                    a.w = 0u;                                                // event_idx
+                    b.x = 0u; b.y = 0u;                                      // diff
+                    b.z = (uint32_t)cid << 16;                               // name_len (0) | contig
+                    b.w = fl;                                                // flags | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
-                    dst[0] = src[0];
-                    dst[1] = src[1];
+                    dst[0] = a;
+                    dst[1] = b;
                 } else {
                     ++c_overflow;
                 }
@@ -506,8 +451,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         }
         if (lane == 0) {
             d_tile_tab[2 * chunk] = (uint32_t)chunk_base;
-            d_tile_tab[2 * chunk + 1] = (uint32_t)(slot_cur - chunk_base);
+            // count | filler flag | state of the chunk's last kept line (0 none, 1 not a candidate, 2 candidate)
+            d_tile_tab[2 * chunk + 1] = (uint32_t)(slot_cur - chunk_base) | (filler << 16) | ((uint32_t)(prev_state + 1) << 17);
         }
+        cur_async = next_async;
     }
 
     // ---- counters: one warp reduction per counter, one atomic per warp ----------------------------------------------------
@@ -548,9 +495,9 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     const size_t smem = sizeof(WarpSmem) * WARPS;
     MC_CUDA_CHECK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (n_chunks + WARPS - 1) / WARPS;
-    const int64_t resident = (int64_t)sms * MC_SCAN_MIN_CTAS;     // persistent: MC_SCAN_MIN_CTAS CTAs of 8 warps per SM
+    const int64_t resident = (int64_t)sms * MC_SCAN_MIN_CTAS;     // persistent: MC_SCAN_MIN_CTAS CTAs per SM
     if (blocks > resident) blocks = resident;
-    // 16-byte loads are allowed up to the end of the caller's '\n' padding
+    // 16-byte loads / bulk copies are allowed up to the end of the caller's '\n' padding
     const int64_t text_limit16 = ((nbytes + MC_TEXT_PAD) / 16) * 16;
     k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, *ref, dense, d_rec,
                                                                      (unsigned long long)rec_cap, d_tile_tab,

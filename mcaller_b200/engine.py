@@ -134,10 +134,10 @@ class Engine(object):
             return res
         ws = self._buf("ws", L.mc_workspace_bytes(max(reserved, n_tiles)))
         rec_b = self._buf("rec_b", 32 * reserved)
-        check(L.mc_order_records(C.c_void_p(tile_tab.data_ptr()), n_tiles, C.c_void_p(rec_a.data_ptr()), rec_cap,
+        check(L.mc_order_records(C.c_void_p(d_text.data_ptr()), nbytes, C.c_void_p(tile_tab.data_ptr()), n_tiles, C.c_void_p(rec_a.data_ptr()), rec_cap,
                                  C.c_void_p(rec_b.data_ptr()), reserved, C.c_void_p(self.d_small.data_ptr() + 8 * 21),
                                  C.c_void_p(ws.data_ptr()), st))
-        self.launches += 4                           # 3 scan kernels + gather
+        self.launches += 6                           # filler resolution + 3 scan kernels + gather + record finishing
         n_rec = int(self._read_small(21, 1)[0])
         res.n_records = n_rec
         if n_rec == 0:
