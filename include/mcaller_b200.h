@@ -32,7 +32,7 @@ extern "C" {
 
 /* text chunks: one warp tokenises MC_TILE_BYTES of TSV; the caller must keep MC_TEXT_PAD readable bytes,
  * all '\n', after the last text byte (so a final line without newline and tile look-ahead are safe). */
-#define MC_TILE_BYTES 3712
+#define MC_TILE_BYTES 3840
 #define MC_TEXT_PAD 4096
 #define MC_MAXK 8            /* largest -n/--num_variables supported (reference default 6) */
 

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcaller_b200.so")
 
-MC_TILE_BYTES = 3712
+MC_TILE_BYTES = 3840
 MC_TEXT_PAD = 4096
 MC_MAXK = 8
 MC_C_COUNT = 16

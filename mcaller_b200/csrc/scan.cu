@@ -1,4 +1,4 @@
-// Stage 1 (K1): eventalign TSV tokeniser + line filter.  One WARP per 3712-byte text chunk, no block barriers,
+// Stage 1 (K1): eventalign TSV tokeniser + line filter.  One WARP per 3840-byte text chunk, no block barriers,
 // text staged by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the parse.
 //
 // Replaces the reader / tokeniser / per-line filters of the reference's extract_features
@@ -8,7 +8,7 @@
 //
 // Per chunk (persistent warps stride over the chunks of the text):
 //   0. lane 0 has already asked the TMA engine for the 4096 staged bytes of this chunk (32 B look-behind, the
-//      3712-byte chunk, 352 B look-ahead) while the previous chunk was being parsed; it now issues the copy of the
+//      3840-byte chunk, 224 B look-ahead) while the previous chunk was being parsed; it now issues the copy of the
 //      warp's next chunk into the other buffer and the warp waits on this buffer's mbarrier;
 //   1. each lane classifies 4 x 32 B in registers (SWAR compare + IDP.4A bit packing) into two bit maps --
 //      non-whitespace (byte > 0x20) and newline (byte == 0x0a); field starts = nonws & ~(nonws << 1);
@@ -27,9 +27,9 @@
 
 namespace {
 
-constexpr int CHUNK = MC_TILE_BYTES;          // 3712 = 29 * 128: ~29 lines of ~128 B, one per lane
+constexpr int CHUNK = MC_TILE_BYTES;          // 3840 = 30 * 128: ~30 lines of ~128 B, one per lane
 constexpr int LOOKB = 32;
-constexpr int LOOKA = 352;
+constexpr int LOOKA = 224;
 constexpr int WB = LOOKB + CHUNK + LOOKA;     // 4096 bytes staged per chunk
 constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_WARPS
@@ -146,8 +146,13 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
             const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : wi == 3 ? c2 : c3;
             return s + 32 * wi + nth_bit(m, k - base);
         };
-        f0 = sel(0);
-        f1 = sel(1);
+        if ((W0 & 1u) && c0 >= 2) {          // the line starts with its first column and the second starts within 32 bytes
+            f0 = s;
+            f1 = s + __ffs(W0 & (W0 - 1u)) - 1;
+        } else {
+            f0 = sel(0);
+            f1 = sel(1);
+        }
         f9 = sel(9);
         f11 = sel(11);
     } else {

@@ -155,7 +155,7 @@ def test_c_abi_exports_match_header():
         assert hasattr(lib, fn), fn
     assert declared == set(_lib.EXPORTS)
     assert lib.mc_version() == 1
-    assert lib.mc_num_tiles(1) == 1 and lib.mc_num_tiles(3712) == 1 and lib.mc_num_tiles(3713) == 2
+    assert lib.mc_num_tiles(1) == 1 and lib.mc_num_tiles(3840) == 1 and lib.mc_num_tiles(3841) == 2
     assert lib.mc_workspace_bytes(1000) > 8000
 
 
