@@ -26,18 +26,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None):
+    if out is None and not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    extra = os.environ.get("MC_NVCC_EXTRA", "").split()          # e.g. "-DMC_SCAN_WARPS=10 -DMC_SCAN_MIN_CTAS=2" for tuning runs
+    cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + srcs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout)
     if res.returncode:
         raise RuntimeError("nvcc failed building libmcaller_b200.so")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

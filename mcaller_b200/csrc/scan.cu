@@ -33,10 +33,10 @@ constexpr int LOOKA = 224;
 constexpr int WB = LOOKB + CHUNK + LOOKA;     // 4096 bytes staged per chunk
 constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_WARPS
-#define MC_SCAN_WARPS 7
+#define MC_SCAN_WARPS 10
 #endif
 #ifndef MC_SCAN_MIN_CTAS
-#define MC_SCAN_MIN_CTAS 3
+#define MC_SCAN_MIN_CTAS 2
 #endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
