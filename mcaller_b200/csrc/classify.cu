@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int MAX_WIDTH = 512;     // widest MLP layer supported
-constexpr int WARPS = 4;
+constexpr int WARPS = 8;
 
 __device__ __forceinline__ double expit(double x) { return x < 0.0 ? exp(x) / (1.0 + exp(x)) : 1.0 / (1.0 + exp(-x)); }
 
@@ -27,15 +27,15 @@ __device__ __forceinline__ double activate(double v, int act) {
 // sklearn MLPClassifier._forward_pass_fast (neural_network/_multilayer_perceptron.py) for a binary classifier:
 // hidden activations, logistic output, P(class 1) = expit(z)
 __global__ void __launch_bounds__(WARPS * 32)
-k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1) {
-    __shared__ double s_act[WARPS][2][MAX_WIDTH];
+k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int width) {
+    extern __shared__ __align__(16) double s_act[];          // [WARPS][2][width]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * WARPS + warp;
     if (i >= n) return;
     mc_call &c = calls[i];
     if (c.kind != MC_CALL) return;
     const mc_model &m = c.model_sel ? m1 : m0;
-    double *a = s_act[warp][0], *b = s_act[warp][1];
+    double *a = s_act + (size_t)warp * 2 * width, *b = a + width;
     if (lane < m.sizes[0]) a[lane] = c.feat[lane];
     __syncwarp();
     const double *w = m.d_weights, *bi = m.d_biases;
@@ -215,7 +215,12 @@ extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *mo
             MC_REQUIRE(m0.n_layers >= 1 && m0.n_layers < 8, "MLP depth out of range");
             for (int l = 0; l <= m0.n_layers; ++l) MC_REQUIRE(m0.sizes[l] >= 1 && m0.sizes[l] <= MAX_WIDTH, "MLP layer too wide");
             MC_REQUIRE(m0.sizes[m0.n_layers] == 1, "MLP must have one logistic output");
-            k_mlp<<<(unsigned)((n_calls + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d_calls, n_calls, m0, m1);
+            int width = 8;
+            for (int l = 0; l <= m0.n_layers; ++l) width = m0.sizes[l] > width ? m0.sizes[l] : width;
+            for (int l = 0; l <= m1.n_layers && m1.kind == MC_MLP; ++l) width = m1.sizes[l] > width ? m1.sizes[l] : width;
+            width = (width + 3) & ~3;
+            const size_t smem = sizeof(double) * 2 * (size_t)width * WARPS;
+            k_mlp<<<(unsigned)((n_calls + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(d_calls, n_calls, m0, m1, width);
             break;
         }
         case MC_LR:

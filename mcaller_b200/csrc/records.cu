@@ -171,6 +171,18 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ til
 // finish raw records in place (one thread per record): walk the line's columns in the text and parse what the window
 // builder needs -- read-name span (column 4), event index (6), np.round(event_mean - model_mean, 4) (7, 11) and the
 // k-mer equality flag (3 vs 10).  Columns split on runs of bytes <= 0x20 like str.split() (extract_contexts.py:150).
+// The walk classifies 16 aligned bytes per step (SWAR compare + IDP.4A packing, as in stage 1) instead of looping bytes.
+__device__ __forceinline__ uint32_t fin_gt20(uint32_t w) { return (((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u; }
+__device__ __forceinline__ uint32_t fin_eq0a(uint32_t w) {
+    const uint32_t t = ((w ^ 0x0a0a0a0au) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | w) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t fin_pack16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    const uint32_t lo = 0x08040201u, hi = 0x80402010u;
+    const uint32_t a = __dp4a(m1, hi, __dp4a(m0, lo, 0u)), b = __dp4a(m3, hi, __dp4a(m2, lo, 0u));
+    return (a >> 7) | (b << 1);
+}
+
 __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
                                                        const unsigned long long *__restrict__ d_n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,38 +190,66 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
     alignas(16) mc_record r = rec[i];
     if (!(r.flags & MC_RF_RAW)) return;
     const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
-    const GlobalBytes t{text + line, limit - line};
-    int nf = 0, f2 = 0, f3 = 0, name_end = 0, f5 = 0, f6 = 0, f9 = 0, f10 = 0;
-    bool in_tok = false;
-    for (int j = 0; j < (1 << 20); ++j) {
-        const int c = t[j];
-        if (c == 0x0a) { if (in_tok && nf == 4) name_end = j; break; }
-        const bool ws = c <= 0x20;
-        if (!ws && !in_tok) {
+    // 16-byte steps from the aligned address at or below the line start; the '\n' padding after the text makes every
+    // line end inside readable memory
+    const int64_t a0 = line & ~15ll;
+    const int skip = (int)(line - a0);
+    int nf = 0, f2 = 0, f3 = 0, name_end = -1, f5 = 0, f6 = 0, f9 = 0, f10 = 0;
+    uint32_t prev_nonws = 0u;          // was the byte before this step non-whitespace (the byte before the line is '\n')
+    bool done = false;
+    for (int step = 0; step < (1 << 16) && !done; ++step) {
+        const int64_t g = a0 + 16ll * step;
+        if (g >= limit) break;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + g));
+        uint32_t nonws = fin_pack16(fin_gt20(v.x), fin_gt20(v.y), fin_gt20(v.z), fin_gt20(v.w));
+        uint32_t nl = fin_pack16(fin_eq0a(v.x), fin_eq0a(v.y), fin_eq0a(v.z), fin_eq0a(v.w));
+        if (step == 0) {                // ignore the bytes before the line start
+            const uint32_t keep = 0xFFFFu << skip;
+            nonws &= keep;
+            nl &= keep;
+        }
+        uint32_t valid = 0xFFFFu;
+        if (nl) {                       // stop at the newline
+            valid = (1u << (__ffs(nl) - 1)) - 1u;
+            done = true;
+        }
+        const int base = 16 * step - skip;                       // line-relative offset of byte 0 of this step
+        uint32_t fs = nonws & ~((nonws << 1) | prev_nonws) & valid;
+        if (name_end < 0 && nf >= 4) {                           // first whitespace (or the newline) after the read name
+            const uint32_t z = ~nonws & 0xFFFFu & ((step == 0) ? (0xFFFFu << skip) : 0xFFFFu);
+            const uint32_t zz = z & ~((1u << max(f3 - base, 0)) - 1u);
+            if (zz) name_end = base + __ffs(zz) - 1;
+        }
+        while (fs) {
+            const int b = __ffs(fs) - 1;
+            fs &= fs - 1u;
+            const int pos = base + b;
             switch (nf) {
-                case 2: f2 = j; break;
-                case 3: f3 = j; break;
-                case 5: f5 = j; break;
-                case 6: f6 = j; break;
-                case 9: f9 = j; break;
-                case 10: f10 = j; break;
+                case 2: f2 = pos; break;
+                case 3: f3 = pos; break;
+                case 5: f5 = pos; break;
+                case 6: f6 = pos; break;
+                case 9: f9 = pos; break;
+                case 10: f10 = pos; break;
                 default: break;
             }
             ++nf;
-            in_tok = true;
-            if (nf == 11) break;
-        } else if (ws && in_tok) {
-            in_tok = false;
-            if (nf == 4) name_end = j;
+            if (nf == 4 && name_end < 0) {                       // the name may end inside this same step
+                const uint32_t z = ~nonws & 0xFFFFu & ~((1u << b) - 1u);
+                if (z) name_end = base + __ffs(z) - 1;
+            }
+            if (nf == 11) { done = true; break; }
         }
+        prev_nonws = (nonws >> 15) & 1u;
     }
+    const GlobalBytes t{text + line, limit - line};
     uint32_t fl = r.flags & ~MC_RF_RAW;
     int ev_idx = 0;
     double diff = 0.0;
-    if (nf < 11 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;      // cannot happen for a kept line
+    if (nf < 11 || name_end < 0 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;   // cannot happen for a kept line
     else parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
     r.name_off = (uint16_t)f3;
-    r.name_len = (uint16_t)(name_end - f3);
+    r.name_len = (uint16_t)(name_end < 0 ? 0 : name_end - f3);
     r.event_idx = ev_idx;
     r.diff = diff;
     r.flags = (uint8_t)fl;
@@ -222,6 +262,17 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
 
+// 8 bytes at any alignment from two aligned 8-byte loads
+__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+    const int sh = 8 * (int)(a & 7);
+    const unsigned long long lo = __ldg(q);
+    if (sh == 0) return lo;
+    const unsigned long long hi = __ldg(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
 __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n,
                                                   uint32_t *__restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,10 +282,15 @@ __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ t
         const mc_record a = rec[i - 1], b = rec[i];
         if (a.name_len == b.name_len) {
             const uint8_t *pa = text + rec_line(a) + a.name_off, *pb = text + rec_line(b) + b.name_off;
-            int j = 0;
             const int L = a.name_len;
-            while (j < L && __ldg(pa + j) == __ldg(pb + j)) ++j;
-            f = (j < L) ? 1u : 0u;
+            unsigned long long diff = 0ull;
+            int j = 0;
+            for (; j + 8 <= L && diff == 0ull; j += 8) diff = load8_unaligned(pa + j) ^ load8_unaligned(pb + j);
+            if (diff == 0ull && j < L) {
+                const unsigned long long m = (1ull << (8 * (L - j))) - 1ull;       // 1..7 tail bytes (padding keeps the loads legal)
+                diff = (load8_unaligned(pa + j) ^ load8_unaligned(pb + j)) & m;
+            }
+            f = diff ? 1u : 0u;
         }
     }
     flags[i] = f;

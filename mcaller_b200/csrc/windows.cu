@@ -204,8 +204,10 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
         for (int c = 0; c < MC_MAXK; ++c) C.cnt[c] = 0;
     };
 
+    mc_record r_next = (b < e) ? load_rec(rec + b) : mc_record();
     for (uint32_t i = b; i < e; ++i) {
-        const mc_record r = load_rec(rec + i);
+        const mc_record r = r_next;
+        if (i + 1 < e) r_next = load_rec(rec + i + 1);              // overlap the next record's latency with this one's work
         const bool same_read = started;
         if (!same_read) {                                          // :161-162
             first_ind = r.event_idx;
