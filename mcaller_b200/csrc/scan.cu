@@ -153,8 +153,22 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
             f0 = sel(0);
             f1 = sel(1);
         }
-        f9 = sel(9);
-        f11 = sel(11);
+        if (c2 <= 9 && c3 > 11) {
+            // usual layout (a ~128-byte line): columns 10 and 12 both start inside the fourth window word
+            uint32_t m = W3;
+            const int j = 9 - c2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (j > t) m &= m - 1u;
+            for (int t = 4; t < j; ++t) m &= m - 1u;
+            f9 = s + 96 + __ffs(m) - 1;
+            m &= m - 1u;
+            m &= m - 1u;
+            f11 = s + 96 + __ffs(m) - 1;
+        } else {
+            f9 = sel(9);
+            f11 = sel(11);
+        }
     } else {
         // fewer than 12 field starts within 160 bytes: short line or unusually wide columns -> generic walk
         int w = w0;
@@ -368,15 +382,31 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // list entries [pass0, pass0+33) (one extra so every lane knows where its line ends)
             {
                 int idx = my_first - pass0;
-                const uint32_t wv[4] = {lsv.x, lsv.y, lsv.z, lsv.w};
+                uint32_t w0 = lsv.x, w1 = lsv.y, w2 = lsv.z, w3 = lsv.w;
+                if (my_cnt <= 2) {
+                    // usual case, no loops: at most two line starts inside this lane's 128 bytes
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t m = wv[j];
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1u;
-                        if (idx >= 0 && idx <= 32) S.lstart[idx] = (uint16_t)(32 * (4 * lane + j) + b);
-                        ++idx;
+                    for (int t = 0; t < 2; ++t) {
+                        if (t < my_cnt) {
+                            const int jw = w0 ? 0 : w1 ? 1 : w2 ? 2 : 3;
+                            const uint32_t m = w0 ? w0 : w1 ? w1 : w2 ? w2 : w3;
+                            if (idx >= 0 && idx <= 32) S.lstart[idx] = (uint16_t)(32 * (4 * lane + jw) + __ffs(m) - 1);
+                            ++idx;
+                            const uint32_t cl = m & (m - 1u);
+                            if (jw == 0) w0 = cl; else if (jw == 1) w1 = cl; else if (jw == 2) w2 = cl; else w3 = cl;
+                        }
+                    }
+                } else {
+                    const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t m = wv[j];
+                        while (m) {
+                            const int b = __ffs(m) - 1;
+                            m &= m - 1u;
+                            if (idx >= 0 && idx <= 32) S.lstart[idx] = (uint16_t)(32 * (4 * lane + j) + b);
+                            ++idx;
+                        }
                     }
                 }
             }
