@@ -208,3 +208,65 @@ def test_device_workload_against_oracle_and_properties(cuda_lib, oracle):
     assert tot["calls"] == st["calls"] + st["pending"] * 0 and tot["too_many_skips"] + 0 >= st["too_many_skips"] - 1
     d2, _, _ = eng.histogram_host()
     assert int(d2.sum()) + tot["pending_resolved"] == tot["calls"]
+
+
+def _rename_reads(tsv, quals, style, seed):
+    """Rewrite read names (column 4) to stress line layouts: 'short' -> ~70-byte lines (more than 32 lines per
+    chunk: multi-pass), 'long' -> 420-byte names (first 12 columns outrun the look-ahead: global-memory slow path),
+    'mixed' -> both plus normal names."""
+    import random
+    rnd = random.Random(seed)
+    mapping, new_quals, out = {}, {}, []
+    for ln in tsv.decode().split("\n"):
+        f = ln.split("\t")
+        if len(f) < 13:
+            out.append(ln)
+            continue
+        old = f[3]
+        if old not in mapping:
+            kind = style if style != "mixed" else rnd.choice(["short", "long", "normal", "wide"])
+            i = len(mapping)
+            if kind == "short":
+                nm = "r%d" % i
+            elif kind == "long":
+                nm = "L%d-" % i + "x" * 420
+            elif kind == "wide":
+                nm = "W%d-" % i + "y" * 170          # columns 10/12 beyond the 160-byte window, inside the look-ahead
+            else:
+                nm = old
+            mapping[old] = nm
+            new_quals[nm.split(":")[0].split("_")[0]] = quals[old.split(":")[0].split("_")[0]]
+        f[3] = mapping[old]
+        out.append("\t".join(f))
+    return "\n".join(out).encode(), new_quals
+
+
+@pytest.mark.parametrize("style", ["short", "long", "mixed"])
+def test_odd_line_layouts_match_oracle(style, cuda_lib, oracle):
+    from mcaller_b200 import engine, models, read_qual, synth
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=31, contigs=[("a_rather_long_contig_name|quiver", 9000), ("b", 7000)], n_reads=40, len_min=200, len_max=700)
+    tsv, fasta, fastq, quals = synth.generate(spec)
+    quals = {k.split("_")[0]: v for k, v in quals.items()}
+    tsv, quals = _rename_reads(tsv, quals, style, 5)
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    want = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=1, model=model, base="A", motif="GATC", cap=100000)
+    for dense in (False, True):
+        eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=1, two_models=True, dense=dense)
+        res = eng.run_chunk(eng.upload(tsv), len(tsv))
+        assert res.missing_quality == 0
+        if style in ("long", "mixed"):
+            assert res.counters["longline"] > 0          # the slow path really ran
+        calls = res.calls()
+        mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
+        assert len(mine) == len(want["calls"]) > 50
+        for c, w in zip(mine, want["calls"]):
+            assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"]
+            assert tsv[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
+            assert [float(x) for x in c["feat"][:7]] == w["feat"]
+            assert abs(float(c["prob"]) - w["prob"]) < 1e-12
+        st = eng.count_rows(res)
+        assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["errors"] == 0
