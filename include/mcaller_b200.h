@@ -260,6 +260,22 @@ typedef struct mc_locus_entry {
 int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_table, int64_t table_size,
                        uint64_t *d_counters, void *stream);
 
+/*
+ * FASTQ read-quality ingest (reference read_qual.py:6-19) on the device.  mc_fastq_index builds the byte offset of every
+ * line start (d_line_start[0] = 0, capacity line_cap; *d_n_newlines = number of '\n' in the buffer; d_tile_cnt/d_tile_off
+ * hold mc_fastq_tiles(nbytes) uint32 each, d_ws >= mc_workspace_bytes(tiles)).  The buffer must be readable up to the next
+ * multiple of 16 bytes.  mc_fastq_quality then treats lines 4r..4r+3 as record r (d_line_start[n_lines] must hold the offset
+ * one past the newline that ends the last line -- nbytes + 1 when the file has no final newline) and inserts
+ * {id.split(':')[0].split('_')[0] -> mean(ord(c) - 33 over the quality line)} into the open-addressing table probed by
+ * mc_segment_quality (d_owner: uint32[table_size], zeroed; d_rec_mean: double[n_lines/4] scratch; the last record with a
+ * given key wins, like the reference's dict).  d_stats[3]: records inserted, records whose header does not start with '@', inserts dropped (table full).
+ */
+int64_t mc_fastq_tiles(int64_t nbytes);
+int mc_fastq_index(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_cnt, uint32_t *d_tile_off, uint64_t *d_line_start,
+                   int64_t line_cap, uint64_t *d_n_newlines, void *d_ws, void *stream);
+int mc_fastq_quality(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_line_start, int64_t n_lines, mc_qual_entry *d_table,
+                     int64_t table_size, uint32_t *d_owner, double *d_rec_mean, uint64_t *d_stats, void *stream);
+
 /* ---- synthetic eventalign generator (bench / test tooling; bit-identical to mcaller_b200/synth.py) ---- */
 typedef struct mc_synth_spec {
     uint64_t seed;

@@ -48,7 +48,7 @@ def mcaller_main(argv=None):
     base = a.motif if (a.motif and len(a.motif) == 1) else a.base
     assert a.skip_thresh < a.num_variables / 2, "too many skips with only " + str(a.num_variables) + " variables - try < half"
     assert os.path.isfile(a.fastq), "fastq file not found at " + a.fastq
-    read2qual = read_qual.extract_read_quality(a.fastq)
+    read2qual = read_qual.extract_read_quality_device(a.fastq)        # FASTQ scanned on the GPU (same mapping as read_qual.py)
     print("%d contigs" % len(refmark.read_fasta(a.reference)))
     print("%d threads" % a.threads)
     k = a.num_variables

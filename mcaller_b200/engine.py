@@ -46,8 +46,12 @@ class Engine(object):
         self.dense = bool(dense) if dense is not None else (self.qual_thresh > 0.0)
         if qual_table is None:
             qual_table = np.zeros(16, dtype=_lib.QUAL_DTYPE)
-        self.qual_table_size = len(qual_table)
-        self.d_qual = torch.from_numpy(qual_table.view(np.uint8).reshape(-1).copy()).to(self.device)
+        if hasattr(qual_table, "table") and hasattr(qual_table, "size"):          # read_qual.DeviceQualityTable
+            self.qual_table_size = int(qual_table.size)
+            self.d_qual = qual_table.table
+        else:
+            self.qual_table_size = len(qual_table)
+            self.d_qual = torch.from_numpy(qual_table.view(np.uint8).reshape(-1).copy()).to(self.device)
         self.histogram = histogram
         ns = max(refindex.n_sites, 1)
         self.d_depth = torch.zeros(ns, dtype=torch.int32, device=self.device)

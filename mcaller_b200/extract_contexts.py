@@ -305,7 +305,8 @@ def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thr
             raise ValueError("model expects %d inputs but -n %d gives %d" % (dm.n_in, k, k + 1))
     else:
         tsv_output = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k) + ".train.tmp" + str(startline)
-    qt = _rq.build_quality_table(read2qual)
+    # read2qual: the reference's dict, or a read_qual.DeviceQualityTable built on the GPU from the FASTQ
+    qt = read2qual if isinstance(read2qual, _rq.DeviceQualityTable) else _rq.build_quality_table(read2qual)
     eng = _engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=skip_thresh, qual_thresh=qual_thresh, two_models=two, histogram=False)
     fmt = _RowFormatter(ref, k, base, train, pos_label, dm is not None)
 

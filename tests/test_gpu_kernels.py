@@ -270,3 +270,54 @@ def test_odd_line_layouts_match_oracle(style, cuda_lib, oracle):
             assert abs(float(c["prob"]) - w["prob"]) < 1e-12
         st = eng.count_rows(res)
         assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["errors"] == 0
+
+
+def test_fastq_quality_on_device_matches_host(tmp_path, cuda_lib):
+    """mc_fastq_index + mc_fastq_quality == read_qual.extract_read_quality (keys, means bit-equal, last duplicate wins)."""
+    import gzip, random
+    from mcaller_b200 import read_qual
+    rnd = random.Random(3)
+    recs = []
+    for i in range(3000):
+        style = i % 4
+        rid = ["%08x-aaaa_Basecall_1D_template" % rnd.getrandbits(32), "ch%d:read%d:template" % (i, i), "plain%d" % i,
+               "dup_key_%d" % (i % 7)][style]
+        n = rnd.randint(1, 400)
+        q = "".join(chr(33 + rnd.randint(0, 60)) for _ in range(n))
+        recs.append("@%s some description\n%s\n+\n%s\n" % (rid, "A" * n, q))
+    text = "".join(recs)
+    p = tmp_path / "r.fastq"
+    p.write_text(text)
+    host = read_qual.extract_read_quality(str(p))
+    for path in (str(p), str(tmp_path / "r.fastq.gz")):
+        if path.endswith(".gz"):
+            with gzip.open(path, "wt") as fh:
+                fh.write(text[:-1])          # also: no trailing newline
+            host_ref = read_qual.extract_read_quality(path)
+        else:
+            host_ref = host
+        dt = read_qual.extract_read_quality_device(path)
+        assert dt.bad_headers == 0 and dt.n_records == 3000
+        tab = dt.to_host()
+        live = tab[tab["hash"] != 0]
+        assert len(live) == len(host_ref)
+        want = read_qual.build_quality_table(host_ref)
+        w = want[want["hash"] != 0]
+        a = {(int(e["hash"]), int(e["check"]), int(e["len"])): float(e["qual"]) for e in live}
+        b = {(int(e["hash"]), int(e["check"]), int(e["len"])): float(e["qual"]) for e in w}
+        assert a == b
+
+
+def test_cli_end_to_end_with_device_fastq(tmp_path, capsys, cuda_lib):
+    """python -m mcaller_b200.cli mCaller ... (FASTQ scanned on the GPU) then make_bed: byte-identical to the reference."""
+    import json
+    from mcaller_b200 import cli
+    case = gc.CASES["gatc_s1"]
+    gold = json.load(open(os.path.join(gc.GOLD, "gatc_s1.json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    for threads in ("1", "3"):
+        cli.mcaller_main(["-m", "GATC", "-r", inp["fasta"], "-e", inp["tsv"], "-f", inp["fastq"], "-d", inp["model"], "-b", "A", "-s", "1",
+                          "-t", threads])
+        out = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
+        assert open(out).read() == gold["diffs"]
+        os.remove(out)
