@@ -376,6 +376,23 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         }
         const unsigned long long chunk_base = slot_cur;
 
+        // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold the
+        // look-ahead words instead of a single lane walking the bit map
+        int e_last;
+        if (!tail) {
+            constexpr int WLAST = (LOOKB + CHUNK - 1) >> 5, BLAST = (LOOKB + CHUNK - 1) & 31;
+            static_assert(NW - WLAST <= 32, "look-ahead words must fit one per lane");
+            int cand_e = NW * 32;
+            if (WLAST + lane < NW) {
+                uint32_t m = S.nl[WLAST + lane];
+                if (lane == 0) m &= 0xFFFFFFFFu << BLAST;
+                if (m) cand_e = 32 * (WLAST + lane) + __ffs(m) - 1;
+            }
+            e_last = __reduce_min_sync(0xffffffffu, cand_e);
+        } else {
+            e_last = -1;           // text ends inside this chunk: fall back to the bit-map walk
+        }
+
         int prev_state = -1;       // -1: no kept line yet in this chunk, 0: last kept line not a candidate, 1: candidate
         uint32_t filler = 0u;      // the chunk's first record exists only because its predecessor line is in another chunk
         for (int pass0 = 0; pass0 < total_lines; pass0 += 32) {
@@ -417,7 +434,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             int cid = -1, pos = 0, s = 0;
             if (lane < n_pass) {
                 s = S.lstart[lane];
-                const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : next_bit(S.nl, s);
+                const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : (e_last >= 0 ? e_last : next_bit(S.nl, s));
                 // columns 1, 2, 10, 12 from a 160-bit window of the field-start bits aligned at the line start
                 int f0, f1, f9, f11;
                 line_fields(S, s, f0, f1, f9, f11);
