@@ -50,9 +50,12 @@ struct WarpSmem {
     alignas(128) uint8_t text[2][WB];    // double-buffered staged bytes (TMA destination)
     alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
     uint32_t nl[NW + 4];                 // newline bits
-    uint32_t ls[NW + 4];                 // line-start bits (owned range only)
-    uint16_t fcnt[NW + 4];               // field starts before each word (exclusive prefix over fs)
+    union {                              // ls is consumed (into registers) before fcnt is produced
+        uint32_t ls[NW + 4];             // line-start bits (owned range only)
+        uint16_t fcnt[NW + 4];           // field starts before each word (exclusive prefix over fs)
+    };
     uint16_t lstart[LCAP + 4];
+    uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
     alignas(8) unsigned long long bar[2];
 };
 
@@ -257,7 +260,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     };
     set_hint(0);
     unsigned long long slot_cur = 0ull, slot_end = 0ull;          // reserved record slots [cur, end)
-    unsigned c_lines = 0, c_kept = 0, c_short = 0, c_unknown = 0, c_nnn = 0, c_badpos = 0, c_slow = 0, c_overflow = 0;
+    unsigned c_lines = 0, c_kept = 0;                             // warp-uniform; rarer events are counted in S.cnt
+    if (lane < 8) S.cnt[lane] = 0u;
 
     if (lane == 0) {
         mbar_init(&S.bar[0], 1);
@@ -301,7 +305,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         if (next < n_chunks) next_async = stage(next, buf ^ 1);
         if (cur_async) {
             const uint32_t ph = buf ? phase1 : phase0;
-            if (!mbar_wait(&S.bar[buf], ph)) ++c_overflow;
+            if (!mbar_wait(&S.bar[buf], ph) && lane == 0) atomicAdd(&S.cnt[5], 1u);
             if (buf) phase1 ^= 1u; else phase0 ^= 1u;
         }
         __syncwarp();
@@ -364,7 +368,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             *reinterpret_cast<uint2 *>(&S.fcnt[4 * lane]) = make_uint2(a, b);
             if (lane == 31) S.fcnt[NW] = (uint16_t)(my_first_fs + my_fs);
         }
-        c_lines += (lane == 0) ? (unsigned)total_lines : 0u;
+        c_lines += (unsigned)total_lines;
 
         // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
         if (slot_end - slot_cur < (unsigned long long)total_lines) {
@@ -445,19 +449,17 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, cid, pos);
                 } else if (e >= NW * 32 || f11 >= NW * 32) {
                     status = classify_from_global(d_text, limit, G0 + s, R, hint, hint_base, hint_len, cid, pos);
-                    ++c_slow;
+                    atomicAdd(&S.cnt[4], 1u);
                 } else {
                     status = ST_SHORT;
                 }
             }
-            c_kept += (status & ST_KEPT) ? 1u : 0u;
-            c_short += (status & ST_SHORT) ? 1u : 0u;
-            c_unknown += (status & ST_UNKNOWN) ? 1u : 0u;
-            c_nnn += (status & ST_NNN) ? 1u : 0u;
-            c_badpos += (status & ST_BADPOS) ? 1u : 0u;
+            if (status & (ST_SHORT | ST_UNKNOWN | ST_NNN | ST_BADPOS))
+                atomicAdd(&S.cnt[(status & ST_SHORT) ? 0 : (status & ST_UNKNOWN) ? 1 : (status & ST_NNN) ? 2 : 3], 1u);
 
             // ---- 4. which lines matter: ballots over the 32 lines of this pass -----------------------------------------
             const uint32_t kept_m = __ballot_sync(0xffffffffu, (status & ST_KEPT) != 0u);
+            c_kept += (unsigned)__popc(kept_m);
             const uint32_t cand_m = __ballot_sync(0xffffffffu, (status & ST_CAND) != 0u);
             bool emit = false, filler_lane = false;
             if (status & ST_KEPT) {
@@ -495,7 +497,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     dst[0] = a;
                     dst[1] = b;
                 } else {
-                    ++c_overflow;
+                    atomicAdd(&S.cnt[5], 1u);
                 }
             }
             slot_cur += __popc(emit_m);
@@ -509,20 +511,17 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         cur_async = next_async;
     }
 
-    // ---- counters: one warp reduction per counter, one atomic per warp ----------------------------------------------------
-    const unsigned r_lines = __reduce_add_sync(0xffffffffu, c_lines), r_kept = __reduce_add_sync(0xffffffffu, c_kept);
-    const unsigned r_short = __reduce_add_sync(0xffffffffu, c_short), r_unknown = __reduce_add_sync(0xffffffffu, c_unknown);
-    const unsigned r_nnn = __reduce_add_sync(0xffffffffu, c_nnn), r_badpos = __reduce_add_sync(0xffffffffu, c_badpos);
-    const unsigned r_slow = __reduce_add_sync(0xffffffffu, c_slow), r_over = __reduce_add_sync(0xffffffffu, c_overflow);
+    // ---- counters: one global atomic per warp and counter ------------------------------------------------------------------
+    __syncwarp();
     if (lane == 0) {
-        if (r_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)r_lines);
-        if (r_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)r_kept);
-        if (r_short) atomicAdd(&d_counters[MC_C_SHORT], (unsigned long long)r_short);
-        if (r_unknown) atomicAdd(&d_counters[MC_C_UNKNOWN_CONTIG], (unsigned long long)r_unknown);
-        if (r_nnn) atomicAdd(&d_counters[MC_C_NNN], (unsigned long long)r_nnn);
-        if (r_badpos) atomicAdd(&d_counters[MC_C_BADPOS], (unsigned long long)r_badpos);
-        if (r_slow) atomicAdd(&d_counters[MC_C_LONGLINE], (unsigned long long)r_slow);
-        if (r_over) atomicAdd(&d_counters[MC_C_OVERFLOW], (unsigned long long)r_over);
+        if (c_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)c_lines);
+        if (c_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)c_kept);
+    }
+    if (lane < 6) {
+        const int which = lane == 0 ? MC_C_SHORT : lane == 1 ? MC_C_UNKNOWN_CONTIG : lane == 2 ? MC_C_NNN : lane == 3 ? MC_C_BADPOS
+                        : lane == 4 ? MC_C_LONGLINE : MC_C_OVERFLOW;
+        const unsigned v = S.cnt[lane];
+        if (v) atomicAdd(&d_counters[which], (unsigned long long)v);
     }
 }
 
