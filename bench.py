@@ -124,13 +124,15 @@ def cpu_oracle_pass(text_bytes, read_offsets, seqs, quals, model, skip, threads)
     bounds = [read_offsets[(n * t) // threads] for t in range(threads)] + [len(text_bytes)]
     mv = memoryview(text_bytes)
 
+    # reference marking, quality table and model are marshalled once (the reference also loads them once per worker)
+    prep = orc.prepare(seqs, quals, model=model, base="A", motif="GATC")
+
     def work(t):
         sl = bytes(mv[bounds[t]:bounds[t + 1]])
-        r = orc.extract(sl, seqs, quals, k=6, skip_thresh=skip, qual_thresh=0.0, model=model, base="A", motif="GATC",
-                        cap=max(4096, len(sl) // 2000), count_only=True)
+        r = orc.extract(sl, None, None, k=6, skip_thresh=skip, qual_thresh=0.0, cap=max(4096, len(sl) // 2000), count_only=True,
+                        prepared=prep)
         return r["counters"]["observations"]
 
-    # marking the 4.6 Mb reference is per-call setup in the python wrapper; warm the library first
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         calls = sum(ex.map(work, range(threads)))

@@ -231,40 +231,59 @@ def fmt_prob(p):
     return repr(float(lib().orc_np_round(float(p), 2)))
 
 
-def extract(tsv_bytes, fasta, quals, k=6, skip_thresh=0, qual_thresh=0.0, model=None, base="A", motif=None,
-            positions=None, cap=None, count_only=False):
-    """Run the restated extract_features over a whole TSV (== reference with -t 1).
+class Prepared(object):
+    """Marshalled inputs of the oracle (marked reference, quality table, model) reusable across calls / threads."""
+    pass
 
-    Returns dict(rows=[str...], calls=[...], counters={...}) where rows are the `.diffs.<k>` lines.
-    `model`: unpickled object (dict or bare estimator) or None (features only).
-    """
-    L = lib()
+
+def prepare(fasta, quals, model=None, base="A", motif=None, positions=None):
     seqs = read_fasta(fasta) if isinstance(fasta, str) else fasta
-    names = list(seqs)
-    carr = (_Contig * len(names))()
-    keep = []
-    for i, nm in enumerate(names):
+    P = Prepared()
+    P.names = list(seqs)
+    P.carr = (_Contig * len(P.names))()
+    P.keep = []
+    for i, nm in enumerate(P.names):
         f, r = mark(seqs[nm], base, motif=motif, positions=positions, contig=nm)
         fb, rb, nb = f.encode(), r.encode(), nm.encode()
-        keep += [fb, rb, nb]
-        carr[i].name, carr[i].fwd, carr[i].rev, carr[i].len = nb, fb, rb, len(fb)
+        P.keep += [fb, rb, nb]
+        P.carr[i].name, P.carr[i].fwd, P.carr[i].rev, P.carr[i].len = nb, fb, rb, len(fb)
     qitems = sorted((kk.encode(), float(v)) for kk, v in quals.items())
-    qarr = (_Qual * max(len(qitems), 1))()
+    P.nq = len(qitems)
+    P.qarr = (_Qual * max(len(qitems), 1))()
     for i, (kk, v) in enumerate(qitems):
-        qarr[i].key, qarr[i].qual = kk, v
-    marr = (_Model * 2)()
-    two = 0
-    label_mod = "m6A" if base == "A" else "m" + base
+        P.qarr[i].key, P.qarr[i].qual = kk, v
+    P.keep.append(qitems)
+    P.marr = (_Model * 2)()
+    P.two = 0
+    P.base = base
+    P.have_model = model is not None
     if model is not None:
         if isinstance(model, dict):
             if base == "A":
-                m0, k0 = export_model(model["MH"]); m1, k1 = export_model(model["MG"]); two = 1
-                marr[0], marr[1] = m0, m1
-                keep += k0 + k1
+                m0, k0 = export_model(model["MH"]); m1, k1 = export_model(model["MG"]); P.two = 1
+                P.marr[0], P.marr[1] = m0, m1
+                P.keep += k0 + k1
             else:
-                m0, k0 = export_model(model["general"]); marr[0] = m0; keep += k0
+                m0, k0 = export_model(model["general"]); P.marr[0] = m0; P.keep += k0
         else:
-            m0, k0 = export_model(model); marr[0] = m0; keep += k0
+            m0, k0 = export_model(model); P.marr[0] = m0; P.keep += k0
+    return P
+
+
+def extract(tsv_bytes, fasta, quals, k=6, skip_thresh=0, qual_thresh=0.0, model=None, base="A", motif=None,
+            positions=None, cap=None, count_only=False, prepared=None):
+    """Run the restated extract_features over a whole TSV (== reference with -t 1).
+
+    Returns dict(rows=[str...], calls=[...], counters={...}) where rows are the `.diffs.<k>` lines.
+    `model`: unpickled object (dict or bare estimator) or None (features only).  `prepared`: result of prepare()
+    (then fasta / quals / model / base / motif / positions are ignored).
+    """
+    L = lib()
+    P = prepared if prepared is not None else prepare(fasta, quals, model=model, base=base, motif=motif, positions=positions)
+    names, carr, qarr, marr, two, base = P.names, P.carr, P.qarr, P.marr, P.two, P.base
+    label_mod = "m6A" if base == "A" else "m" + base
+    model = True if P.have_model else None
+    qitems = range(P.nq)
     cap = cap or max(1024, len(tsv_bytes) // 64)
     calls = (_Call * cap)()
     n = L.orc_extract(C.c_char_p(tsv_bytes), C.c_int64(len(tsv_bytes)), carr, C.c_int32(len(names)), qarr, C.c_int64(len(qitems)),
