@@ -204,46 +204,21 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
         for (int c = 0; c < MC_MAXK; ++c) C.cnt[c] = 0;
     };
 
-    mc_record r_next = (b < e) ? load_rec(rec + b) : mc_record();
-    for (uint32_t i = b; i < e; ++i) {
-        const mc_record r = r_next;
+    // The row-producing code (column means, divisions, context look-ups) is by far the heaviest path and a lane needs it
+    // only once per ~20 records.  Run in rounds so the warp executes it together: each lane advances through its records
+    // until it reaches a window close (or its end-of-read hand-off), then all lanes that have one emit, then the next round.
+    uint32_t i = b;
+    mc_record r = (b < e) ? load_rec(rec + b) : mc_record();
+    mc_record r_next = (b + 1 < e) ? load_rec(rec + b + 1) : mc_record();
+    auto advance = [&]() {
+        ++i;
+        r = r_next;
         if (i + 1 < e) r_next = load_rec(rec + i + 1);              // overlap the next record's latency with this one's work
-        const bool same_read = started;
-        if (!same_read) {                                          // :161-162
-            first_ind = r.event_idx;
-            if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
-        }
-        int rev;
-        if (!same_read) rev = !(r.flags & MC_RF_EQ);               // :169-174
-        else {
-            if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
-            rev = !(r.event_idx > first_ind);
-        }
-        const int cid = r.contig, pos = r.pos;
-        uint32_t bits = 0u;                                        // 'M's of meth_ref[pos:pos+k] (:176)
-        if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, k);
-        const int first_m = bits ? (__ffs(bits) - 1) : -1;
-
-        if (MPOS_TRUTHY && pos >= mpos + 1 && same_read) {         // :179 (the other-read case is the segment hand-off below)
-            emit_window(i, cid);
-            if (first_m < 0 || pos > mpos + skip_thresh + 1) {     // :242-245
-                reset_cols();
-                has_mpos = false;
-            } else {                                               // :246-256 multi-M carry
-                if (first_m != 0) emit_multi();
-                const int last_mpos = mpos;
-                mpos = pos + first_m;
-                int sp = mpos - last_mpos;
-                if (sp > k) sp = k;
-                if (sp <= 0) { sticky_err |= MC_CE_SPACING; sp = k; }
-                int nm[MC_MAXK];
-                for (int c = 0; c < k; ++c) {
-                    if (c < sp) { nm[c] = map[k - sp + c]; C.cnt[nm[c]] = 0; }
-                    else nm[c] = map[c - sp];
-                }
-                for (int c = 0; c < k; ++c) map[c] = nm[c];
-            }
-        }
+    };
+    int rev = 0, first_m = -1, cid = 0, pos = 0;
+    bool pending_close = false, handoff_done = false;
+    // part of a record's processing after the close decision: feed or reset (:269-291)
+    auto feed = [&]() {
         if (first_m >= 0) {                                        // :269-287
             if (MPOS_TRUTHY && rev != last_rev) has_mpos = false;  // columns kept (:276-277)
             if (!MPOS_TRUTHY) { has_mpos = true; mpos = pos + first_m; }
@@ -258,19 +233,75 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
             has_mpos = false;
             reset_cols();
         }
-    }
-    // hand-off: a window still open at the end of the read is closed by the next kept line of the file, i.e. the
-    // first record of the next segment that passes the quality filter (:179, read_name != last_read)
-    if (MPOS_TRUTHY) {
-        int64_t j = seg + 1;
-        while (j < n_seg && seg_qual[j] < qual_thresh) ++j;
-        if (j < n_seg) {
-            const uint32_t ci = seg_start[j];
-            const mc_record cr = load_rec(rec + ci);
-            emit_window(ci, cr.contig);
-        } else {
-            emit_window(0xFFFFFFFFu, -1);                          // pending: resolved by the next chunk, dropped at EOF
+    };
+    for (;;) {
+        // ---- phase 1: advance to the next emission point ---------------------------------------------------------------
+        while (!pending_close && i < e) {
+            const bool same_read = started;
+            if (!same_read) {                                      // :161-162
+                first_ind = r.event_idx;
+                if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+            }
+            if (!same_read) rev = !(r.flags & MC_RF_EQ);           // :169-174
+            else {
+                if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+                rev = !(r.event_idx > first_ind);
+            }
+            cid = r.contig;
+            pos = r.pos;
+            uint32_t bits = 0u;                                    // 'M's of meth_ref[pos:pos+k] (:176)
+            if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, k);
+            first_m = bits ? (__ffs(bits) - 1) : -1;
+            if (MPOS_TRUTHY && pos >= mpos + 1 && same_read) {     // :179 (the other-read case is the segment hand-off below)
+                pending_close = true;
+                break;
+            }
+            feed();
+            advance();
         }
+        // hand-off: a window still open at the end of the read is closed by the next kept line of the file, i.e. the
+        // first record of the next segment that passes the quality filter (:179, read_name != last_read)
+        const bool pending_handoff = !pending_close && i >= e && !handoff_done && MPOS_TRUTHY;
+        if (!pending_close && !pending_handoff) break;
+        // ---- phase 2: the lanes that reached an emission point emit together --------------------------------------------
+        uint32_t close_idx = i;
+        int chrom = cid;
+        if (pending_handoff) {
+            int64_t j = seg + 1;
+            while (j < n_seg && seg_qual[j] < qual_thresh) ++j;
+            if (j < n_seg) {
+                close_idx = seg_start[j];
+                chrom = load_rec(rec + close_idx).contig;
+            } else {
+                close_idx = 0xFFFFFFFFu;                           // pending: resolved by the next chunk, dropped at EOF
+                chrom = -1;
+            }
+        }
+        emit_window(close_idx, chrom);
+        if (pending_handoff) {
+            handoff_done = true;
+            continue;
+        }
+        if (first_m < 0 || pos > mpos + skip_thresh + 1) {         // :242-245
+            reset_cols();
+            has_mpos = false;
+        } else {                                                   // :246-256 multi-M carry
+            if (first_m != 0) emit_multi();
+            const int last_mpos = mpos;
+            mpos = pos + first_m;
+            int sp = mpos - last_mpos;
+            if (sp > k) sp = k;
+            if (sp <= 0) { sticky_err |= MC_CE_SPACING; sp = k; }
+            int nm[MC_MAXK];
+            for (int c = 0; c < k; ++c) {
+                if (c < sp) { nm[c] = map[k - sp + c]; C.cnt[nm[c]] = 0; }
+                else nm[c] = map[c - sp];
+            }
+            for (int c = 0; c < k; ++c) map[c] = nm[c];
+        }
+        pending_close = false;
+        feed();
+        advance();
     }
     if (!WRITE) seg_count[seg] = n_out;
     (void)n_records;
