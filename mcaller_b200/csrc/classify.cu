@@ -44,11 +44,27 @@ k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int widt
         const int ni = m.sizes[l], no = m.sizes[l + 1];
         const bool last = (l + 1 == m.n_layers);
         if (no >= 8) {
-            for (int o = lane; o < no; o += 32) {
-                double acc = 0.0;
-                for (int k = 0; k < ni; ++k) acc = fma(a[k], __ldg(w + (size_t)k * no + o), acc);
-                acc += __ldg(bi + o);
-                b[o] = last ? acc : activate(acc, m.hidden_act);
+            // four outputs per lane at a time: independent FMA / activation chains interleave and hide each other's latency
+            for (int o0 = 0; o0 < no; o0 += 128) {
+                double acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = 0.0;
+                for (int k = 0; k < ni; ++k) {
+                    const double ak = a[k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int o = o0 + lane + 32 * j;
+                        if (o < no) acc[j] = fma(ak, __ldg(w + (size_t)k * no + o), acc[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o = o0 + lane + 32 * j;
+                    if (o < no) {
+                        const double z = acc[j] + __ldg(bi + o);          // dot product first, then the intercept (as sklearn)
+                        b[o] = last ? z : activate(z, m.hidden_act);
+                    }
+                }
             }
         } else {
             for (int o = 0; o < no; ++o) {

@@ -321,3 +321,49 @@ def test_cli_end_to_end_with_device_fastq(tmp_path, capsys, cuda_lib):
         out = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
         assert open(out).read() == gold["diffs"]
         os.remove(out)
+
+
+def test_iupac_motif_with_general_dict_model(tmp_path, cuda_lib, oracle, capsys):
+    """BASELINE configs[4] semantics: `-m CAAYNNNNNRTAC` with the shipped {'general'} pickle.  The reference cannot run
+    this as written (KeyError); its defined equivalent is `-p` with the IUPAC-expanded positions and the
+    bare estimator, which the oracle runs.  Rows must be identical."""
+    import random
+    from mcaller_b200 import extract_contexts as ec, read_qual, refmark, synth
+    spec = synth.SynthSpec(seed=41, contigs=[("m1", 9000), ("m2", 6000)], n_reads=50, len_min=300, len_max=800)
+    tsv, fasta, fastq, quals = synth.generate(spec)
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    rnd = random.Random(2)
+    for nm in seqs:                       # plant motif instances on both strands (the TSV never looks at the FASTA)
+        s = list(seqs[nm])
+        for _ in range(25):
+            p = rnd.randrange(40, len(s) - 40)
+            inst = "CAA" + rnd.choice("CT") + "".join(rnd.choice("ACGT") for _ in range(5)) + rnd.choice("AG") + "TAC"
+            if rnd.random() < 0.5:
+                inst = refmark.revcomp(inst)
+            s[p:p + 13] = inst
+        seqs[nm] = "".join(s)
+    d = str(tmp_path)
+    with open(os.path.join(d, "ref.fasta"), "w") as fh:
+        for nm, s in seqs.items():
+            fh.write(">%s\n%s\n" % (nm, s))
+    with open(os.path.join(d, "syn.eventalign.tsv"), "wb") as fh:
+        fh.write(tsv)
+    with open(os.path.join(d, "syn.fastq"), "w") as fh:
+        fh.write(fastq)
+    pos_path = os.path.join(d, "pos.txt")
+    rc = "GTAYNNNNNRTTG"
+    with open(pos_path, "w") as fh:
+        for nm, s in seqs.items():
+            for p in refmark.expand_iupac_sites(s, "CAAYNNNNNRTAC", "A"):
+                fh.write("%s\t%d\t+\tm6A\n" % (nm, p))
+            for p in refmark.expand_iupac_sites(s, rc, "T"):
+                fh.write("%s\t%d\t-\tm6A\n" % (nm, p))
+    q = orc_quals = oracle.read_fastq_quals(os.path.join(d, "syn.fastq"))
+    want = oracle.extract(tsv, os.path.join(d, "ref.fasta"), orc_quals, k=6, skip_thresh=1,
+                          model=oracle.load_pickle(os.path.join(gc.GOLD, "models", gc.CAAY_BARE)), base="A", positions=pos_path)
+    assert len(want["rows"]) > 20
+    ec.extract_features(os.path.join(d, "syn.eventalign.tsv"), os.path.join(d, "ref.fasta"), read_qual.extract_read_quality(os.path.join(d, "syn.fastq")),
+                        6, 1, 0.0, os.path.join(gc.GOLD, "models", "CAAYNNNNNRTAC_model_6_m6A.pkl"), "NN", 0,
+                        endline=len(tsv), base="A", motif="CAAYNNNNNRTAC")
+    mine = open(os.path.join(d, "syn.eventalign.diffs.6.tmp0")).read()
+    assert mine == "".join(r + "\n" for r in want["rows"])

@@ -181,3 +181,20 @@ def test_no_cpu_fallback_without_cuda():
         engine.require_cuda()
     with pytest.raises(_lib.McallerCudaError):
         ec.extract_features("x.tsv", "x.fa", {}, 6, 0, 0, "m.pkl", "NN", 0, endline=1, base="A", motif="GATC")
+
+
+def test_iupac_expansion_matches_regex():
+    """Documented extension: IUPAC motifs are expanded on both strands (all, also overlapping, matches)."""
+    import re as _re
+    rnd = random.Random(9)
+    seq = "".join(rnd.choice("ACGT") for _ in range(20000))
+    for motif, base in (("CAAYNNNNNRTAC", "A"), ("GANTC", "A"), ("CCWGG", "C"), ("RAACY", "A")):
+        pat = "".join("[%s]" % refmark.IUPAC[c] for c in motif)
+        want = set()
+        for m in _re.finditer("(?=(%s))" % pat, seq):
+            for j, ch in enumerate(motif):
+                if ch == base:
+                    want.add(m.start() + j)
+        assert refmark.expand_iupac_sites(seq, motif, base) == sorted(want)
+    f, r = refmark.mark_reference("TTCAACGGGGGATACTTGTATCCCCCGTTGAA", "A", motif="CAAYNNNNNRTAC")
+    assert f.count("M") == 3 and r.count("M") == 3          # one instance per strand, three A's / T's each
