@@ -139,8 +139,26 @@ def cpu_oracle_pass(text_bytes, read_offsets, seqs, quals, model, skip, threads)
     return calls, time.perf_counter() - t0
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """The one JSON line of the contract goes to the real stdout; everything else (NCCL banners, library prints) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for the rest of the run
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +203,7 @@ def main():
                                  "sample": "C restatement of the reference (oracle/mcaller_oracle.c) on %d reads, %d host threads; the "
                                            "reference itself is pure Python and cannot travel to this box" % (n_s, host_cores)},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit_line(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------ our arm
@@ -320,7 +338,7 @@ def main():
                            "calls_per_step": total_calls // args.steps, "lines_per_step_per_gpu": res.counters["lines"],
                            "records_per_step_per_gpu": res.n_records},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit_line(line)
     if use_dist:
         dist.destroy_process_group()
     return 0
