@@ -29,7 +29,9 @@ CASES = {
     "masonread1_gatc": dict(fixture="masonread1", motif="GATC", model=R95, base="A"),
     "masonread1_gatc_s2": dict(fixture="masonread1", motif="GATC", model=R95, base="A", s=2),
     # synthetic, three contigs + header line, methylation signal on half the sites
-    "gatc_s0": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, beds=[["-d", "1", "-t", "0.5"], ["-d", "3", "-t", "0.3"]]),
+    "gatc_s0": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True,
+                    beds=[["-d", "1", "-t", "0.5"], ["-d", "3", "-t", "0.3"], ["-d", "1", "-t", "0.5", "--gff"],
+                          ["-d", "2", "-t", "0.4", "--ref", "ref.fasta"], ["-d", "1", "-t", "0.6", "--control", "--gff", "--ref", "ref.fasta"]]),
     "gatc_s1": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1),
     "gatc_s2": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=2, beds=[["-d", "2", "-t", "0.5"], ["-d", "2", "-t", "0.5", "--control"]]),
     # dense multi-M windows (every A is a target), reads truncated so windows stay open across reads/contigs

@@ -70,12 +70,15 @@ def test_bed_matches_reference(name, tmp_path, capsys, cuda_lib):
     diffs = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
     with open(diffs, "w") as fh:
         fh.write(gold["diffs"])
+    ref_fa = None
+    if any("--ref" in b["args"] for b in gold["beds"]):
+        ref_fa = gc.build_inputs(gc.CASES[name], str(tmp_path))["fasta"]
     for b in gold["beds"]:
         a = b["args"]
         out = os.path.join(str(tmp_path), "o.bed")
-        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), None, "--control" in a, False, False,
-                            None, False, "x", False)
-        assert open(out).read() == b["bed"]
+        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), None, "--control" in a, False, "--gff" in a,
+                            ref_fa if "--ref" in a else None, False, "x", False)
+        assert open(out).read() == b["bed"], a
 
 
 def test_reference_fixture_bed(tmp_path, cuda_lib):
@@ -96,3 +99,30 @@ def test_reference_fixture_features(tmp_path, capsys, cuda_lib):
     assert len(rows) == len(fx) == 9
     for a, b in zip(rows, fx):
         assert a.split("\t")[:6] == b.split("\t")[:6]
+
+
+def test_train_mode_windows_match_reference_fixture(tmp_path, capsys, cuda_lib):
+    """extract_features(train=True): the 44 labelled windows of the reference's own
+    masonread1.eventalign.diffs.6.train come out of the GPU path (set equality, features to 1e-9: the fixture was printed
+    with 12 significant digits by the python2-era reference)."""
+    from mcaller_b200 import extract_contexts as ec, read_qual
+    case = dict(gc.CASES["masonread1_p"], positions="test_positions.txt")
+    inp = gc.build_inputs(case, str(tmp_path))
+    keep = [ln for ln in open(inp["positions"]) if ln.split() and 13200 <= int(ln.split()[1]) <= 26370]
+    with open(inp["positions"], "w") as fh:
+        fh.writelines(keep)
+    pos_label = {(f[0], int(f[1]), f[2]): f[3] for f in (ln.split() for ln in keep)}       # train_model.pos2label
+    sig, ctx = ec.extract_features(inp["tsv"], inp["fasta"], read_qual.extract_read_quality(inp["fastq"]), 6, 0, 0.0, None, "NN", 0,
+                                   endline=os.path.getsize(inp["tsv"]), train=True, pos_label=pos_label, base="A",
+                                   positions_list=inp["positions"])
+    mine = {}
+    for row in open(os.path.join(str(tmp_path), "syn.eventalign.diffs.6.train.tmp0")):
+        f = row.rstrip("\n").split("\t")
+        mine[(int(f[2]), f[3], f[5], f[6])] = [float(x) for x in f[4].split(",")]
+    fx = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(gc.GOLD, "masonread1", "masonread1.eventalign.diffs.6.train"))]
+    assert len(fx) == 44 == len(mine)
+    for f in fx:
+        key = (int(f[1]), f[2], f[4], f[5])
+        assert key in mine, key
+        assert all(abs(a - b) < 1e-9 for a, b in zip([float(x) for x in f[3].split(",")], mine[key]))
+    assert sum(len(v) for v in sig["general"].values()) == 44 and set(sig["general"]) == {"A", "m6A"}

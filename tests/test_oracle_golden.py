@@ -37,6 +37,8 @@ def test_oracle_bed(name, oracle):
     gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
     for b in gold["beds"]:
         a = b["args"]
+        if "--gff" in a or "--ref" in a:
+            continue            # reporting variants of the same counts: covered by the GPU drop-in test
         rows = oracle.aggregate(gold["diffs"], int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), "--control" in a)
         assert "".join(x + "\n" for x in rows) == b["bed"]
 

@@ -72,10 +72,10 @@ def make_case(name):
             rec["diffs"] = open(diffs_path).read()
             for bed_args in case.get("beds", [["-d", "1", "-t", "0.5"]]):
                 for f in os.listdir(tmp):
-                    if f.endswith(".bed"):
+                    if f.endswith(".bed") or f.endswith(".gff"):
                         os.remove(os.path.join(tmp, f))
                 rc2, so2, se2 = run([sys.executable, os.path.join(REF, "make_bed.py"), "-f", "syn.eventalign.diffs.%d" % case.get("k", 6)] + bed_args, tmp)
-                beds = [f for f in os.listdir(tmp) if f.endswith(".bed")]
+                beds = [f for f in os.listdir(tmp) if f.endswith(".bed") or f.endswith(".gff")]
                 rec.setdefault("beds", []).append({"args": bed_args, "rc": rc2,
                                                    "bed": open(os.path.join(tmp, beds[0])).read() if beds else None})
         with open(os.path.join(GOLD, name + ".json"), "w") as fh:
