@@ -367,3 +367,60 @@ def test_iupac_motif_with_general_dict_model(tmp_path, cuda_lib, oracle, capsys)
                         endline=len(tsv), base="A", motif="CAAYNNNNNRTAC")
     mine = open(os.path.join(d, "syn.eventalign.diffs.6.tmp0")).read()
     assert mine == "".join(r + "\n" for r in want["rows"])
+
+
+def test_size_independent_properties_at_scale(cuda_lib):
+    """1.5 GB of device-generated TSV (3 000 reads): chunk-invariance (streamed from host in 128 MB read-aligned chunks ==
+    one pass), shard-invariance (two read slices with the slice-edge hand-off == one pass, histograms add up), idempotence,
+    and conservation (histogram mass == closed calls)."""
+    import torch
+    from mcaller_b200 import engine, models, read_qual, stream, synth, synth_device
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=77, contigs=[("ecoli", 1000000)], n_reads=3000, len_min=1000, len_max=3000)
+    seqs = {"ecoli": synth.genome(spec, 0).tobytes().decode()}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    gen = synth_device.DeviceSynth(spec, ref, None)
+    keys, q = synth_device.quality_table_for(spec)
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(dict(zip(keys, q.tolist()))), skip_thresh=1, two_models=True)
+    d_text, n, offs = gen.generate(0, spec.n_reads)
+    assert n > 1.2e9
+    res = eng.run_chunk(d_text, n)
+    whole = eng.count_rows(res)
+    hist_whole = [a.copy() for a in eng.histogram_host()]
+    assert whole["errors"] == 0 and whole["calls"] > 10000
+    assert int(hist_whole[0].sum()) == whole["calls"]                            # conservation
+    # idempotence
+    eng.reset_histogram()
+    res2 = eng.run_chunk(d_text, n)
+    assert eng.count_rows(res2) == whole and all((a == b).all() for a, b in zip(eng.histogram_host(), hist_whole))
+    # chunk-invariance through the host streaming path
+    eng.reset_histogram()
+    hbuf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hbuf.copy_(d_text[:n])
+    torch.cuda.synchronize()
+    hs = stream.HostStreamer(eng, chunk_bytes=128 << 20)
+    tot = hs.run(hbuf, stream.plan_chunks(offs.cpu().numpy(), n, hs.chunk_bytes))
+    assert tot["calls"] == whole["calls"] + whole["pending"] * 0 and tot["dropped_at_eof"] == whole["pending"]
+    assert tot["too_many_skips"] == whole["too_many_skips"] and tot["multi"] == whole["multi"]
+    d_s, m_s, _ = eng.histogram_host()
+    # windows handed over a chunk edge are closed on the host side (their rows carry no closing record on the device)
+    assert int(d_s.sum()) + tot["pending_resolved"] == whole["calls"]
+    assert (d_s <= hist_whole[0]).all() and int((hist_whole[0] - d_s).sum()) == tot["pending_resolved"]
+    # shard-invariance: two read slices
+    o = offs.cpu().numpy()
+    half = 1500
+    cut = int(o[half])
+    eng.reset_histogram()
+    a = eng.run_chunk(d_text[:cut + engine.MC_TEXT_PAD + 64].clone().index_fill_(0, torch.arange(cut, cut + engine.MC_TEXT_PAD + 64, device=d_text.device), 10), cut)
+    sa = eng.count_rows(a)
+    d_b = torch.full((eng.padded_capacity(n - cut),), 10, dtype=torch.uint8, device=d_text.device)
+    d_b[: n - cut] = d_text[cut:n]
+    b = eng.run_chunk(d_b, n - cut)
+    sb = eng.count_rows(b)
+    resolved = sa["pending"] if b.counters["kept"] > 0 else 0               # slice-edge hand-off (dist.exchange_boundaries)
+    assert sa["calls"] + sb["calls"] + resolved == whole["calls"]
+    assert sa["too_many_skips"] + sb["too_many_skips"] <= whole["too_many_skips"] <= sa["too_many_skips"] + sb["too_many_skips"] + sa["pending"]
+    d_ab, m_ab, _ = eng.histogram_host()
+    assert int(d_ab.sum()) + resolved == whole["calls"]
