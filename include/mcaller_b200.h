@@ -261,6 +261,18 @@ int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_
                        uint64_t *d_counters, void *stream);
 
 /*
+ * Host-side writer (no device work): renders the MC_CALL rows of a chunk (host copy of the mc_call array; rows still
+ * pending are skipped) as `.diffs.<k>` text exactly like the reference (extract_contexts.py:216, :83-86): chrom, read,
+ * position, 2k-1 context cut from the marked reference copies, comma-joined features (shortest round-trip repr, integer 0
+ * for empty columns) + read quality, strand, and -- with_prob -- label and np.round(prob, 2).  h_text is the host copy
+ * of the chunk (read names).  Returns the number of bytes written, MC_ECAPACITY when out_cap is too small, or
+ * -100 - err when a row carries MC_CE_* error flags.
+ */
+int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const char *const *contig_names,
+                       const char *const *marked_fwd, const char *const *marked_rev, const int64_t *contig_len, int32_t n_contigs,
+                       int32_t k, const char *base_label, const char *mod_label, int32_t with_prob, char *out, int64_t out_cap);
+
+/*
  * FASTQ read-quality ingest (reference read_qual.py:6-19) on the device.  mc_fastq_index builds the byte offset of every
  * line start (d_line_start[0] = 0, capacity line_cap; *d_n_newlines = number of '\n' in the buffer; d_tile_cnt/d_tile_off
  * hold mc_fastq_tiles(nbytes) uint32 each, d_ws >= mc_workspace_bytes(tiles)).  The buffer must be readable up to the next

@@ -188,6 +188,7 @@ class _RowFormatter(object):
         self.signals, self.contexts = {}, {}
         self.pending = None        # (call fields, read name, segment key) awaiting the contig of the next kept line
         self.seg_base = 0
+        self._native = None        # ctypes argument pack of mc_format_rows, built on first use
 
     @staticmethod
     def _check(err, mpos):
@@ -225,8 +226,60 @@ class _RowFormatter(object):
         self.n_obs += 1
         self.pos_set.add(mpos)
         if int(c["n_empty"]) > 0:
-            self.wskips.add((segkey, mpos))
+            self.wskips.add((segkey << 32) | mpos)
         return row
+
+    def _native_args(self):
+        import ctypes as C
+        if self._native is None:
+            names = self.ref.names
+            n = len(names)
+            keep = [nm.encode() for nm in names] + [self.ref.marked[nm][0].encode() for nm in names] + [self.ref.marked[nm][1].encode() for nm in names]
+            self._native = dict(keep=keep, names=(C.c_char_p * n)(*keep[:n]), fwd=(C.c_char_p * n)(*keep[n:2 * n]),
+                                rev=(C.c_char_p * n)(*keep[2 * n:]), lens=(C.c_int64 * n)(*[len(self.ref.marked[nm][0]) for nm in names]), n=n)
+        return self._native
+
+    def consume_bytes(self, calls, text, first_kept_contig, n_segments):
+        """Like consume() but returns the rows as bytes, rendered by the native writer (mc_format_rows); counters are
+        updated with vectorised numpy operations.  Inference mode only."""
+        import ctypes as C
+        from . import _lib
+        head = b""
+        if self.pending is not None and first_kept_contig is not None:
+            rows = self.consume(calls[:0], text, first_kept_contig, 0)
+            head = b"".join(("\t".join(r) + "\n").encode() for r in rows)
+        n = len(calls)
+        if n == 0:
+            self.seg_base += n_segments
+            return head
+        kind = calls["kind"]
+        pend = calls["close_rec"] == 0xFFFFFFFF
+        segkey = calls["seg"].astype(np.int64) + self.seg_base
+        pair = (segkey << 32) | calls["mpos"].astype(np.int64)
+        closed0 = (kind == 0) & ~pend
+        self.multi.update(np.unique(pair[kind == 2]).tolist())
+        self.toomany.update(np.unique(pair[(kind == 1) & ~pend]).tolist())
+        self.wskips.update(np.unique(pair[closed0 & (calls["n_empty"] > 0)]).tolist())
+        self.pos_set.update(np.unique(calls["mpos"][closed0]).tolist())
+        self.n_obs += int(closed0.sum())
+        for c in calls[pend & (kind != 2)]:                      # at most one per chunk: keep for the next chunk
+            ro = int(c["read_off"])
+            self.pending = (c.copy(), bytes(text[ro:ro + int(c["read_len"])]), self.seg_base + int(c["seg"]))
+        a = self._native_args()
+        L = _lib.lib()
+        cap = int(closed0.sum()) * (96 + 26 * (self.k + 1) + int(calls["read_len"].max())) + 4096
+        out = C.create_string_buffer(cap)
+        tbuf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
+        calls_c = np.ascontiguousarray(calls)
+        r = L.mc_format_rows(calls_c.ctypes.data_as(C.c_void_p), n, tbuf, a["names"], a["fwd"], a["rev"], a["lens"], a["n"], self.k,
+                             self.base.encode(), self.mod_label.encode(), 1 if self.have_model else 0, out, cap)
+        if r <= -100:
+            bad = calls[closed0 & (calls["err"] != 0)][0]
+            self._check(int(bad["err"]), int(bad["mpos"]))
+        if r < 0:
+            _lib.check(int(r))
+        self.seg_base += n_segments
+        return head + out.raw[:r]
 
     def consume(self, calls, text, first_kept_contig, n_segments):
         """Rows of one chunk (host structured array) -> list of row lists.  `first_kept_contig`: contig index of the
@@ -237,13 +290,13 @@ class _RowFormatter(object):
             if int(pc["kind"]) == 0:
                 out.append(self._row(pc, pread, pkey, first_kept_contig))
             else:
-                self.toomany.add((pkey, int(pc["mpos"])))
+                self.toomany.add((pkey << 32) | int(pc["mpos"]))
             self.pending = None
         for c in calls:
             kind = int(c["kind"])
             segkey = self.seg_base + int(c["seg"])
             if kind == 2:
-                self.multi.add((segkey, int(c["mpos"])))
+                self.multi.add((segkey << 32) | int(c["mpos"]))
                 continue
             ro = int(c["read_off"])
             read = bytes(text[ro:ro + int(c["read_len"])])
@@ -251,7 +304,7 @@ class _RowFormatter(object):
                 self.pending = (c.copy(), read, segkey)      # still open at the end of the chunk
                 continue
             if kind == 1:
-                self.toomany.add((segkey, int(c["mpos"])))
+                self.toomany.add((segkey << 32) | int(c["mpos"]))
                 continue
             out.append(self._row(c, read, segkey, int(c["chrom_contig"])))
         self.seg_base += n_segments
@@ -336,8 +389,11 @@ def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thr
             if not data:
                 continue
             rows = _run_text(eng, fmt, data, qual_thresh)
-            writefi(rows, tsv_output)
-            towrite_total += len(rows)
+            if isinstance(rows, bytes):
+                with open(tsv_output, "ab") as outfi:          # append, like writefi (:83-86)
+                    outfi.write(rows)
+            else:
+                writefi(rows, tsv_output)
         # a window still open at the end of my range is closed by the first kept line after it (next worker's range)
         if fmt.pending is not None and hi < fsize:
             fh.seek(hi)
@@ -373,4 +429,6 @@ def _run_text(eng, fmt, data, qual_thresh):
     res = eng.run_chunk(d_text, len(data))
     _raise_on_counters(res)
     fk = _first_kept_contig(eng, res, qual_thresh) if fmt.pending is not None else None
-    return fmt.consume(res.calls(), data, fk, res.n_segments)
+    if fmt.train:
+        return fmt.consume(res.calls(), data, fk, res.n_segments)
+    return fmt.consume_bytes(res.calls(), data, fk, res.n_segments)

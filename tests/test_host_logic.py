@@ -198,3 +198,51 @@ def test_iupac_expansion_matches_regex():
         assert refmark.expand_iupac_sites(seq, motif, base) == sorted(want)
     f, r = refmark.mark_reference("TTCAACGGGGGATACTTGTATCCCCCGTTGAA", "A", motif="CAAYNNNNNRTAC")
     assert f.count("M") == 3 and r.count("M") == 3          # one instance per strand, three A's / T's each
+
+
+def test_native_row_writer_matches_python_repr():
+    """mc_format_rows (host-side C++): shortest round-trip float text == repr(float) / str(np.float64), np.round(p, 2),
+    integer 0 for empty columns, revcomp'd context for '-' rows."""
+    import ctypes as C
+    from mcaller_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    rnd = random.Random(1)
+    vals = [0.0, -0.0, 1.0, -1.5, 1e-5, 5e-05, 0.0001, 0.00011, 123456789012345678.0, 1e16, 9999999999999998.0, 1e15, 0.1 + 0.2, -4.55,
+            7.055265349382997, 1e-300, float("nan"), 3.0, 100000.0, 1e22, 1.7976931348623157e308, -0.4066666666666667]
+    vals += [rnd.uniform(-20, 20) for _ in range(2000)] + [float(np.round(rnd.uniform(-10, 10), 4)) for _ in range(2000)]
+    vals += [rnd.uniform(-1, 1) * 10 ** rnd.randint(-8, 18) for _ in range(1000)]
+    n = len(vals)
+    calls = np.zeros(n, dtype=_lib.CALL_DTYPE)
+    calls["feat"][:, 0] = vals
+    calls["feat"][:, 1] = 11.5
+    calls["prob"] = [abs(v) % 1 if v == v else 0.5 for v in vals]
+    calls["mpos"] = 10
+    calls["read_len"] = 2
+    calls["rev"] = np.arange(n) % 2
+    calls["empty_mask"][5::7] = 1
+    calls["kind"][3::11] = 1                      # non-call rows are skipped
+    text = b"rd" + b"\n" * 16
+    fwd, rev = b"ACGTACGTACMCGTACGTACGTAAAA", b"TTGTACGTACMCGGACGTACGTAAAA"
+    names = (C.c_char_p * 1)(b"c1")
+    a_f, a_r, ln = (C.c_char_p * 1)(fwd), (C.c_char_p * 1)(rev), (C.c_int64 * 1)(26)
+    out = C.create_string_buffer(400 * n)
+    r = lib.mc_format_rows(calls.ctypes.data_as(C.c_void_p), n, text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+    assert r > 0, lib.mc_last_error()
+    rows = out.raw[:r].decode().split("\n")[:-1]
+    live = [i for i in range(n) if calls["kind"][i] == 0]
+    assert len(rows) == len(live)
+    for i, row in zip(live, rows):
+        f = row.split("\t")
+        c = calls[i]
+        want_feat = "0" if c["empty_mask"] & 1 else repr(float(vals[i]))
+        assert f[:4] == ["c1", "rd", "10", "M"] and f[5] == ("-" if c["rev"] else "+")
+        assert f[4] == want_feat + ",11.5"
+        assert f[6] == ("m6A" if c["prob"] >= 0.5 else "A") and f[7] == str(np.round(np.float64(c["prob"]), 2))
+    # k = 3: context is cut from the strand's marked copy and reverse-complemented for '-' rows
+    calls2 = np.zeros(2, dtype=_lib.CALL_DTYPE)
+    calls2["mpos"], calls2["read_len"], calls2["rev"] = 10, 2, [0, 1]
+    r = lib.mc_format_rows(calls2.ctypes.data_as(C.c_void_p), 2, text, names, a_f, a_r, ln, 1, 3, b"A", b"m6A", 0, out, len(out))
+    rows = out.raw[:r].decode().split("\n")[:-1]
+    assert rows[0].split("\t")[3] == fwd[8:13].decode() and rows[1].split("\t")[3] == refmark.revcomp(rev[8:13].decode())
+    assert len(rows[0].split("\t")) == 6
