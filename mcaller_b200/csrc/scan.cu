@@ -33,10 +33,10 @@ constexpr int LOOKA = 224;
 constexpr int WB = LOOKB + CHUNK + LOOKA;     // 4096 bytes staged per chunk
 constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_WARPS
-#define MC_SCAN_WARPS 10
+#define MC_SCAN_WARPS 23
 #endif
 #ifndef MC_SCAN_MIN_CTAS
-#define MC_SCAN_MIN_CTAS 2
+#define MC_SCAN_MIN_CTAS 1
 #endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
@@ -233,21 +233,22 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
-k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks, mc_refindex R, int dense,
+k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, mc_refindex R, int dense,
        mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
        unsigned long long *__restrict__ d_counters) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
-    const int64_t warp_global = (int64_t)blockIdx.x * WARPS + wib;
-    const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
+    const int warp_global = (int)blockIdx.x * WARPS + wib;      // chunk indices fit 32 bits (mc_scan checks)
+    const int warp_stride = (int)gridDim.x * WARPS;
+    const int n_chunks = (int)n_chunks64;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // warp-uniform state
     int hint = -1;
     int64_t hint_base = 0;
     int hint_len = 0, hint_nlen = 0;
-    unsigned long long hint_key = 0ull, hint_keymask = 0ull;      // first bytes of the hint contig's name (fast compare)
+    unsigned long long hint_key = 0ull;                           // first bytes of the hint contig's name (fast compare)
     auto set_hint = [&](int c) {
         hint = c;
         hint_base = __ldg(R.d_base + c);
@@ -256,10 +257,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         hint_nlen = __ldg(R.d_name_off + c + 1) - o0;
         hint_key = 0ull;
         for (int j = 0; j < hint_nlen && j < 7; ++j) hint_key |= (unsigned long long)__ldg(R.d_names + o0 + j) << (8 * j);
-        hint_keymask = hint_nlen <= 7 ? ((1ull << (8 * hint_nlen)) - 1ull) : 0ull;
     };
     set_hint(0);
-    unsigned long long slot_cur = 0ull, slot_end = 0ull;          // reserved record slots [cur, end)
+    unsigned long long slot_cur = 0ull;                           // next free reserved record slot
+    unsigned slot_left = 0u;                                      // slots left in the warp's reserved block
     unsigned c_lines = 0, c_kept = 0;                             // warp-uniform; rarer events are counted in S.cnt
     if (lane < 8) S.cnt[lane] = 0u;
 
@@ -270,11 +271,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     }
     __syncwarp();
     uint32_t phase0 = 0u, phase1 = 0u;
-    const int64_t limit = nbytes + MC_TEXT_PAD - 64;              // bytes the slow path may read
 
     // stage a chunk: interior chunks by one TMA bulk copy (asynchronous), edge chunks by guarded loads (synchronous)
-    auto stage = [&](int64_t c, int b) -> bool {
-        const int64_t g0 = c * (int64_t)CHUNK - LOOKB;
+    auto stage = [&](int c, int b) -> bool {
+        const int64_t g0 = (int64_t)c * CHUNK - LOOKB;
         if (g0 >= 0 && g0 + WB <= text_limit16) {
             if (lane == 0) {
                 fence_proxy_async();                               // earlier generic reads of this buffer are done (__syncwarp)
@@ -295,12 +295,12 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     bool cur_async = false;
     if (warp_global < n_chunks) cur_async = stage(warp_global, 0);
 
-    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride, buf ^= 1) {
-        const int64_t G0 = chunk * (int64_t)CHUNK - LOOKB;        // global offset of staged byte 0
+    for (int chunk = warp_global; chunk < n_chunks; chunk += warp_stride, buf ^= 1) {
+        const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
         const bool tail = G0 + WB > nbytes;                       // chunk touches the end of the text
         __syncwarp();
         // ---- 0. prefetch the next chunk, wait for this one ----------------------------------------------------------------
-        const int64_t next = chunk + warp_stride;
+        const int next = chunk + warp_stride;
         bool next_async = false;
         if (next < n_chunks) next_async = stage(next, buf ^ 1);
         if (cur_async) {
@@ -371,14 +371,14 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         c_lines += (unsigned)total_lines;
 
         // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
-        if (slot_end - slot_cur < (unsigned long long)total_lines) {
+        if (slot_left < (unsigned)total_lines) {
             unsigned long long got = 0ull;
             const unsigned want = total_lines > RESERVE ? (unsigned)total_lines : (unsigned)RESERVE;
             if (lane == 0) got = atomicAdd(&d_counters[MC_C_RECORDS], (unsigned long long)want);
             slot_cur = __shfl_sync(0xffffffffu, got, 0);
-            slot_end = slot_cur + want;
+            slot_left = want;
         }
-        const unsigned long long chunk_base = slot_cur;
+        unsigned n_emitted = 0u;
 
         // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold the
         // look-ahead words instead of a single lane walking the bit map
@@ -445,10 +445,12 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 if (f11 < e) {
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
                     const unsigned long long k8 = load8(text, f0);
-                    const bool hit = hint_keymask && (k8 & hint_keymask) == hint_key && ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull;
+                    // names of up to 7 bytes compare in registers: the name bytes and the whitespace right after them
+                    const bool hit = hint_nlen <= 7 && (k8 & ((1ull << (8 * hint_nlen)) - 1ull)) == hint_key &&
+                                     ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull;
                     status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, cid, pos);
                 } else if (e >= NW * 32 || f11 >= NW * 32) {
-                    status = classify_from_global(d_text, limit, G0 + s, R, hint, hint_base, hint_len, cid, pos);
+                    status = classify_from_global(d_text, nbytes + MC_TEXT_PAD - 64, G0 + s, R, hint, hint_base, hint_len, cid, pos);
                     atomicAdd(&S.cnt[4], 1u);
                 } else {
                     status = ST_SHORT;
@@ -500,13 +502,18 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     atomicAdd(&S.cnt[5], 1u);
                 }
             }
-            slot_cur += __popc(emit_m);
+            {
+                const unsigned ne = (unsigned)__popc(emit_m);
+                slot_cur += ne;
+                slot_left -= ne;
+                n_emitted += ne;
+            }
             __syncwarp();
         }
         if (lane == 0) {
-            d_tile_tab[2 * chunk] = (uint32_t)chunk_base;
+            d_tile_tab[2 * (int64_t)chunk] = (uint32_t)(slot_cur - n_emitted);
             // count | filler flag | state of the chunk's last kept line (0 none, 1 not a candidate, 2 candidate)
-            d_tile_tab[2 * chunk + 1] = (uint32_t)(slot_cur - chunk_base) | (filler << 16) | ((uint32_t)(prev_state + 1) << 17);
+            d_tile_tab[2 * (int64_t)chunk + 1] = n_emitted | (filler << 16) | ((uint32_t)(prev_state + 1) << 17);
         }
         cur_async = next_async;
     }
@@ -540,6 +547,7 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     MC_REQUIRE(rec_cap < (1ll << 32), "record capacity must fit 32 bits");
     const int64_t n_chunks = mc_num_tiles(nbytes);
     if (n_chunks == 0) return MC_OK;
+    MC_REQUIRE(n_chunks < (1ll << 30), "too many chunks (chunk of text larger than 4 TB)");
     int dev = 0, sms = 0;
     MC_CUDA_CHECK(cudaGetDevice(&dev));
     MC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
