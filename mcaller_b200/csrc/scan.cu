@@ -33,7 +33,7 @@ constexpr int LOOKA = 224;
 constexpr int WB = LOOKB + CHUNK + LOOKA;     // 4096 bytes staged per chunk
 constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_WARPS
-#define MC_SCAN_WARPS 23
+#define MC_SCAN_WARPS 24
 #endif
 #ifndef MC_SCAN_MIN_CTAS
 #define MC_SCAN_MIN_CTAS 1
@@ -47,13 +47,10 @@ static_assert(CHUNK % 16 == 0, "chunks must keep 16-byte alignment");
 static_assert(MC_TEXT_PAD >= LOOKA + 64, "text padding must cover the look-ahead");
 
 struct WarpSmem {
-    alignas(128) uint8_t text[2][WB];    // double-buffered staged bytes (TMA destination)
+    alignas(16) uint8_t text[2][WB];     // double-buffered staged bytes (TMA destination, 16-byte aligned)
     alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
-    uint32_t nl[NW + 4];                 // newline bits
-    union {                              // ls is consumed (into registers) before fcnt is produced
-        uint32_t ls[NW + 4];             // line-start bits (owned range only)
-        uint16_t fcnt[NW + 4];           // field starts before each word (exclusive prefix over fs)
-    };
+    alignas(16) uint32_t nl[NW + 4];     // newline bits
+    uint16_t fcnt[NW + 4];               // field starts before each word (exclusive prefix over fs)
     uint16_t lstart[LCAP + 4];
     uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
     alignas(8) unsigned long long bar[2];
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
 k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, mc_refindex R, int dense,
        mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
        unsigned long long *__restrict__ d_counters) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
     const int warp_global = (int)blockIdx.x * WARPS + wib;      // chunk indices fit 32 bits (mc_scan checks)
@@ -313,7 +310,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         const SmemBytes T{text};
 
         // ---- 1. classify: lane owns words lane, lane+32, lane+64, lane+96 ---------------------------------------------------
-        uint32_t prev_tops = 0u;                                  // top bits (nonws | nl << 1) of word 32r-1
+        uint32_t prev_top = 0u;                                   // was the last byte of word 32r-1 non-whitespace
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int w = 32 * r + lane;
@@ -323,30 +320,45 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                                           gt20_msb(vb.z), gt20_msb(vb.w));
             const uint32_t nl = pack32(eq0a_msb(va.x), eq0a_msb(va.y), eq0a_msb(va.z), eq0a_msb(va.w), eq0a_msb(vb.x), eq0a_msb(vb.y),
                                        eq0a_msb(vb.z), eq0a_msb(vb.w));
-            // top bits of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
-            const uint32_t tops = (nonws >> 31) | ((nl >> 31) << 1);
-            uint32_t pt = __shfl_up_sync(0xffffffffu, tops, 1);
-            if (lane == 0) pt = prev_tops;
-            prev_tops = __shfl_sync(0xffffffffu, tops, 31);
+            // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
+            const uint32_t top = nonws >> 31;
+            uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
+            if (lane == 0) pt = prev_top;
+            prev_top = __shfl_sync(0xffffffffu, top, 31);
             S.nl[w] = nl;
-            S.fs[w] = nonws & ~((nonws << 1) | (pt & 1u));
-            // line starts: byte p starts a line iff byte p-1 is '\n'; owned range LOOKB <= p < LOOKB+CHUNK, global p < nbytes
-            uint32_t ls = (nl << 1) | (pt >> 1);
-            const int p0 = 32 * w;
-            if (p0 < LOOKB || p0 >= LOOKB + CHUNK) ls = 0u;       // LOOKB and CHUNK are multiples of 32: whole words
-            else if (tail) {
-                const int64_t room = nbytes - (G0 + p0);
-                if (room <= 0) ls = 0u;
-                else if (room < 32) ls &= (1u << room) - 1u;
-            }
-            S.ls[w] = ls;
+            S.fs[w] = nonws & ~((nonws << 1) | pt);
         }
         if (lane < 8) S.fs[NW + lane] = 0u;
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
 
         // ---- 2. line list + field-start prefix counts: lane owns words 4*lane .. 4*lane+3 -------------------------------------
-        const uint4 lsv = *reinterpret_cast<const uint4 *>(&S.ls[4 * lane]);
+        // line starts: byte p starts a line iff byte p-1 is '\n'; owned words are LOOKB/32 .. (LOOKB+CHUNK)/32 - 1, global p < nbytes
+        uint4 lsv;
+        {
+            const uint4 nlv = *reinterpret_cast<const uint4 *>(&S.nl[4 * lane]);
+            const uint32_t nprev = lane ? S.nl[4 * lane - 1] : 0u;
+            lsv.x = (nlv.x << 1) | (nprev >> 31);
+            lsv.y = (nlv.y << 1) | (nlv.x >> 31);
+            lsv.z = (nlv.z << 1) | (nlv.y >> 31);
+            lsv.w = (nlv.w << 1) | (nlv.z >> 31);
+            constexpr int W_LO = LOOKB / 32, W_HI = (LOOKB + CHUNK) / 32;      // owned words [W_LO, W_HI)
+            const int w0 = 4 * lane;
+            if (w0 < W_LO || w0 >= W_HI) lsv.x = 0u;
+            if (w0 + 1 < W_LO || w0 + 1 >= W_HI) lsv.y = 0u;
+            if (w0 + 2 < W_LO || w0 + 2 >= W_HI) lsv.z = 0u;
+            if (w0 + 3 < W_LO || w0 + 3 >= W_HI) lsv.w = 0u;
+            if (tail) {
+                auto clip = [&](uint32_t v, int w) {
+                    const int64_t room = nbytes - (G0 + 32 * w);
+                    return room <= 0 ? 0u : (room < 32 ? (v & ((1u << room) - 1u)) : v);
+                };
+                lsv.x = clip(lsv.x, w0);
+                lsv.y = clip(lsv.y, w0 + 1);
+                lsv.z = clip(lsv.z, w0 + 2);
+                lsv.w = clip(lsv.w, w0 + 3);
+            }
+        }
         const uint4 fsv = *reinterpret_cast<const uint4 *>(&S.fs[4 * lane]);
         const int pf0 = __popc(fsv.x), pf1 = __popc(fsv.y), pf2 = __popc(fsv.z), pf3 = __popc(fsv.w);
         const int my_cnt = __popc(lsv.x) + __popc(lsv.y) + __popc(lsv.z) + __popc(lsv.w);
