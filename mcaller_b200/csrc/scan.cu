@@ -50,7 +50,6 @@ struct WarpSmem {
     alignas(16) uint8_t text[2][WB];     // double-buffered staged bytes (TMA destination, 16-byte aligned)
     alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
     alignas(16) uint32_t nl[NW + 4];     // newline bits
-    uint16_t fcnt[NW + 4];               // field starts before each word (exclusive prefix over fs)
     uint16_t lstart[LCAP + 4];
     uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
     alignas(8) unsigned long long bar[2];
@@ -105,14 +104,19 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
     return (a >> 7) + b * 2u + c * 512u + d * 131072u;
 }
 
-// ---- rank / select on the field-start bits -----------------------------------------------------------------------------------
-// position of the field start with rank n (0-based over the staged bytes), searching forward from word w;
-// NW*32 when it lies beyond the staged bytes
-__device__ __forceinline__ int select_fs(const WarpSmem &S, int &w, int n) {
-    while (w < NW && (int)S.fcnt[w + 1] <= n) ++w;
-    if (w >= NW) return NW * 32;
-    uint32_t m = S.fs[w];
-    for (int j = n - (int)S.fcnt[w]; j > 0; --j) m &= m - 1u;
+// ---- generic field walk (rare: lines whose first 12 columns do not fit the 160-bit window) ------------------------------
+// position of the n-th (0-based) field start at or after smem offset s; NW*32 when it lies beyond the staged bytes
+__device__ __noinline__ int select_fs_walk(const uint32_t *fs, int s, int n) {
+    int w = s >> 5;
+    uint32_t m = fs[w] & (0xFFFFFFFFu << (s & 31));
+    int c = __popc(m);
+    while (c <= n) {
+        n -= c;
+        if (++w >= NW) return NW * 32;
+        m = fs[w];
+        c = __popc(m);
+    }
+    for (; n > 0; --n) m &= m - 1u;
     return (w << 5) + __ffs(m) - 1;
 }
 __device__ __forceinline__ int next_bit(const uint32_t *m, int q) {
@@ -171,12 +175,10 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
         }
     } else {
         // fewer than 12 field starts within 160 bytes: short line or unusually wide columns -> generic walk
-        int w = w0;
-        const int k0 = (int)S.fcnt[w] + __popc(S.fs[w] & ((1u << sh) - 1u));
-        f0 = select_fs(S, w, k0);
-        f1 = select_fs(S, w, k0 + 1);
-        f9 = select_fs(S, w, k0 + 9);
-        f11 = select_fs(S, w, k0 + 11);
+        f0 = select_fs_walk(S.fs, s, 0);
+        f1 = select_fs_walk(S.fs, s, 1);
+        f9 = select_fs_walk(S.fs, s, 9);
+        f11 = select_fs_walk(S.fs, s, 11);
     }
 }
 
@@ -332,7 +334,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
 
-        // ---- 2. line list + field-start prefix counts: lane owns words 4*lane .. 4*lane+3 -------------------------------------
+        // ---- 2. line list: lane owns words 4*lane .. 4*lane+3 ------------------------------------------------------------------
         // line starts: byte p starts a line iff byte p-1 is '\n'; owned words are LOOKB/32 .. (LOOKB+CHUNK)/32 - 1, global p < nbytes
         uint4 lsv;
         {
@@ -359,27 +361,15 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 lsv.w = clip(lsv.w, w0 + 3);
             }
         }
-        const uint4 fsv = *reinterpret_cast<const uint4 *>(&S.fs[4 * lane]);
-        const int pf0 = __popc(fsv.x), pf1 = __popc(fsv.y), pf2 = __popc(fsv.z), pf3 = __popc(fsv.w);
         const int my_cnt = __popc(lsv.x) + __popc(lsv.y) + __popc(lsv.z) + __popc(lsv.w);
-        const int my_fs = pf0 + pf1 + pf2 + pf3;
-        int incl = my_cnt | (my_fs << 16);                         // both scans in one: lines low half, field starts high half
+        int incl = my_cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int tt = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += tt;
         }
-        const int totals = __shfl_sync(0xffffffffu, incl, 31);
-        const int total_lines = totals & 0xFFFF;
-        const int my_first = (incl & 0xFFFF) - my_cnt;
-        const int my_first_fs = (incl >> 16) - my_fs;
-        {
-            // fcnt[w] = field starts before word w
-            const uint32_t a = (uint32_t)my_first_fs | ((uint32_t)(my_first_fs + pf0) << 16);
-            const uint32_t b = (uint32_t)(my_first_fs + pf0 + pf1) | ((uint32_t)(my_first_fs + pf0 + pf1 + pf2) << 16);
-            *reinterpret_cast<uint2 *>(&S.fcnt[4 * lane]) = make_uint2(a, b);
-            if (lane == 31) S.fcnt[NW] = (uint16_t)(my_first_fs + my_fs);
-        }
+        const int total_lines = __shfl_sync(0xffffffffu, incl, 31);
+        const int my_first = incl - my_cnt;
         c_lines += (unsigned)total_lines;
 
         // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
