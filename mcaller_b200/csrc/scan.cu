@@ -196,10 +196,11 @@ enum { ST_KEPT = 1u, ST_CAND = 2u, ST_SHORT = 4u, ST_UNKNOWN = 8u, ST_NNN = 16u,
 // contig / NNNNNN / position / candidate test of one line whose columns 1, 2, 10 start at f0, f1, f9
 template <class B>
 __device__ __forceinline__ uint32_t classify_line(const B &t, int f0, int f1, int f9, const mc_refindex &R, int hint, int64_t hint_base,
-                                                  int hint_len, int known_cid, int &cid, int &pos) {
+                                                  int hint_len, int known_cid, int nnn_state /* 1 yes, 0 no, -1 unknown */, int &cid,
+                                                  int &pos) {
     cid = known_cid >= 0 ? known_cid : contig_lookup(t, f0, R, hint);
     if (cid < 0) return ST_UNKNOWN;
-    if (is_nnnnnn(t, f9)) return ST_NNN;
+    if (nnn_state > 0 || (nnn_state < 0 && is_nnnnnn(t, f9))) return ST_NNN;
     if (!parse_uint(t, f1, pos)) return ST_BADPOS;
     uint32_t st = ST_KEPT;
     const int len = (cid == hint) ? hint_len : __ldg(R.d_len + cid);
@@ -228,7 +229,7 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
         } else if (ws) in_tok = false;
     }
     if (nf < 12) return ST_SHORT;
-    return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, cid, pos);
+    return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, cid, pos);
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
@@ -362,14 +363,23 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
         }
         const int my_cnt = __popc(lsv.x) + __popc(lsv.y) + __popc(lsv.z) + __popc(lsv.w);
-        int incl = my_cnt;
+        // exclusive prefix of the per-lane counts: two ballots when every lane holds at most 3 line starts (always, for
+        // ~128-byte lines), a shuffle scan otherwise
+        int my_first, total_lines;
+        if (__ballot_sync(0xffffffffu, my_cnt > 3) == 0u) {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, my_cnt & 1), b1 = __ballot_sync(0xffffffffu, my_cnt & 2);
+            my_first = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask);
+            total_lines = __popc(b0) + 2 * __popc(b1);
+        } else {
+            int incl = my_cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int tt = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += tt;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tt = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += tt;
+            }
+            total_lines = __shfl_sync(0xffffffffu, incl, 31);
+            my_first = incl - my_cnt;
         }
-        const int total_lines = __shfl_sync(0xffffffffu, incl, 31);
-        const int my_first = incl - my_cnt;
         c_lines += (unsigned)total_lines;
 
         // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
@@ -450,7 +460,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     // names of up to 7 bytes compare in registers: the name bytes and the whitespace right after them
                     const bool hit = hint_nlen <= 7 && (k8 & ((1ull << (8 * hint_nlen)) - 1ull)) == hint_key &&
                                      ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull;
-                    status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, cid, pos);
+                    // model_kmer == 'NNNNNN' (:167): first byte in the common case, one 8-byte register compare otherwise
+                    int nnn = 0;
+                    if (text[f9] == 'N') {
+                        const unsigned long long m8 = load8(text, f9);
+                        nnn = ((m8 & 0xFFFFFFFFFFFFull) == 0x4E4E4E4E4E4Eull && ((m8 >> 48) & 0xFFull) <= 0x20ull) ? 1 : 0;
+                    }
+                    status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, nnn, cid, pos);
                 } else if (e >= NW * 32 || f11 >= NW * 32) {
                     status = classify_from_global(d_text, nbytes + MC_TEXT_PAD - 64, G0 + s, R, hint, hint_base, hint_len, cid, pos);
                     atomicAdd(&S.cnt[4], 1u);
