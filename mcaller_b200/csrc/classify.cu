@@ -25,65 +25,104 @@ __device__ __forceinline__ double activate(double v, int act) {
 }
 
 // sklearn MLPClassifier._forward_pass_fast (neural_network/_multilayer_perceptron.py) for a binary classifier:
-// hidden activations, logistic output, P(class 1) = expit(z)
+// hidden activations, logistic output, P(class 1) = expit(z).
+// Persistent warps: a block stages the weights and intercepts of both models in shared memory once (7-100-1: 7.2 KB per
+// model) and its warps then stride over the calls, so the inner loops read nothing but shared memory; the features of a
+// warp's next call are fetched while the current one is evaluated.  STAGED = false (models too wide for shared memory)
+// reads the weights through the read-only cache instead.
+template <bool STAGED>
 __global__ void __launch_bounds__(WARPS * 32)
-k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int width) {
-    extern __shared__ __align__(16) double s_act[];          // [WARPS][2][width]
+k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int width, int nw0, int nb0, int nw1, int nb1, int alias) {
+    extern __shared__ __align__(16) double s_mlp[];          // [weights 0][biases 0][weights 1][biases 1][WARPS][2][width]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * WARPS + warp;
-    if (i >= n) return;
-    mc_call &c = calls[i];
-    if (c.kind != MC_CALL) return;
-    const mc_model &m = c.model_sel ? m1 : m0;
+    double *s_act = s_mlp;
+    if (STAGED) {
+        for (int j = threadIdx.x; j < nw0; j += WARPS * 32) s_mlp[j] = __ldg(m0.d_weights + j);
+        for (int j = threadIdx.x; j < nb0; j += WARPS * 32) s_mlp[nw0 + j] = __ldg(m0.d_biases + j);
+        for (int j = threadIdx.x; j < nw1; j += WARPS * 32) s_mlp[nw0 + nb0 + j] = __ldg(m1.d_weights + j);
+        for (int j = threadIdx.x; j < nb1; j += WARPS * 32) s_mlp[nw0 + nb0 + nw1 + j] = __ldg(m1.d_biases + j);
+        s_act = s_mlp + nw0 + nb0 + nw1 + nb1;
+        __syncthreads();
+    }
     double *a = s_act + (size_t)warp * 2 * width, *b = a + width;
-    if (lane < m.sizes[0]) a[lane] = c.feat[lane];
-    __syncwarp();
-    const double *w = m.d_weights, *bi = m.d_biases;
-    double out = 0.0;
-    for (int l = 0; l < m.n_layers; ++l) {
-        const int ni = m.sizes[l], no = m.sizes[l + 1];
-        const bool last = (l + 1 == m.n_layers);
-        if (no >= 8) {
-            // four outputs per lane at a time: independent FMA / activation chains interleave and hide each other's latency
-            for (int o0 = 0; o0 < no; o0 += 128) {
-                double acc[4];
+    const int64_t stride = (int64_t)gridDim.x * WARPS;
+    int64_t i = (int64_t)blockIdx.x * WARPS + warp;
+    // features (and row kind / model selector) of the call the warp handles next
+    auto fetch = [&](int64_t idx, double &f, int &kind_sel) {
+        f = 0.0;
+        kind_sel = -1;
+        if (idx < n) {
+            const mc_call &c = calls[idx];
+            kind_sel = c.kind == MC_CALL ? (int)c.model_sel : -1;
+            if (lane <= MC_MAXK) f = c.feat[lane];
+        }
+    };
+    double f_cur;
+    int ks_cur;
+    fetch(i, f_cur, ks_cur);
+    for (; i < n; i += stride) {
+        double f_next;
+        int ks_next;
+        fetch(i + stride, f_next, ks_next);
+        if (ks_cur >= 0) {
+            const mc_model &m = ks_cur ? m1 : m0;
+            // model 1 follows model 0 in shared memory unless both selectors name the same model (alias)
+            const double *w = STAGED ? ((ks_cur && !alias) ? s_mlp + nw0 + nb0 : s_mlp) : m.d_weights;
+            const double *bi = STAGED ? ((ks_cur && !alias) ? s_mlp + nw0 + nb0 + nw1 : s_mlp + nw0) : m.d_biases;
+            auto ld = [&](const double *p) { return STAGED ? *p : __ldg(p); };
+            double *x = a, *y = b;
+            if (lane < m.sizes[0]) x[lane] = f_cur;
+            __syncwarp();
+            for (int l = 0; l < m.n_layers; ++l) {
+                const int ni = m.sizes[l], no = m.sizes[l + 1];
+                const bool last = (l + 1 == m.n_layers);
+                if (no >= 8) {
+                    // four outputs per lane at a time: independent FMA / activation chains interleave and hide each other's latency
+                    for (int o0 = 0; o0 < no; o0 += 128) {
+                        double acc[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = 0.0;
-                for (int k = 0; k < ni; ++k) {
-                    const double ak = a[k];
+                        for (int j = 0; j < 4; ++j) acc[j] = 0.0;
+                        for (int k = 0; k < ni; ++k) {
+                            const double ak = x[k];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int o = o0 + lane + 32 * j;
-                        if (o < no) acc[j] = fma(ak, __ldg(w + (size_t)k * no + o), acc[j]);
+                            for (int j = 0; j < 4; ++j) {
+                                const int o = o0 + lane + 32 * j;
+                                if (o < no) acc[j] = fma(ak, ld(w + (size_t)k * no + o), acc[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int o = o0 + lane + 32 * j;
+                            if (o < no) {
+                                const double z = acc[j] + ld(bi + o);          // dot product first, then the intercept (as sklearn)
+                                y[o] = last ? z : activate(z, m.hidden_act);
+                            }
+                        }
+                    }
+                } else {
+                    for (int o = 0; o < no; ++o) {
+                        double acc = 0.0;
+                        for (int k = lane; k < ni; k += 32) acc = fma(x[k], ld(w + (size_t)k * no + o), acc);
+                        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                        acc += ld(bi + o);
+                        if (lane == 0) y[o] = last ? acc : activate(acc, m.hidden_act);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int o = o0 + lane + 32 * j;
-                    if (o < no) {
-                        const double z = acc[j] + __ldg(bi + o);          // dot product first, then the intercept (as sklearn)
-                        b[o] = last ? z : activate(z, m.hidden_act);
-                    }
-                }
+                __syncwarp();
+                double *t = x; x = y; y = t;
+                w += (size_t)ni * no;
+                bi += no;
             }
-        } else {
-            for (int o = 0; o < no; ++o) {
-                double acc = 0.0;
-                for (int k = lane; k < ni; k += 32) acc = fma(a[k], __ldg(w + (size_t)k * no + o), acc);
-                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                acc += __ldg(bi + o);
-                if (lane == 0) b[o] = last ? acc : activate(acc, m.hidden_act);
+            const double out = expit(x[0]);
+            __syncwarp();
+            if (lane == 0) {
+                mc_call &c = calls[i];
+                c.prob = out;
+                c.label = (uint8_t)(out >= 0.5);
             }
         }
-        __syncwarp();
-        double *t = a; a = b; b = t;
-        w += (size_t)ni * no;
-        bi += no;
-    }
-    out = expit(a[0]);
-    if (lane == 0) {
-        c.prob = out;
-        c.label = (uint8_t)(out >= 0.5);
+        f_cur = f_next;
+        ks_cur = ks_next;
     }
 }
 
@@ -235,8 +274,29 @@ extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *mo
             for (int l = 0; l <= m0.n_layers; ++l) width = m0.sizes[l] > width ? m0.sizes[l] : width;
             for (int l = 0; l <= m1.n_layers && m1.kind == MC_MLP; ++l) width = m1.sizes[l] > width ? m1.sizes[l] : width;
             width = (width + 3) & ~3;
-            const size_t smem = sizeof(double) * 2 * (size_t)width * WARPS;
-            k_mlp<<<(unsigned)((n_calls + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(d_calls, n_calls, m0, m1, width);
+            auto count = [](const mc_model &m, int &nw, int &nb) {
+                nw = nb = 0;
+                if (m.kind != MC_MLP) return;
+                for (int l = 0; l < m.n_layers; ++l) { nw += m.sizes[l] * m.sizes[l + 1]; nb += m.sizes[l + 1]; }
+            };
+            int nw0, nb0, nw1, nb1;
+            count(m0, nw0, nb0);
+            count(m1, nw1, nb1);
+            const int alias = (m1.kind == MC_MLP && m1.d_weights == m0.d_weights) ? 1 : 0;
+            if (alias) nw1 = nb1 = 0;                             // one model given twice: stage it once
+            int dev = 0, sms = 0;
+            MC_CUDA_CHECK(cudaGetDevice(&dev));
+            MC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const size_t act_bytes = sizeof(double) * 2 * (size_t)width * WARPS;
+            const size_t staged_bytes = act_bytes + sizeof(double) * (size_t)(nw0 + nb0 + nw1 + nb1);
+            int64_t blocks = (n_calls + WARPS - 1) / WARPS;
+            if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;           // persistent: warps stride over the calls
+            if (staged_bytes <= 100 * 1024) {
+                MC_CUDA_CHECK(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
+                k_mlp<true><<<(unsigned)blocks, WARPS * 32, staged_bytes, st>>>(d_calls, n_calls, m0, m1, width, nw0, nb0, nw1, nb1, alias);
+            } else {
+                k_mlp<false><<<(unsigned)blocks, WARPS * 32, act_bytes, st>>>(d_calls, n_calls, m0, m1, width, 0, 0, 0, 0, 0);
+            }
             break;
         }
         case MC_LR:

@@ -191,17 +191,40 @@ __device__ __forceinline__ unsigned long long load8(const uint8_t *text, int q) 
     return ((unsigned long long)hi << 32) | lo;
 }
 
+// position column decoded from its first 8 bytes in registers: up to 7 digits and the byte that ends them.
+// Returns 1 (pos set), 0 (not a number / not followed by whitespace) or -1 (8 or more digits: take the byte loop).
+__device__ __forceinline__ uint32_t conv4(uint32_t h) {            // 4 digit values, most significant in byte 0 -> 0..9999
+    const uint32_t t = ((h * 2561u) >> 8) & 0x00ff00ffu;
+    return (t * 6553601u) >> 16;
+}
+__device__ __forceinline__ int parse_pos8(unsigned long long k8, int &pos) {
+    const uint32_t lo = (uint32_t)k8, hi = (uint32_t)(k8 >> 32);
+    const uint32_t xl = lo ^ 0x30303030u, xh = hi ^ 0x30303030u;
+    const uint32_t ndl = (((xl & 0x7f7f7f7fu) + 0x76767676u) | lo) & 0x80808080u;      // 0x80 where the byte is not a digit
+    const uint32_t ndh = (((xh & 0x7f7f7f7fu) + 0x76767676u) | hi) & 0x80808080u;
+    if ((ndl | ndh) == 0u) return -1;
+    const int n = ndl ? ((__ffs(ndl) - 1) >> 3) : 4 + ((__ffs(ndh) - 1) >> 3);          // leading digits: 0..7
+    const uint32_t term = (n < 4 ? (lo >> (8 * n)) : (hi >> (8 * n - 32))) & 0xFFu;
+    if (n == 0 || term > 0x20u) return 0;
+    // right-align the digits in the 8 bytes (leading zero digits below them), then two 4-digit conversions
+    const int sh = 64 - 8 * n;                                                           // 8..56
+    const uint32_t H = sh < 32 ? __funnelshift_l(xl, xh, sh) : (xl << (sh - 32));
+    const uint32_t L = sh < 32 ? (xl << sh) : 0u;
+    pos = (int)(conv4(L) * 10000u + conv4(H));
+    return 1;
+}
+
 enum { ST_KEPT = 1u, ST_CAND = 2u, ST_SHORT = 4u, ST_UNKNOWN = 8u, ST_NNN = 16u, ST_BADPOS = 32u };
 
 // contig / NNNNNN / position / candidate test of one line whose columns 1, 2, 10 start at f0, f1, f9
 template <class B>
 __device__ __forceinline__ uint32_t classify_line(const B &t, int f0, int f1, int f9, const mc_refindex &R, int hint, int64_t hint_base,
-                                                  int hint_len, int known_cid, int nnn_state /* 1 yes, 0 no, -1 unknown */, int &cid,
-                                                  int &pos) {
+                                                  int hint_len, int known_cid, int nnn_state /* 1 yes, 0 no, -1 unknown */,
+                                                  int pos_state /* 1 pos set, 0 bad, -1 unknown */, int &cid, int &pos) {
     cid = known_cid >= 0 ? known_cid : contig_lookup(t, f0, R, hint);
     if (cid < 0) return ST_UNKNOWN;
     if (nnn_state > 0 || (nnn_state < 0 && is_nnnnnn(t, f9))) return ST_NNN;
-    if (!parse_uint(t, f1, pos)) return ST_BADPOS;
+    if (pos_state == 0 || (pos_state < 0 && !parse_uint(t, f1, pos))) return ST_BADPOS;
     uint32_t st = ST_KEPT;
     const int len = (cid == hint) ? hint_len : __ldg(R.d_len + cid);
     if (pos < len) {
@@ -229,7 +252,7 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
         } else if (ws) in_tok = false;
     }
     if (nf < 12) return ST_SHORT;
-    return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, cid, pos);
+    return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, -1, cid, pos);
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
@@ -466,7 +489,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                         const unsigned long long m8 = load8(text, f9);
                         nnn = ((m8 & 0xFFFFFFFFFFFFull) == 0x4E4E4E4E4E4Eull && ((m8 >> 48) & 0xFFull) <= 0x20ull) ? 1 : 0;
                     }
-                    status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, nnn, cid, pos);
+                    const int pst = parse_pos8(load8(text, f1), pos);
+                    status = classify_line(T, f0, f1, f9, R, hint, hint_base, hint_len, hit ? hint : -1, nnn, pst, cid, pos);
                 } else if (e >= NW * 32 || f11 >= NW * 32) {
                     status = classify_from_global(d_text, nbytes + MC_TEXT_PAD - 64, G0 + s, R, hint, hint_base, hint_len, cid, pos);
                     atomicAdd(&S.cnt[4], 1u);

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Re-collects the round evidence under gpurun_out/ev/ on a GPU box (run via gpurun from the repo root):
+#   1. default bench.py line (the number the driver re-measures)        -> bench_default.json
+#   2. ncu launch list of one full-size step                             -> launches_full_step.csv
+#   3. ncu DRAM bytes of the full-size k_scan launch                     -> k_scan_dram_full_size.csv
+#   4. ncu --set full of k_scan on a 2 GB input (+ source page)          -> k_scan_full.ncu-rep
+# Summaries are produced afterwards in the build container with tools/ncu_summary.py, tools/ncu_phases.py and
+# tools/launch_summary.py and copied into profiles/.
+set -u
+O=gpurun_out/ev
+mkdir -p $O
+timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_full_step.csv \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/launches.log 2>&1
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k k_scan -c 1 --csv --log-file $O/k_scan_dram_full_size.csv \
+    python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/dram.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k k_scan -c 1 -f -o $O/k_scan_full \
+    python bench.py --reads 4000 --steps 1 --warmup 0 --no-e2e --no-cpu > $O/full.log 2>&1
+ls -la $O
+tail -c 600 $O/bench_default.json
