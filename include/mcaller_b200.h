@@ -80,6 +80,8 @@ typedef struct mc_record {
 #define MC_RF_BADNUM 4u    /* event/model mean not a plain decimal (<= 18 digits) */
 #define MC_RF_BADIDX 8u    /* event index not a plain integer */
 #define MC_RF_RAW 16u      /* stage-1 form: event_idx/diff still hold column offsets; cleared by mc_order_records */
+#define MC_RF_NEWREAD 32u  /* read name differs from the previous record's (valid when MC_RF_SEGKNOWN is set) */
+#define MC_RF_SEGKNOWN 64u /* mc_order_records compared the read name with the previous record's */
 
 /* counters written by mc_scan (uint64 each) */
 enum {

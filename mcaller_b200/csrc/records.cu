@@ -183,13 +183,57 @@ __device__ __forceinline__ uint32_t fin_pack16(uint32_t m0, uint32_t m1, uint32_
     return (a >> 7) | (b << 1);
 }
 
+__device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
+
+// 8 bytes at any alignment from two aligned 8-byte loads
+__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+    const int sh = 8 * (int)(a & 7);
+    const unsigned long long lo = __ldg(q);
+    if (sh == 0) return lo;
+    const unsigned long long hi = __ldg(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
+// do the L bytes at pa and pb differ (the '\n' padding after the text keeps the 8-byte loads legal).  Both sides are
+// streamed as aligned 8-byte words and realigned in registers: 1 + ceil(L / 8) loads per side, all independent.
+__device__ __forceinline__ bool bytes_differ(const uint8_t *pa, const uint8_t *pb, int L) {
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(pa), ub = reinterpret_cast<uintptr_t>(pb);
+    const unsigned long long *qa = reinterpret_cast<const unsigned long long *>(ua & ~(uintptr_t)7);
+    const unsigned long long *qb = reinterpret_cast<const unsigned long long *>(ub & ~(uintptr_t)7);
+    const int sa = 8 * (int)(ua & 7), sb = 8 * (int)(ub & 7);
+    unsigned long long a_lo = __ldg(qa), b_lo = __ldg(qb), diff = 0ull;
+#pragma unroll 5
+    for (int j = 0; j < L; j += 8) {
+        const unsigned long long a_hi = __ldg(++qa), b_hi = __ldg(++qb);
+        const unsigned long long va = sa ? ((a_lo >> sa) | (a_hi << (64 - sa))) : a_lo;
+        const unsigned long long vb = sb ? ((b_lo >> sb) | (b_hi << (64 - sb))) : b_lo;
+        unsigned long long d = va ^ vb;
+        if (L - j < 8) d &= (1ull << (8 * (L - j))) - 1ull;               // 1..7 tail bytes
+        diff |= d;
+        a_lo = a_hi;
+        b_lo = b_hi;
+    }
+    return diff != 0ull;
+}
+
 __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
                                                        const unsigned long long *__restrict__ d_n) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *d_n) return;
-    alignas(16) mc_record r = rec[i];
-    if (!(r.flags & MC_RF_RAW)) return;
+    // A warp finishes 31 records; lane 0 re-walks the record before them (the previous warp's last) only to know its
+    // read-name span, so that every lane can compare its read name with its predecessor's, handed over by one shuffle
+    // while both lines are still in L1.  That comparison is the read segmentation flag (MC_RF_NEWREAD).
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long i = warp * 31 + lane - 1;
+    const bool active = i >= 0 && (unsigned long long)i < *d_n;
+    alignas(16) mc_record r;
+    if (active) r = rec[i];
+    else { r.line_lo = 0u; r.line_hi = 0; r.name_off = 0; r.name_len = 0; r.flags = 0; r.pos = 0; r.contig = 0; r.event_idx = 0; r.diff = 0.0; }
+    // lane 0 always walks: the record's owner (previous warp) may be rewriting it right now, only its line offset is stable
+    const bool raw = active && (lane == 0 || (r.flags & MC_RF_RAW));
     const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
+    if (raw) {
     // 16-byte steps from the aligned address at or below the line start; the '\n' padding after the text makes every
     // line end inside readable memory
     const int64_t a0 = line & ~15ll;
@@ -247,50 +291,42 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
     int ev_idx = 0;
     double diff = 0.0;
     if (nf < 11 || name_end < 0 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;   // cannot happen for a kept line
-    else parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+    else if (lane > 0) parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
     r.name_off = (uint16_t)f3;
     r.name_len = (uint16_t)(name_end < 0 ? 0 : name_end - f3);
     r.event_idx = ev_idx;
     r.diff = diff;
     r.flags = (uint8_t)fl;
+    }
+    // read segmentation: same read as the previous record <=> equal name length and bytes (extract_contexts.py:161, :179)
+    const unsigned long long prev_line = __shfl_up_sync(0xffffffffu, (unsigned long long)line, 1);
+    const uint32_t prev_span = __shfl_up_sync(0xffffffffu, (uint32_t)r.name_off | ((uint32_t)r.name_len << 16), 1);
+    if (!active || lane == 0) return;
+    uint32_t fl = r.flags | MC_RF_SEGKNOWN;
+    if (i == 0 || (prev_span >> 16) != r.name_len ||
+        bytes_differ(text + (int64_t)prev_line + (prev_span & 0xFFFFu), text + line + r.name_off, r.name_len))
+        fl |= MC_RF_NEWREAD;
+    r.flags = (uint8_t)fl;
     uint4 *dst = reinterpret_cast<uint4 *>(rec + i);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    dst[0] = src[0];
+    if (raw) dst[0] = src[0];
     dst[1] = src[1];
 }
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
-
-// 8 bytes at any alignment from two aligned 8-byte loads
-__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
-    const int sh = 8 * (int)(a & 7);
-    const unsigned long long lo = __ldg(q);
-    if (sh == 0) return lo;
-    const unsigned long long hi = __ldg(q + 1);
-    return (lo >> sh) | (hi << (64 - sh));
-}
-
 __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n,
                                                   uint32_t *__restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t f = 1u;
     if (i > 0) {
-        const mc_record a = rec[i - 1], b = rec[i];
-        if (a.name_len == b.name_len) {
-            const uint8_t *pa = text + rec_line(a) + a.name_off, *pb = text + rec_line(b) + b.name_off;
-            const int L = a.name_len;
-            unsigned long long diff = 0ull;
-            int j = 0;
-            for (; j + 8 <= L && diff == 0ull; j += 8) diff = load8_unaligned(pa + j) ^ load8_unaligned(pb + j);
-            if (diff == 0ull && j < L) {
-                const unsigned long long m = (1ull << (8 * (L - j))) - 1ull;       // 1..7 tail bytes (padding keeps the loads legal)
-                diff = (load8_unaligned(pa + j) ^ load8_unaligned(pb + j)) & m;
-            }
-            f = diff ? 1u : 0u;
+        const mc_record b = rec[i];
+        if (b.flags & MC_RF_SEGKNOWN) {
+            f = (b.flags & MC_RF_NEWREAD) ? 1u : 0u;              // compared while the record was finished
+        } else {
+            const mc_record a = rec[i - 1];
+            if (a.name_len == b.name_len)
+                f = bytes_differ(text + rec_line(a) + a.name_off, text + rec_line(b) + b.name_off, a.name_len) ? 1u : 0u;
         }
     }
     flags[i] = f;
@@ -356,7 +392,8 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t 
                                  (unsigned long long)rec_out_cap);
     MC_LAUNCH_CHECK();
     // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
-    k_finish_records<<<(unsigned)((rec_out_cap + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
+    // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
+    k_finish_records<<<(unsigned)((rec_out_cap + 247) / 248), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
                                                                             reinterpret_cast<const unsigned long long *>(d_n_out));
     MC_LAUNCH_CHECK();
     return MC_OK;

@@ -296,9 +296,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     uint32_t phase0 = 0u, phase1 = 0u;
 
     // stage a chunk: interior chunks by one TMA bulk copy (asynchronous), edge chunks by guarded loads (synchronous)
+    // chunks 1 .. c_bulk_hi have all 4096 staged bytes inside the (padded) text; chunks >= c_tail_lo touch its end
+    const int64_t q_hi = text_limit16 - WB + LOOKB, q_tail = nbytes - WB + LOOKB;
+    const int c_bulk_hi = q_hi < 0 ? -1 : (int)min(q_hi / CHUNK, (int64_t)0x7fffffff);
+    const int c_tail_lo = q_tail < 0 ? 0 : (int)min(q_tail / CHUNK + 1, (int64_t)0x7fffffff);
     auto stage = [&](int c, int b) -> bool {
         const int64_t g0 = (int64_t)c * CHUNK - LOOKB;
-        if (g0 >= 0 && g0 + WB <= text_limit16) {
+        if (c >= 1 && c <= c_bulk_hi) {
             if (lane == 0) {
                 fence_proxy_async();                               // earlier generic reads of this buffer are done (__syncwarp)
                 tma_load_1d(S.text[b], d_text + g0, WB, &S.bar[b]);
@@ -320,7 +324,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 
     for (int chunk = warp_global; chunk < n_chunks; chunk += warp_stride, buf ^= 1) {
         const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
-        const bool tail = G0 + WB > nbytes;                       // chunk touches the end of the text
+        const bool tail = chunk >= c_tail_lo;                     // chunk touches the end of the text (G0 + WB > nbytes)
         __syncwarp();
         // ---- 0. prefetch the next chunk, wait for this one ----------------------------------------------------------------
         const int next = chunk + warp_stride;
@@ -369,11 +373,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             lsv.z = (nlv.z << 1) | (nlv.y >> 31);
             lsv.w = (nlv.w << 1) | (nlv.z >> 31);
             constexpr int W_LO = LOOKB / 32, W_HI = (LOOKB + CHUNK) / 32;      // owned words [W_LO, W_HI)
+            static_assert(W_LO == 1 && W_HI == 121, "the lane tests below assume words 1..120 are owned");
             const int w0 = 4 * lane;
-            if (w0 < W_LO || w0 >= W_HI) lsv.x = 0u;
-            if (w0 + 1 < W_LO || w0 + 1 >= W_HI) lsv.y = 0u;
-            if (w0 + 2 < W_LO || w0 + 2 >= W_HI) lsv.z = 0u;
-            if (w0 + 3 < W_LO || w0 + 3 >= W_HI) lsv.w = 0u;
+            if (lane == 0) lsv.x = 0u;                                          // word 0 is look-behind
+            if (lane >= 30) {                                                   // words 121..127 are look-ahead
+                if (lane == 31) lsv.x = 0u;
+                lsv.y = 0u; lsv.z = 0u; lsv.w = 0u;
+            }
             if (tail) {
                 auto clip = [&](uint32_t v, int w) {
                     const int64_t room = nbytes - (G0 + 32 * w);
