@@ -214,6 +214,9 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
         ++i;
         r = r_next;
         if (i + 1 < e) r_next = load_rec(rec + i + 1);              // overlap the next record's latency with this one's work
+        // a lane streams its own 32-byte records: pull the 128-byte line 16 records ahead into L2 (L1 is left to the
+        // column state, which lives in local memory).  Count pass only: in the write pass the prefetch was measured slower.
+        if (!WRITE && (i & 3u) == 0u && (int64_t)i + 16 < n_records) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + i + 16));
     };
     int rev = 0, first_m = -1, cid = 0, pos = 0;
     bool pending_close = false, handoff_done = false;
