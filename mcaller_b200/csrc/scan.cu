@@ -12,15 +12,16 @@
 //      warp's next chunk into the other buffer and the warp waits on this buffer's mbarrier;
 //   1. each lane classifies 4 x 32 B in registers (SWAR compare + IDP.4A bit packing) into two bit maps --
 //      non-whitespace (byte > 0x20) and newline (byte == 0x0a); field starts = nonws & ~(nonws << 1);
-//   2. line starts inside the chunk are compacted into a list with one warp scan, which also yields the running count
-//      of field starts per 32-byte word;
+//   2. line starts inside the chunk come from the newline map; per-lane counts are prefix-summed with two ballots and
+//      the starts are compacted into a 32-entry list;
 //   3. one lane per line: rank/select on the field-start bits finds columns 1, 2, 10 and 12 without touching the bytes
-//      in between (the ~58 B read name is never walked); the contig is compared in registers against a warp-uniform
-//      hint, column 2 is parsed and the per-position candidate bitmap (L1/L2 resident) is tested;
+//      in between (the ~58 B read name is never walked); the contig and the NNNNNN test are 8-byte register compares
+//      against a warp-uniform hint, column 2 is decoded from one 8-byte register load and the per-position candidate
+//      bitmap (L1/L2 resident) is tested;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the chunk, or
 //      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags}.  Their
 //      values (event index, currents, k-mer equality, read-name span) are parsed in stage 2 at full lane occupancy.
-//      Record slots are reserved per warp in blocks, so the global allocation counter sees ~1 atomic per 80 chunks.
+//      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
 // Algorithmic HBM traffic: the text itself (once) + 32 B per record (~2 B per line in sparse mode).
 #include "parse.cuh"
