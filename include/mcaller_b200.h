@@ -251,7 +251,8 @@ int mc_count_calls(const mc_call *d_calls, int64_t n_calls, uint64_t *d_out, voi
  * make_bed drop-in: aggregate a `.diffs.<k>` text file (make_bed.py:75-98, default mode).  d_table is an open-addressing
  * table (power-of-two entries; hash == 0 means empty, first_off must be initialised to ~0) keyed by the FNV-1a hash of
  * "chrom\tpos\tcontext\tstrand"; first_off is the smallest byte offset of a row with that key (first-seen order, :134).
- * d_counters[4]: rows, malformed rows (field count not 7/8), rows skipped by the centre-'M' test (:84), table-full drops.
+ * d_counters[8] (see mc_diffs_aggregate_ex): rows, malformed rows (field count not 7/8), rows skipped by the centre-'M'
+ * test (:84), table-full drops, ...
  */
 typedef struct mc_locus_entry {
     unsigned long long hash;
@@ -261,6 +262,40 @@ typedef struct mc_locus_entry {
 } mc_locus_entry;
 int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_table, int64_t table_size,
                        uint64_t *d_counters, void *stream);
+
+/*
+ * make_bed variants that need per-read lists (make_bed.py -p and --vo).
+ *
+ * mc_diffs_aggregate_ex: mc_diffs_aggregate with the `-p` filter of make_bed.py:73-74/:84 -- d_posset (may be NULL) is an
+ *   open-addressing set (power-of-two entries, 0 = empty) of FNV-1a hashes of "chrom\tpos\tstrand" built by the host from
+ *   the positions file (entries whose end column is not start + 1 can never match and are left out).
+ *   d_counters[8]: rows, malformed, centre-not-'M', table-full drops, rows outside the positions set, old-format rows
+ *   (7 fields), value tokens float() would not parse, value tokens outside the exactly-rounded range.
+ * mc_diffs_rows: second pass; one mc_diffs_row per used row in arbitrary order (sort by line_off for file order):
+ *   the locus slot in d_table, and the spans of the values (column 5) and stripped probability (column 8) fields.
+ * mc_diffs_colstats: the one-sample t-test inputs of make_bed.py:115-127 (scipy.stats.ttest_1samp, popmean 0).  d_order
+ *   lists the row indices grouped by locus in file order, d_locus_off[n_loci + 1] is the CSR over that order.  Values are
+ *   parsed like `[float(v) for v in values.split(',')][:-1]` (exactly rounded) into d_vals[n_rows][MC_MAXK + 1] /
+ *   d_ncol[n_rows]; d_stats[n_loci][ncols][2] receives np.mean(x) and np.add.reduce((x - mean)**2) in numpy's pairwise
+ *   summation order, so t = mean / sqrt(ss / n * (n / (n - 1)) / n) is bit-identical to scipy's.
+ */
+typedef struct mc_diffs_row {
+    uint64_t line_off;         /* byte offset of the row in the file */
+    uint32_t slot;             /* index of its locus in d_table */
+    uint32_t values_off;       /* column 5 (comma-joined features), relative to line_off */
+    uint32_t values_len;
+    uint32_t prob_off;         /* column 8 without surrounding whitespace; length 0 for old-format rows */
+    uint32_t prob_len;
+    uint32_t pad;
+} mc_diffs_row;                /* 32 bytes */
+int mc_diffs_aggregate_ex(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,
+                          mc_locus_entry *d_table, int64_t table_size, uint64_t *d_counters, void *stream);
+int mc_diffs_rows(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,
+                  const mc_locus_entry *d_table, int64_t table_size, mc_diffs_row *d_rows, int64_t row_cap, uint64_t *d_nrows,
+                  void *stream);
+int mc_diffs_colstats(const uint8_t *d_text, const mc_diffs_row *d_rows, const uint32_t *d_order, int64_t n_rows,
+                      const uint32_t *d_locus_off, int64_t n_loci, int ncols, double *d_vals, uint32_t *d_ncol,
+                      double *d_stats, uint64_t *d_counters, void *stream);
 
 /*
  * Host-side writer (no device work): renders the MC_CALL rows of a chunk (host copy of the mc_call array; rows still

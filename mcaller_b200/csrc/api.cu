@@ -32,6 +32,7 @@ extern "C" int mc_sizeof(int what) {
         case 4: return (int)sizeof(mc_qual_entry);
         case 5: return (int)sizeof(mc_synth_spec);
         case 6: return (int)sizeof(mc_locus_entry);
+        case 7: return (int)sizeof(mc_diffs_row);
         default: return -1;
     }
 }

@@ -1,8 +1,17 @@
 """Drop-in replacement for the hot part of the reference's make_bed.py: `aggregate_by_pos` (make_bed.py:67-164) and
 `check_thresh` (:21-28) with the same signatures.  The per-position depth / methylated counts are built on the GPU
-(mc_diffs_aggregate: tab-split of the `.diffs.<k>` rows + integer atomics in a hash table); the host only formats
-the BED/GFF rows of the surviving loci in first-seen order.  Reporting variants that need per-read value lists
-(-p positions with t-tests, --vo, --plot*) are out of scope and raise NotImplementedError.
+(mc_diffs_aggregate_ex: tab-split of the `.diffs.<k>` rows + integer atomics in a hash table); the host formats the
+BED/GFF rows of the surviving loci in first-seen order.
+
+Variants:
+* `--vo` (verbose_results): the GPU indexes the used rows (mc_diffs_rows); the host joins the probability strings of each
+  locus in file order (:158-159) and, with `--gff`, calls the same scipy/numpy functions as the reference on them
+  (fracLow / fracUp / identificationQv, :147-151).
+* `-p positions`: rows are filtered on the GPU through a hash set of the positions file; the per-locus, per-column
+  one-sample t-tests of :115-127 are computed from exactly parsed values with numpy's summation order on the GPU
+  (mc_diffs_colstats) and finished (Student-t tail, -log10, rounding) on the host with scipy's own special function.
+`--plot` / `--plotsummary` (matplotlib figures) are out of scope and raise NotImplementedError.  The reference's debugging
+`print(values_dict)` / `print(aggfi)` lines are not reproduced.
 """
 import ctypes as C
 import os
@@ -10,6 +19,8 @@ import os
 import numpy as np
 
 LOCUS_DTYPE = np.dtype([("hash", "<u8"), ("first_off", "<u8"), ("depth", "<u4"), ("meth", "<u4")])
+
+_FNV_OFF, _FNV_PRIME, _M64 = 14695981039346656037, 1099511628211, (1 << 64) - 1
 
 
 def check_thresh(locus_list, mod_thresh, depth_thresh, control):
@@ -30,64 +41,230 @@ def _check_counts(depth, meth, mod_thresh, depth_thresh, control):
     return False
 
 
+def make_pos_set(pos_list):
+    """reference make_bed.py:13-19."""
+    pos_set = set()
+    with open(pos_list, "r") as fi:
+        for line in fi:
+            if len(line) > 3:
+                pos_set.add(tuple(line.strip().split("\t")[:4]))
+    return pos_set
+
+
+def _fnv(parts):
+    h = _FNV_OFF
+    for i, part in enumerate(parts):
+        if i:
+            h = ((h ^ 9) * _FNV_PRIME) & _M64
+        for b in part:
+            h = ((h ^ b) * _FNV_PRIME) & _M64
+    return h or 1
+
+
+def _pos_hash_set(pos_set):
+    """Open-addressing set of FNV-1a("chrom\\tpos\\tstrand") for the entries a row can match: the reference tests
+    (csome, pos, str(int(pos)+1), strand) in pos_set (:83-84), so an entry whose end column is not start + 1 never matches."""
+    keys = set()
+    for t in pos_set:
+        if len(t) != 4:
+            continue
+        chrom, start, end, strand = t
+        try:
+            if str(int(start) + 1) != end:
+                continue
+        except ValueError:
+            continue
+        keys.add(_fnv([chrom.encode(), start.encode(), strand.encode()]))
+    size = 64
+    while size < 2 * len(keys) + 2:
+        size *= 2
+    tab = np.zeros(size, dtype=np.uint64)
+    mask = size - 1
+    for k in keys:
+        s = k & mask
+        while tab[s] != 0 and tab[s] != k:
+            s = (s + 1) & mask
+        tab[s] = k
+    return tab
+
+
+class _Aggregation(object):
+    """GPU passes over one `.diffs.<k>` file."""
+
+    def __init__(self, meth_fi, pos_set=None):
+        import torch
+        from . import _lib, engine
+        engine.require_cuda()
+        self.torch, self._lib, self.L = torch, _lib, _lib.lib()
+        self.path = meth_fi
+        self.data = open(meth_fi, "rb").read()
+        self.n = len(self.data)
+        self.dev = torch.device("cuda")
+        self.loci = []            # (chrom, pos, context, strand, depth, meth) in first-seen order
+        self.slots = np.zeros(0, dtype=np.int64)
+        self.counters = np.zeros(8, dtype=np.int64)
+        if self.n == 0:
+            return
+        self.d_text = torch.from_numpy(np.frombuffer(self.data, dtype=np.uint8).copy()).to(self.dev)
+        self.d_posset = None
+        self.posset_size = 0
+        if pos_set is not None:
+            tab = _pos_hash_set(pos_set)
+            self.d_posset = torch.from_numpy(tab.view(np.int64)).to(self.dev)
+            self.posset_size = len(tab)
+        size = 1024
+        while size < 2 * (self.n // 48 + 16):
+            size *= 2
+        self.table_size = size
+        init = np.zeros(size, dtype=LOCUS_DTYPE)
+        init["first_off"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        self.d_table = torch.from_numpy(init.view(np.uint8).reshape(-1)).to(self.dev)
+        self.d_cnt = torch.zeros(8, dtype=torch.int64, device=self.dev)
+        _lib.check(self.L.mc_diffs_aggregate_ex(self._p(self.d_text), self.n, self._p(self.d_posset), self.posset_size,
+                                                self._p(self.d_table), size, self._p(self.d_cnt), self._stream()))
+        cnt = self.d_cnt.cpu().numpy()
+        self.counters = cnt
+        if cnt[1]:
+            raise ValueError("%d rows of %s do not have 7 or 8 tab-separated fields" % (cnt[1], meth_fi))
+        if cnt[3]:
+            raise RuntimeError("locus table overflow")
+        table = self.d_table.cpu().numpy().view(LOCUS_DTYPE)
+        used = np.nonzero(table["hash"] != 0)[0]
+        order = np.argsort(table["first_off"][used], kind="stable")
+        self.slots = used[order]                              # table slot of each locus, first-seen order
+        for e in table[self.slots]:
+            off = int(e["first_off"])
+            end = self.data.find(b"\n", off)
+            f = self.data[off:end if end >= 0 else self.n].split(b"\t")
+            self.loci.append((f[0].decode(), f[2].decode(), f[3].decode(), f[5].decode(), int(e["depth"]), int(e["meth"])))
+
+    def _p(self, t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def index_rows(self):
+        """Row index grouped by locus (first-seen order) and in file order inside a locus: (rows, order, locus_off)."""
+        torch, _lib = self.torch, self._lib
+        n_rows = int(sum(l[4] for l in self.loci))
+        self.n_rows = n_rows
+        if n_rows == 0:
+            self.rows = np.zeros(0, dtype=_lib.DIFFS_ROW_DTYPE)
+            self.order = np.zeros(0, dtype=np.uint32)
+            self.locus_off = np.zeros(len(self.loci) + 1, dtype=np.uint32)
+            return
+        self.d_rows = torch.zeros(n_rows * _lib.DIFFS_ROW_DTYPE.itemsize, dtype=torch.uint8, device=self.dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        _lib.check(self.L.mc_diffs_rows(self._p(self.d_text), self.n, self._p(self.d_posset), self.posset_size, self._p(self.d_table),
+                                        self.table_size, self._p(self.d_rows), n_rows, self._p(d_n), self._stream()))
+        got = int(d_n.cpu()[0])
+        if got != n_rows:
+            raise RuntimeError("row index holds %d rows, the locus table counted %d" % (got, n_rows))
+        rows = self.d_rows.cpu().numpy().view(_lib.DIFFS_ROW_DTYPE)
+        rank = np.full(self.table_size, -1, dtype=np.int64)
+        rank[self.slots] = np.arange(len(self.slots))
+        self.rows = rows
+        self.order = np.lexsort((rows["line_off"], rank[rows["slot"]])).astype(np.uint32)
+        depth = np.array([l[4] for l in self.loci], dtype=np.int64)
+        self.locus_off = np.concatenate([[0], np.cumsum(depth)]).astype(np.uint32)
+
+    def prob_strings(self, li):
+        """pos_dict_verbose[locus] (:96-97): the stripped probability column of the locus's rows, file order."""
+        out = []
+        for j in self.order[self.locus_off[li]:self.locus_off[li + 1]]:
+            r = self.rows[j]
+            a = int(r["line_off"]) + int(r["prob_off"])
+            out.append(self.data[a:a + int(r["prob_len"])].decode())
+        return out
+
+    def column_tests(self):
+        """values_dict[locus] of :115-127: [np.round(max t, 3), np.round(sum -log10 p, 3)] per locus."""
+        import warnings
+        from scipy import special
+        torch, _lib = self.torch, self._lib
+        n_loci = len(self.loci)
+        if n_loci == 0:
+            return []
+        # number of columns = features per row minus the trailing read quality (:91); taken from the first used row
+        r0 = self.rows[self.order[0]]
+        a = int(r0["line_off"]) + int(r0["values_off"])
+        ncols = len(self.data[a:a + int(r0["values_len"])].split(b",")) - 1
+        if ncols < 1 or ncols > _lib.MC_MAXK + 1:
+            raise ValueError("rows of %s hold %d feature columns" % (self.path, ncols))
+        d_order = torch.from_numpy(self.order.astype(np.int32)).to(self.dev)
+        d_off = torch.from_numpy(self.locus_off.astype(np.int32)).to(self.dev)
+        d_vals = torch.zeros(self.n_rows * (_lib.MC_MAXK + 1), dtype=torch.float64, device=self.dev)
+        d_ncol = torch.zeros(self.n_rows, dtype=torch.int32, device=self.dev)
+        d_stats = torch.zeros(n_loci * ncols * 2, dtype=torch.float64, device=self.dev)
+        _lib.check(self.L.mc_diffs_colstats(self._p(self.d_text), self._p(self.d_rows), self._p(d_order), self.n_rows, self._p(d_off),
+                                            n_loci, ncols, self._p(d_vals), self._p(d_ncol), self._p(d_stats), self._p(self.d_cnt),
+                                            self._stream()))
+        cnt = self.d_cnt.cpu().numpy()
+        self.counters = cnt
+        if cnt[6]:
+            raise ValueError("%d feature values of %s are not plain floats" % (cnt[6], self.path))
+        ncol = d_ncol.cpu().numpy()
+        self.vals = d_vals.cpu().numpy().reshape(self.n_rows, _lib.MC_MAXK + 1)     # parsed features, grouped row order
+        if (ncol != ncols).any():
+            raise ValueError("rows of %s do not all hold %d feature columns" % (self.path, ncols))
+        stats = d_stats.cpu().numpy().reshape(n_loci, ncols, 2)
+        n = (self.locus_off[1:].astype(np.int64) - self.locus_off[:-1].astype(np.int64)).astype(np.float64)[:, None]
+        out = []
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore")
+            # scipy.stats.ttest_1samp(x, 0): mean, _var = mean((x-mean)**2) * (n / (n-1)), t = mean / sqrt(var / n),
+            # p = 2 * stdtr(n-1, -|t|)
+            mean = stats[:, :, 0]
+            var = (stats[:, :, 1] / n) * (n / (n - 1.0))
+            t = mean / np.sqrt(var / n)
+            p = 2 * special.stdtr(n - 1.0, -np.abs(t))
+            for li in range(n_loci):
+                pvals = [(p[li, c], t[li, c]) for c in range(ncols)]
+                pval = (sum([-np.log10(x[0]) for x in pvals]), max([x[1] for x in pvals]))
+                out.append([np.round(x, 3) for x in [pval[1], pval[0]]])
+        return out
+
+
 def count_loci(meth_fi):
     """GPU pass over the file -> list of (chrom, pos, context, strand, depth, meth) in first-seen order."""
-    import torch
-    from . import _lib, engine
-    engine.require_cuda()
-    L = _lib.lib()
-    data = open(meth_fi, "rb").read()
-    n = len(data)
-    if n == 0:
-        return []
-    dev = torch.device("cuda")
-    d_text = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).to(dev)
-    size = 1024
-    while size < 2 * (n // 48 + 16):
-        size *= 2
-    init = np.zeros(size, dtype=LOCUS_DTYPE)
-    init["first_off"] = np.uint64(0xFFFFFFFFFFFFFFFF)
-    d_table = torch.from_numpy(init.view(np.uint8).reshape(-1)).to(dev)
-    d_cnt = torch.zeros(8, dtype=torch.int64, device=dev)
-    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(L.mc_diffs_aggregate(C.c_void_p(d_text.data_ptr()), n, C.c_void_p(d_table.data_ptr()), size, C.c_void_p(d_cnt.data_ptr()), st))
-    cnt = d_cnt.cpu().numpy()
-    if cnt[1]:
-        raise ValueError("%d rows of %s do not have 7 or 8 tab-separated fields" % (cnt[1], meth_fi))
-    if cnt[3]:
-        raise RuntimeError("locus table overflow")
-    table = d_table.cpu().numpy().view(LOCUS_DTYPE)
-    table = table[table["hash"] != 0]
-    table = table[np.argsort(table["first_off"], kind="stable")]
-    out = []
-    for e in table:
-        off = int(e["first_off"])
-        end = data.find(b"\n", off)
-        f = data[off:end if end >= 0 else n].split(b"\t")
-        out.append((f[0].decode(), f[2].decode(), f[3].decode(), f[5].decode(), int(e["depth"]), int(e["meth"])))
-    return out
+    return _Aggregation(meth_fi).loci
+
+
+def _read_fasta(ref):
+    seqs = {}
+    name, parts = None, []
+    for ln in open(ref):                         # make_bed.py:36-40 keeps the case of the file
+        if ln.startswith(">"):
+            if name is not None:
+                seqs[name] = "".join(parts)
+            t = ln[1:].split()
+            name, parts = (t[0] if t else ""), []
+        elif name is not None:
+            parts.append(ln.strip())
+    if name is not None:
+        seqs[name] = "".join(parts)
+    return seqs
 
 
 def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control, verbose_results, gff, ref, plot, plotdir, plotsummary):
-    """reference make_bed.py:67; default mode plus --control, --gff (without --vo) and --ref."""
-    if pos_list or verbose_results or plot or plotsummary:
-        raise NotImplementedError("make_bed -p/--vo/--plot/--plotsummary are outside the accelerated path")
-    loci = count_loci(meth_fi)
+    """reference make_bed.py:67: default mode, --control, --gff, --ref, --vo and -p."""
+    if plot or plotsummary:
+        raise NotImplementedError("make_bed --plot/--plotsummary are outside the accelerated path")
+    pos_set = make_pos_set(pos_list) if pos_list else None
+    agg = _Aggregation(meth_fi, pos_set)
+    loci = agg.loci
+    if verbose_results and agg.counters[5]:
+        raise ValueError("--vo needs the 8-column format: %d rows of %s have no probability column" % (agg.counters[5], meth_fi))
+    tests = None
+    if verbose_results or pos_list:
+        agg.index_rows()
+    if pos_list:
+        tests = agg.column_tests()
     contexts = None
     if ref:
         from . import refmark
-        seqs = {}
-        name, parts = None, []
-        for ln in open(ref):                         # make_bed.py:36-40 keeps the case of the file
-            if ln.startswith(">"):
-                if name is not None:
-                    seqs[name] = "".join(parts)
-                t = ln[1:].split()
-                name, parts = (t[0] if t else ""), []
-            elif name is not None:
-                parts.append(ln.strip())
-        if name is not None:
-            seqs[name] = "".join(parts)
+        seqs = _read_fasta(ref)
         contexts = {}
         for chrom, pos, ctx, strand, _, _ in loci:
             if chrom in seqs:
@@ -95,8 +272,9 @@ def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control
                 contexts[(chrom, pos, ctx, strand)] = refmark.revcomp(cx) if strand == "-" else cx
     count = 0
     with open(aggfi, "w") as outfi:
-        for chrom, pos, ctx, strand, depth, meth in loci:
-            if not _check_counts(depth, meth, mod_thresh, depth_thresh, control):
+        for li, (chrom, pos, ctx, strand, depth, meth) in enumerate(loci):
+            # :134-136 -- thresholds apply without -p; with -p every locus of the positions file is reported
+            if not pos_list and not _check_counts(depth, meth, mod_thresh, depth_thresh, control):
                 continue
             count += 1
             frac = np.float64(meth) / np.float64(depth)
@@ -104,13 +282,25 @@ def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control
             nextpos = str(int(pos) + 1)
             if gff:
                 deets = "coverage=" + str(depth) + ";context=" + cx + ";IPDRatio=5;frac=" + str(frac)
+                if verbose_results:                                      # :147-151
+                    from scipy import stats
+                    probs = [float(x) for x in agg.prob_strings(li)]
+                    se_95 = 2 * stats.sem(probs)
+                    deets = deets + ";fracLow=" + str(frac - se_95) + ";fracUp=" + str(frac + se_95) + ";identificationQv=" + \
+                        str(int(100 * np.mean([float(x) for x in probs])))
                 outfi.write("\t".join([chrom, "kinModCall", "m6A", nextpos, nextpos, "10", strand, ".", deets]) + "\n")
             else:
-                outfi.write("\t".join([chrom, pos, nextpos, ctx, str(frac), strand, str(depth)]) + "\n")
-    if not control:
-        print(count, "methylated loci found with min depth", depth_thresh, "reads")
-    else:
-        print(count, "unmethylated loci found with min depth", depth_thresh, "reads")
+                out_line = "\t".join([chrom, pos, nextpos, ctx, str(frac), strand, str(depth)])
+                if pos_list:
+                    out_line = out_line + "\t" + "\t".join([str(x) for x in tests[li]])
+                if verbose_results:
+                    out_line = out_line + "\t" + ",".join(agg.prob_strings(li))
+                outfi.write(out_line + "\n")
+    if not pos_list:
+        if not control:
+            print(count, "methylated loci found with min depth", depth_thresh, "reads")
+        else:
+            print(count, "unmethylated loci found with min depth", depth_thresh, "reads")
     return count
 
 

@@ -336,3 +336,73 @@ def aggregate(diffs_text, depth_thresh=15, mod_thresh=0.5, control=False):
         if lc.depth >= depth_thresh and ((not control and frac >= mod_thresh) or (control and frac < mod_thresh)):
             out.append("\t".join([key[0], key[1], str(int(key[1]) + 1), key[2], repr(float(frac)), key[3], str(lc.depth)]))
     return out
+
+
+def aggregate_variants(diffs_text, depth_thresh=15, mod_thresh=0.5, control=False, pos_lines=None, verbose=False, gff=False):
+    """make_bed.py aggregate_by_pos with -p / --vo / --gff (make_bed.py:67-164), restated row by row for small inputs.
+    `pos_lines` is the text of the positions file (None without -p).  Uses scipy/numpy exactly where the reference does
+    (stats.ttest_1samp :120, stats.sem :149, np.mean :143, np.round :127)."""
+    import numpy as np
+    from scipy import stats
+    import warnings
+    pos_set = None
+    if pos_lines is not None:                                      # make_pos_set, :13-19
+        pos_set = set()
+        for line in pos_lines.splitlines(True):
+            if len(line) > 3:
+                pos_set.add(tuple(line.strip().split("\t")[:4]))
+    pos_dict, values_dict, verbose_dict = {}, {}, {}
+    for line in diffs_text.splitlines(True):
+        f = line.split("\t")
+        if len(f) == 8:
+            csome, read, pos, context, values, strand, label, prob = f
+        elif len(f) == 7:
+            csome, read, pos, context, values, strand, label = f
+            prob = ""
+        else:
+            raise OracleError("malformed diffs row")
+        nextpos = str(int(pos) + 1)
+        if (pos_set is not None and (csome, pos, nextpos, strand) not in pos_set) or context[int(len(context) / 2)] != "M":   # :84
+            continue
+        key = (csome, pos, nextpos, context, strand)
+        if key not in pos_dict:
+            pos_dict[key], values_dict[key], verbose_dict[key] = [], [], []
+        if pos_set is not None:
+            values_dict[key].append([float(v) for v in values.split(",")][:-1])      # :91
+        pos_dict[key].append(1 if label[0] == "m" else 0)
+        verbose_dict[key].append(prob.strip())
+    out = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if pos_set is not None:                                    # :115-127
+            for key in values_dict:
+                cols = list(zip(*values_dict[key]))
+                pvals = []
+                for col in cols:
+                    t = stats.ttest_1samp(np.asarray(col, dtype=np.float64), 0)
+                    pvals.append((t[1], t[0]))
+                pval = (sum([-np.log10(x[0]) for x in pvals]), max([x[1] for x in pvals]))
+                values_dict[key] = [np.round(x, 3) for x in [pval[1], pval[0]]]
+        for key, lst in pos_dict.items():                          # :132-159
+            frac = np.mean(lst)
+            if pos_set is None:
+                ok = len(lst) >= depth_thresh and ((not control and frac >= mod_thresh) or (control and frac < mod_thresh))
+            else:
+                ok = (key[0], key[1], key[2], key[4]) in pos_set
+            if not ok:
+                continue
+            if gff:
+                deets = "coverage=" + str(len(lst)) + ";context=" + key[3] + ";IPDRatio=5;frac=" + str(frac)
+                if verbose:
+                    probs = [float(x) for x in verbose_dict[key]]
+                    se_95 = 2 * stats.sem(probs)
+                    deets += ";fracLow=" + str(frac - se_95) + ";fracUp=" + str(frac + se_95) + ";identificationQv=" + str(int(100 * np.mean(probs)))
+                out.append("\t".join([key[0], "kinModCall", "m6A", key[2], key[2], "10", key[4], ".", deets]))
+            else:
+                row = "\t".join(list(key)[:-1] + [str(frac)] + [key[-1]] + [str(len(lst))])
+                if pos_set is not None:
+                    row += "\t" + "\t".join([str(x) for x in values_dict[key]])
+                if verbose:
+                    row += "\t" + ",".join(verbose_dict[key])
+                out.append(row)
+    return out

@@ -31,9 +31,12 @@ CASES = {
     # synthetic, three contigs + header line, methylation signal on half the sites
     "gatc_s0": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True,
                     beds=[["-d", "1", "-t", "0.5"], ["-d", "3", "-t", "0.3"], ["-d", "1", "-t", "0.5", "--gff"],
-                          ["-d", "2", "-t", "0.4", "--ref", "ref.fasta"], ["-d", "1", "-t", "0.6", "--control", "--gff", "--ref", "ref.fasta"]]),
+                          ["-d", "2", "-t", "0.4", "--ref", "ref.fasta"], ["-d", "1", "-t", "0.6", "--control", "--gff", "--ref", "ref.fasta"],
+                          ["-d", "1", "-t", "0.5", "--vo"], ["-d", "2", "-t", "0.4", "--gff", "--vo"],
+                          ["-d", "1", "-t", "0.5", "-p", "bedpos.txt"], ["-d", "1", "-t", "0.5", "-p", "bedpos.txt", "--vo"]]),
     "gatc_s1": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1),
-    "gatc_s2": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=2, beds=[["-d", "2", "-t", "0.5"], ["-d", "2", "-t", "0.5", "--control"]]),
+    "gatc_s2": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=2,
+                    beds=[["-d", "2", "-t", "0.5"], ["-d", "2", "-t", "0.5", "--control"], ["-d", "2", "-t", "0.5", "-p", "bedpos.txt"]]),
     # dense multi-M windows (every A is a target), reads truncated so windows stay open across reads/contigs
     "A_s0": dict(spec=_SPEC_A, motif="A", model=R95, base="A", post="truncate"),
     "A_s2": dict(spec=_SPEC_A, motif="A", model=R95, base="A", s=2, post="truncate"),
@@ -200,3 +203,63 @@ def cli_args(case, inputs):
     if case.get("q"):
         a += ["-q", str(case["q"])]
     return a
+
+
+def write_bed_positions(diffs_text, path):
+    """Positions file for `make_bed.py -p` derived from a `.diffs` text: every second locus in first-seen order
+    (chrom, start, start+1, strand), one entry whose end column is wrong (never matches, make_bed.py:83-84), one unknown
+    contig and one short line (skipped by make_pos_set, make_bed.py:17)."""
+    seen, order = set(), []
+    for ln in diffs_text.split("\n"):
+        f = ln.split("\t")
+        if len(f) < 7:
+            continue
+        key = (f[0], f[2], f[5])
+        if key not in seen:
+            seen.add(key)
+            order.append(key)
+    with open(path, "w") as fh:
+        for i, (chrom, pos, strand) in enumerate(order):
+            if i % 2 == 0:
+                fh.write("%s\t%s\t%d\t%s\n" % (chrom, pos, int(pos) + 1, strand))
+            elif i % 7 == 1:
+                fh.write("%s\t%s\t%d\t%s\n" % (chrom, pos, int(pos) + 2, strand))
+        fh.write("nosuchcontig\t10\t11\t+\n")
+        fh.write("x\n")
+
+
+# ---- make_bed-only golden: deep coverage (pairwise-summation paths of the t-tests, 17-digit and scientific-notation values) ----
+BED_DEEP_VARIANTS = [["-d", "1", "-t", "0.5", "-p", "bedpos.txt"], ["-d", "1", "-t", "0.5", "-p", "bedpos.txt", "--vo"],
+                     ["-d", "1", "-t", "0.5", "--vo"], ["-d", "5", "-t", "0.3", "--gff", "--vo"], ["-d", "5", "-t", "0.3", "--gff"]]
+
+
+def deep_diffs_text(seed=7):
+    """Deterministic `.diffs.6` text with loci of depth 1..520, rows interleaved across loci, feature text as repr(float64)."""
+    import random
+    rng = random.Random(seed)
+    depths = [1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 23, 24, 64, 127, 128, 129, 130, 136, 255, 256, 257, 300, 400, 520]
+    rows = []
+    for li, depth in enumerate(depths):
+        chrom = "ctgA" if li % 3 else "ctgB"
+        pos = 1000 + 37 * li
+        strand = "+" if li % 2 else "-"
+        ctx = "".join(rng.choice("ACGT") for _ in range(5)) + "M" + "".join(rng.choice("ACGT") for _ in range(5))
+        shift = rng.uniform(-1.5, 1.5)
+        for d in range(depth):
+            feats = []
+            for c in range(6):
+                u = rng.random()
+                if u < 0.05:
+                    feats.append("0")                                   # empty column
+                elif u < 0.10:
+                    feats.append(repr(rng.gauss(0, 3) * 1e-5))           # scientific notation
+                elif u < 0.30:
+                    feats.append(repr(round(rng.gauss(shift, 2), 4)))    # few digits
+                else:
+                    feats.append(repr(rng.gauss(shift, 2)))              # 16-17 significant digits
+            feats.append(repr(round(rng.uniform(5, 15), 3)))
+            p = round(rng.random(), 2)
+            label = "m6A" if p >= 0.5 else "A"
+            rows.append((rng.random(), "%s\tread%d_%d\t%d\t%s\t%s\t%s\t%s\t%s\n" % (chrom, li, d, pos, ctx, ",".join(feats), strand, label, repr(p))))
+    rows.sort()
+    return "".join(r[1] for r in rows)

@@ -76,8 +76,13 @@ def test_bed_matches_reference(name, tmp_path, capsys, cuda_lib):
     for b in gold["beds"]:
         a = b["args"]
         out = os.path.join(str(tmp_path), "o.bed")
-        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), None, "--control" in a, False, "--gff" in a,
-                            ref_fa if "--ref" in a else None, False, "x", False)
+        pos_list = None
+        if "-p" in a:
+            pos_list = os.path.join(str(tmp_path), a[a.index("-p") + 1])
+            gc.write_bed_positions(gold["diffs"], pos_list)
+        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), pos_list, "--control" in a, "--vo" in a,
+                            "--gff" in a, ref_fa if "--ref" in a else None, False, "x", False)
+        assert b["rc"] == 0 and b["bed"] is not None, a
         assert open(out).read() == b["bed"], a
 
 
@@ -126,3 +131,27 @@ def test_train_mode_windows_match_reference_fixture(tmp_path, capsys, cuda_lib):
         assert key in mine, key
         assert all(abs(a - b) < 1e-9 for a, b in zip([float(x) for x in f[3].split(",")], mine[key]))
     assert sum(len(v) for v in sig["general"].values()) == 44 and set(sig["general"]) == {"A", "m6A"}
+
+
+def test_bed_deep_matches_reference(tmp_path, cuda_lib):
+    """make_bed -p / --vo / --gff --vo on a deep-coverage `.diffs` (depth up to 520: every branch of numpy's pairwise sum;
+    17-digit and scientific-notation feature text): t-test columns, probability lists and fracLow/fracUp are
+    byte-identical to the reference's output (scipy 1.18.1 / numpy 2.3.5, tools/make_golden.py bed_deep)."""
+    import hashlib
+    from mcaller_b200 import make_bed as mb
+    gold = json.load(open(os.path.join(gc.GOLD, "bed_deep.json")))
+    text = gc.deep_diffs_text()
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["diffs_sha256"]
+    diffs = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
+    with open(diffs, "w") as fh:
+        fh.write(text)
+    for b in gold["beds"]:
+        a = b["args"]
+        out = os.path.join(str(tmp_path), "o.bed")
+        pos_list = None
+        if "-p" in a:
+            pos_list = os.path.join(str(tmp_path), a[a.index("-p") + 1])
+            gc.write_bed_positions(text, pos_list)
+        mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), pos_list, False, "--vo" in a, "--gff" in a,
+                            None, False, "x", False)
+        assert b["rc"] == 0 and open(out).read() == b["bed"], a

@@ -424,3 +424,68 @@ def test_size_independent_properties_at_scale(cuda_lib):
     assert sa["too_many_skips"] + sb["too_many_skips"] <= whole["too_many_skips"] <= sa["too_many_skips"] + sb["too_many_skips"] + sa["pending"]
     d_ab, m_ab, _ = eng.histogram_host()
     assert int(d_ab.sum()) + resolved == whole["calls"]
+
+
+def test_diffs_value_parse_is_exact(tmp_path, cuda_lib):
+    """mc_diffs_colstats parses the feature column like Python's float(): bit-exact for <= 19 significant digits and
+    decimal exponents in [-27, 0] (everything repr(float64) prints for |x| >= 1e-11), within 1 ulp outside (counted)."""
+    import random
+    import struct
+    from mcaller_b200 import make_bed as mb
+    rng = random.Random(11)
+    toks = []
+    for i in range(36000):
+        u = i % 12
+        if u == 0:
+            x = rng.gauss(0, 3)
+        elif u == 1:
+            x = rng.gauss(0, 3) * 10 ** rng.randint(-9, 3)
+        elif u == 2:
+            x = round(rng.gauss(0, 50), rng.randint(0, 6))
+        elif u == 3:
+            x = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64) & 0x7FFFFFFFFFFFFFFF))[0]
+            x = x if (x == x and 1e-11 <= abs(x) < 1e15) else rng.random()
+        elif u == 4:
+            x = rng.randint(-10 ** 6, 10 ** 6) / 10 ** rng.randint(0, 8)
+        elif u == 5:
+            x = float(rng.randint(0, 10 ** 15))
+        elif u == 6:
+            x = rng.gauss(0, 1) * 1e-5
+        else:
+            x = rng.uniform(-200, 200)
+        t = repr(x)
+        if u == 7:
+            t = "%.17g" % x
+        elif u == 8:
+            t = "%.4f" % x
+        elif u == 9:
+            t = "%.12e" % x
+        elif u == 10:
+            t = "+" + repr(abs(x))
+        elif u == 11:
+            t = str(rng.randint(-99999, 99999))
+        toks.append(t)
+    toks[5], toks[17], toks[29] = "0", "-0.0", "1e-05"
+    rows = []
+    per = 9
+    for r in range(len(toks) // per):
+        vals = toks[r * per:(r + 1) * per]
+        rows.append("ctg\tread%d\t100\tAAAAAMAAAAA\t%s,9.5\t+\tm6A\t0.7\n" % (r, ",".join(vals)))
+    path = os.path.join(str(tmp_path), "v.diffs.6")
+    with open(path, "w") as fh:
+        fh.write("".join(rows))
+    pos = os.path.join(str(tmp_path), "p.txt")
+    with open(pos, "w") as fh:
+        fh.write("ctg\t100\t101\t+\n")
+    agg = mb._Aggregation(path, mb.make_pos_set(pos))
+    assert len(agg.loci) == 1 and agg.loci[0][4] == len(rows)
+    agg.index_rows()
+    agg.column_tests()
+    assert agg.counters[6] == 0
+    got = agg.vals[:, :per]
+    want = np.array([[float(t) for t in toks[r * per:(r + 1) * per]] for r in range(len(rows))])
+    exact = got.view(np.uint64) == want.view(np.uint64)
+    n_bad = int((~exact).sum())
+    assert n_bad <= int(agg.counters[7]), (n_bad, int(agg.counters[7]), [(toks[i], got.ravel()[i], want.ravel()[i]) for i in np.nonzero(~exact.ravel())[0][:5]])
+    assert np.allclose(got, want, rtol=3e-16, atol=0)
+    assert int(agg.counters[7]) < 0.02 * len(toks)

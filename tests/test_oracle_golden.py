@@ -37,10 +37,37 @@ def test_oracle_bed(name, oracle):
     gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
     for b in gold["beds"]:
         a = b["args"]
-        if "--gff" in a or "--ref" in a:
-            continue            # reporting variants of the same counts: covered by the GPU drop-in test
-        rows = oracle.aggregate(gold["diffs"], int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), "--control" in a)
-        assert "".join(x + "\n" for x in rows) == b["bed"]
+        if "--ref" in a:
+            continue            # reporting variant of the same counts: covered by the GPU drop-in test
+        d, t = int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1])
+        if "--gff" in a or "--vo" in a or "-p" in a:
+            pos_lines = None
+            if "-p" in a:
+                import tempfile
+                with tempfile.TemporaryDirectory() as td:
+                    gc.write_bed_positions(gold["diffs"], os.path.join(td, "p.txt"))
+                    pos_lines = open(os.path.join(td, "p.txt")).read()
+            rows = oracle.aggregate_variants(gold["diffs"], d, t, "--control" in a, pos_lines, "--vo" in a, "--gff" in a)
+        else:
+            rows = oracle.aggregate(gold["diffs"], d, t, "--control" in a)
+        assert "".join(x + "\n" for x in rows) == b["bed"], a
+
+
+def test_oracle_bed_deep(oracle):
+    """make_bed -p / --vo / --gff on the deep-coverage synthetic `.diffs` (tools/make_golden.py bed_deep)."""
+    import hashlib
+    import tempfile
+    gold = json.load(open(os.path.join(gc.GOLD, "bed_deep.json")))
+    text = gc.deep_diffs_text()
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["diffs_sha256"]
+    with tempfile.TemporaryDirectory() as td:
+        gc.write_bed_positions(text, os.path.join(td, "p.txt"))
+        pos_text = open(os.path.join(td, "p.txt")).read()
+    for b in gold["beds"]:
+        a = b["args"]
+        rows = oracle.aggregate_variants(text, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), False,
+                                         pos_text if "-p" in a else None, "--vo" in a, "--gff" in a)
+        assert "".join(x + "\n" for x in rows) == b["bed"], a
 
 
 def test_reference_fixture_diffs(tmp_path, oracle):

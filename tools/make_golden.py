@@ -74,6 +74,8 @@ def make_case(name):
                 for f in os.listdir(tmp):
                     if f.endswith(".bed") or f.endswith(".gff"):
                         os.remove(os.path.join(tmp, f))
+                if "-p" in bed_args:
+                    golden_cases.write_bed_positions(rec["diffs"], os.path.join(tmp, bed_args[bed_args.index("-p") + 1]))
                 rc2, so2, se2 = run([sys.executable, os.path.join(REF, "make_bed.py"), "-f", "syn.eventalign.diffs.%d" % case.get("k", 6)] + bed_args, tmp)
                 beds = [f for f in os.listdir(tmp) if f.endswith(".bed") or f.endswith(".gff")]
                 rec.setdefault("beds", []).append({"args": bed_args, "rc": rc2,
@@ -82,6 +84,30 @@ def make_case(name):
             json.dump(rec, fh, indent=1, sort_keys=True)
         nrows = rec["diffs"].count("\n") if rec["diffs"] else -1
         print("%-18s rc=%d rows=%d counters=%s" % (name, rc, nrows, rec["counters"]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def make_bed_deep():
+    """make_bed-only golden on a synthetic deep-coverage `.diffs.6` (golden_cases.deep_diffs_text)."""
+    tmp = tempfile.mkdtemp(prefix="gold_")
+    try:
+        text = golden_cases.deep_diffs_text()
+        with open(os.path.join(tmp, "syn.eventalign.diffs.6"), "w") as fh:
+            fh.write(text)
+        rec = {"case": "bed_deep", "diffs_sha256": hashlib.sha256(text.encode()).hexdigest(), "beds": []}
+        for bed_args in golden_cases.BED_DEEP_VARIANTS:
+            for f in os.listdir(tmp):
+                if f.endswith(".bed") or f.endswith(".gff"):
+                    os.remove(os.path.join(tmp, f))
+            if "-p" in bed_args:
+                golden_cases.write_bed_positions(text, os.path.join(tmp, bed_args[bed_args.index("-p") + 1]))
+            rc2, so2, se2 = run([sys.executable, os.path.join(REF, "make_bed.py"), "-f", "syn.eventalign.diffs.6"] + bed_args, tmp)
+            beds = [f for f in os.listdir(tmp) if f.endswith(".bed") or f.endswith(".gff")]
+            rec["beds"].append({"args": bed_args, "rc": rc2, "bed": open(os.path.join(tmp, beds[0])).read() if beds else None})
+            print("bed_deep %s rc=%d rows=%d" % (bed_args, rc2, rec["beds"][-1]["bed"].count("\n") if beds else -1))
+        with open(os.path.join(GOLD, "bed_deep.json"), "w") as fh:
+            json.dump(rec, fh, indent=1, sort_keys=True)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -114,6 +140,9 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if not os.path.exists(os.path.join(GOLD, "models", "CAAY_bare_model_6_m6A.pkl")):
         copy_fixtures()
-    names = sys.argv[1:] or list(golden_cases.CASES)
+    names = sys.argv[1:] or (list(golden_cases.CASES) + ["bed_deep"])
     for nm in names:
-        make_case(nm)
+        if nm == "bed_deep":
+            make_bed_deep()
+        else:
+            make_case(nm)
