@@ -243,8 +243,9 @@ int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void 
 int mc_hist_accumulate(const mc_call *d_calls, int64_t n_calls, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first,
                        int64_t n_sites, uint64_t row_base, uint64_t *d_skipped, void *stream);
 
-/* Row statistics on the device (adds to d_out[6], which the caller zeroes): calls closed in the chunk, calls still
- * pending, too-many-skips events, multi-M events, rows with an error flag, calls labelled methylated. */
+/* Row statistics on the device (adds to d_out[7], which the caller zeroes): calls closed in the chunk, calls still
+ * pending, too-many-skips events closed in the chunk, multi-M events, rows with an error flag, calls labelled
+ * methylated, too-many-skips events still pending (counted by the reference only once a later kept line closes them). */
 int mc_count_calls(const mc_call *d_calls, int64_t n_calls, uint64_t *d_out, void *stream);
 
 /*

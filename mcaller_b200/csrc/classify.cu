@@ -229,10 +229,12 @@ k_hist(const mc_call *__restrict__ calls, int64_t n, uint32_t *__restrict__ dept
 }
 
 // row statistics without a D2H copy of the rows: [0] calls closed in this chunk, [1] calls still pending,
-// [2] too-many-skips events, [3] multi-M events, [4] rows with an error flag, [5] calls labelled methylated
+// [2] too-many-skips events closed in this chunk, [3] multi-M events, [4] rows with an error flag, [5] calls labelled
+// methylated, [6] too-many-skips events still pending (a window open at the end of the chunk is closed -- and only then
+// counted, extract_contexts.py:179/:238 -- by the next kept line of the file; the last one of a file never is)
 __global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__ calls, int64_t n, unsigned long long *__restrict__ out) {
-    __shared__ unsigned int s[6];
-    if (threadIdx.x < 6) s[threadIdx.x] = 0u;
+    __shared__ unsigned int s[7];
+    if (threadIdx.x < 7) s[threadIdx.x] = 0u;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -240,12 +242,12 @@ __global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__
         if (c.kind == MC_CALL) {
             atomicAdd(&s[c.close_rec == 0xFFFFFFFFu ? 1 : 0], 1u);
             if (c.label) atomicAdd(&s[5], 1u);
-        } else if (c.kind == MC_TOO_MANY_SKIPS) atomicAdd(&s[2], 1u);
+        } else if (c.kind == MC_TOO_MANY_SKIPS) atomicAdd(&s[c.close_rec == 0xFFFFFFFFu ? 6 : 2], 1u);
         else atomicAdd(&s[3], 1u);
         if (c.err) atomicAdd(&s[4], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 6 && s[threadIdx.x]) atomicAdd(out + threadIdx.x, (unsigned long long)s[threadIdx.x]);
+    if (threadIdx.x < 7 && s[threadIdx.x]) atomicAdd(out + threadIdx.x, (unsigned long long)s[threadIdx.x]);
 }
 
 }  // namespace

@@ -188,12 +188,13 @@ class Engine(object):
 
     def count_rows(self, res):
         """Device-side row statistics of a chunk -> dict (one tiny kernel + 48-byte read-back)."""
-        self.d_small[24:30].zero_()
+        self.d_small[24:31].zero_()
         if res.n_calls:
             check(self.L.mc_count_calls(C.c_void_p(res.calls_dev.data_ptr()), res.n_calls, C.c_void_p(self.d_small.data_ptr() + 8 * 24), self._sptr()))
             self.launches += 1
-        v = self._read_small(24, 6)
-        return dict(calls=int(v[0]), pending=int(v[1]), too_many_skips=int(v[2]), multi=int(v[3]), errors=int(v[4]), methylated=int(v[5]))
+        v = self._read_small(24, 7)
+        return dict(calls=int(v[0]), pending=int(v[1]), too_many_skips=int(v[2]), multi=int(v[3]), errors=int(v[4]), methylated=int(v[5]),
+                    pending_too_many_skips=int(v[6]))
 
     def records(self, n_rec):
         """Ordered stage-1 records of the last chunk (host copy; test helper)."""

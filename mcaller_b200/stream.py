@@ -62,7 +62,7 @@ class HostStreamer(object):
         bounds = [0] + list(cuts)
         if len(bounds) > 1:
             self._enqueue_copy(0, host_buf, bounds[0], bounds[1])
-        pending_prev = 0
+        pending_prev = pending_tms_prev = 0
         for i in range(len(bounds) - 1):
             slot = i & 1
             if i + 2 < len(bounds):
@@ -79,10 +79,12 @@ class HostStreamer(object):
                 self.d2h_bytes += nb
             self.free[slot].record(cur)
             # a window left open by the previous chunk closes on this chunk's first kept line (any kept line does)
-            if pending_prev and res.counters["kept"] > 0:
+            if (pending_prev or pending_tms_prev) and res.counters["kept"] > 0:
                 tot["pending_resolved"] += pending_prev
-                pending_prev = 0
+                tot["too_many_skips"] += pending_tms_prev
+                pending_prev = pending_tms_prev = 0
             pending_prev += st["pending"]
+            pending_tms_prev += st["pending_too_many_skips"]
             for kx in ("calls", "too_many_skips", "multi", "errors", "methylated"):
                 tot[kx] += st[kx]
             tot["records"] += res.n_records
