@@ -86,7 +86,7 @@ typedef struct mc_record {
 /* counters written by mc_scan (uint64 each) */
 enum {
     MC_C_LINES = 0,        /* lines owned by the scanned range */
-    MC_C_KEPT,             /* >= 12 fields, known contig, model_kmer != NNNNNN */
+    MC_C_KEPT,             /* >= 12 fields, known contig, model_kmer != NNNNNN (see mc_scan for the sparse mode) */
     MC_C_RECORDS,          /* record slots reserved (allocation cursor, >= records written) */
     MC_C_SHORT,            /* lines with < 12 whitespace separated fields (:149-152) */
     MC_C_UNKNOWN_CONTIG,   /* contig not in the reference (:154-160) */
@@ -94,6 +94,7 @@ enum {
     MC_C_BADPOS,           /* column 2 not a non-negative integer on a known contig (reference: ValueError) */
     MC_C_LONGLINE,         /* lines whose first 12 columns outran the look-ahead and took the byte-wise slow path (informational) */
     MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
+    MC_C_RUN_CURSOR,       /* internal: next unclaimed run of chunks (dynamic work distribution of mc_scan) */
     MC_C_COUNT = 16
 };
 
@@ -170,13 +171,16 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
 /*
  * Stage 1 -- tokenise + filter.  Replaces the reader/tokeniser and the per-line filters of
  * extract_contexts.py:140-176 (readlines, line.split()[:12], contig lookup, NNNNNN filter, k-mer
- * 'has M' test).  One CTA per MC_TILE_BYTES tile; a line belongs to the tile holding its first byte.
+ * 'has M' test).  One warp per MC_TILE_BYTES chunk; a line belongs to the chunk holding its first byte.
  * Emits a record for every kept line that is a candidate (k-mer window touches a target on either
- * strand), that follows a candidate, or that is the first kept line of its tile; with dense != 0 for
+ * strand), that follows a candidate, or that is the first kept line of a run of chunks; with dense != 0 for
  * every kept line (needed with -q).  Records of one chunk are contiguous and in line order; warps reserve slots in
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
  * holes); d_tile_tab[chunk] = {first record slot, count | flags} (flags are consumed by mc_order_records, which also
- * drops the chunk-first records whose predecessor line turns out not to be a candidate).
+ * drops the run-first records whose predecessor line turns out not to be a candidate).
+ * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
+ * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
+ * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
  * d_counters (MC_C_COUNT uint64) must be zeroed by the caller.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,

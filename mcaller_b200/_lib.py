@@ -15,7 +15,7 @@ MC_TILE_BYTES = 3840
 MC_TEXT_PAD = 4096
 MC_MAXK = 8
 MC_C_COUNT = 16
-COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow"]
+COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor"]
 
 MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M = 0, 1, 2
 MC_CE_CONTEXT, MC_CE_MODELKEY, MC_CE_BADNUM, MC_CE_COLUMN, MC_CE_SPACING = 1, 2, 4, 8, 16

@@ -39,6 +39,9 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_MIN_CTAS
 #define MC_SCAN_MIN_CTAS 1
 #endif
+#ifndef MC_SCAN_RUN
+#define MC_SCAN_RUN 32
+#endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int LCAP = 32;                      // lines per pass (one per lane)
@@ -257,15 +260,16 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
-k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, mc_refindex R, int dense,
-       mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
+k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, int run_len, mc_refindex R,
+       int dense, mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
        unsigned long long *__restrict__ d_counters) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
     const int warp_global = (int)blockIdx.x * WARPS + wib;      // chunk indices fit 32 bits (mc_scan checks)
-    const int warp_stride = (int)gridDim.x * WARPS;
+    const int n_warps = (int)gridDim.x * WARPS;
     const int n_chunks = (int)n_chunks64;
+    const int n_runs = (n_chunks + run_len - 1) / run_len;       // a run = run_len consecutive chunks parsed by one warp
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // warp-uniform state
@@ -319,16 +323,30 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         return false;
     };
 
+    // Runs are claimed dynamically: run `warp_global` first, then one atomic per run on the run cursor.  Inside a run the
+    // state of the last kept line (prev_state) carries from chunk to chunk, so only the first kept line of a RUN is a
+    // "filler" record that stage 2 may have to drop.
     int buf = 0;
     bool cur_async = false;
-    if (warp_global < n_chunks) cur_async = stage(warp_global, 0);
+    int chunk = warp_global < n_runs ? warp_global * run_len : n_chunks;
+    int run_end = min(chunk + run_len, n_chunks);
+    if (chunk < n_chunks) cur_async = stage(chunk, 0);
+    int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
 
-    for (int chunk = warp_global; chunk < n_chunks; chunk += warp_stride, buf ^= 1) {
+    while (chunk < n_chunks) {
         const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
         const bool tail = chunk >= c_tail_lo;                     // chunk touches the end of the text (G0 + WB > nbytes)
         __syncwarp();
-        // ---- 0. prefetch the next chunk, wait for this one ----------------------------------------------------------------
-        const int next = chunk + warp_stride;
+        // ---- 0. prefetch the next chunk (claiming the next run at the end of this one), wait for this chunk ------------------
+        int next = chunk + 1, next_end = run_end;
+        const bool last_of_run = next >= run_end;
+        if (last_of_run) {
+            unsigned long long got = 0ull;
+            if (lane == 0) got = atomicAdd(&d_counters[MC_C_RUN_CURSOR], 1ull);
+            got = __shfl_sync(0xffffffffu, got, 0) + (unsigned long long)n_warps;
+            next = got < (unsigned long long)n_runs ? (int)got * run_len : n_chunks;
+            next_end = min(next + run_len, n_chunks);
+        }
         bool next_async = false;
         if (next < n_chunks) next_async = stage(next, buf ^ 1);
         if (cur_async) {
@@ -340,28 +358,19 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         const uint8_t *text = S.text[buf];
         const SmemBytes T{text};
 
-        // ---- 1. classify: lane owns words lane, lane+32, lane+64, lane+96 ---------------------------------------------------
-        uint32_t prev_top = 0u;                                   // was the last byte of word 32r-1 non-whitespace
+        // ---- 1. newline map: lane owns words lane, lane+32, lane+64, lane+96 -------------------------------------------------
+        // (the non-whitespace / field-start map is built only when a pass of this chunk needs the full parse, see 3b)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int w = 32 * r + lane;
             const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
             const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
-            const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x), gt20_msb(vb.y),
-                                          gt20_msb(vb.z), gt20_msb(vb.w));
-            const uint32_t nl = pack32(eq0a_msb(va.x), eq0a_msb(va.y), eq0a_msb(va.z), eq0a_msb(va.w), eq0a_msb(vb.x), eq0a_msb(vb.y),
-                                       eq0a_msb(vb.z), eq0a_msb(vb.w));
-            // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
-            const uint32_t top = nonws >> 31;
-            uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
-            if (lane == 0) pt = prev_top;
-            prev_top = __shfl_sync(0xffffffffu, top, 31);
-            S.nl[w] = nl;
-            S.fs[w] = nonws & ~((nonws << 1) | pt);
+            S.nl[w] = pack32(eq0a_msb(va.x), eq0a_msb(va.y), eq0a_msb(va.z), eq0a_msb(va.w), eq0a_msb(vb.x), eq0a_msb(vb.y),
+                             eq0a_msb(vb.z), eq0a_msb(vb.w));
         }
-        if (lane < 8) S.fs[NW + lane] = 0u;
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
+        bool full_ready = false;   // field-start map and e_last built for this chunk
 
         // ---- 2. line list: lane owns words 4*lane .. 4*lane+3 ------------------------------------------------------------------
         // line starts: byte p starts a line iff byte p-1 is '\n'; owned words are LOOKB/32 .. (LOOKB+CHUNK)/32 - 1, global p < nbytes
@@ -422,24 +431,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         }
         unsigned n_emitted = 0u;
 
-        // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold the
-        // look-ahead words instead of a single lane walking the bit map
-        int e_last;
-        if (!tail) {
-            constexpr int WLAST = (LOOKB + CHUNK - 1) >> 5, BLAST = (LOOKB + CHUNK - 1) & 31;
-            static_assert(NW - WLAST <= 32, "look-ahead words must fit one per lane");
-            int cand_e = NW * 32;
-            if (WLAST + lane < NW) {
-                uint32_t m = S.nl[WLAST + lane];
-                if (lane == 0) m &= 0xFFFFFFFFu << BLAST;
-                if (m) cand_e = 32 * (WLAST + lane) + __ffs(m) - 1;
-            }
-            e_last = __reduce_min_sync(0xffffffffu, cand_e);
-        } else {
-            e_last = -1;           // text ends inside this chunk: fall back to the bit-map walk
-        }
-
-        int prev_state = -1;       // -1: no kept line yet in this chunk, 0: last kept line not a candidate, 1: candidate
+        int e_last = -1;           // end of the chunk's last line (built with the field-start map)
         uint32_t filler = 0u;      // the chunk's first record exists only because its predecessor line is in another chunk
         for (int pass0 = 0; pass0 < total_lines; pass0 += 32) {
             // list entries [pass0, pass0+33) (one extra so every lane knows where its line ends)
@@ -475,7 +467,64 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
             __syncwarp();
             const int n_pass = min(32, total_lines - pass0);
-            // ---- 3. structural parse, one lane per line --------------------------------------------------------------
+            // ---- 3a. quick look, one lane per line: "<hint contig><ws><digits><ws>" -> position -> candidate bit -------------
+            // A pass in which every line passes this test on a non-candidate position, entered with the last kept line not a
+            // candidate, emits nothing and leaves the state as it is whatever the rest of its lines holds (kept or not, a
+            // non-candidate line neither gets a record nor changes "last kept line is not a candidate") -> skip the full parse.
+            if (!dense && prev_state == 0) {
+                bool quiet = true;
+                if (lane < n_pass) {
+                    const int s0 = S.lstart[lane];
+                    const unsigned long long k8 = load8(text, s0);
+                    quiet = false;
+                    if (hint_nlen >= 1 && hint_nlen <= 7 && (k8 & ((1ull << (8 * hint_nlen)) - 1ull)) == hint_key &&
+                        ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull) {
+                        int p0 = 0;
+                        if (parse_pos8(load8(text, s0 + hint_nlen + 1), p0) == 1) {
+                            quiet = true;
+                            if (p0 < hint_len) {
+                                const int64_t g = hint_base + p0;
+                                quiet = ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) == 0u;
+                            }
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, quiet)) continue;
+            }
+            // ---- 3b. full parse: field-start map of the chunk (once), then one lane per line -------------------------------
+            if (!full_ready) {
+                full_ready = true;
+                uint32_t prev_top = 0u;                               // was the last byte of word 32r-1 non-whitespace
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int w = 32 * r + lane;
+                    const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
+                    const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
+                    const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x),
+                                                  gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w));
+                    // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
+                    const uint32_t top = nonws >> 31;
+                    uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
+                    if (lane == 0) pt = prev_top;
+                    prev_top = __shfl_sync(0xffffffffu, top, 31);
+                    S.fs[w] = nonws & ~((nonws << 1) | pt);
+                }
+                if (lane < 8) S.fs[NW + lane] = 0u;
+                // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold
+                // the look-ahead words instead of a single lane walking the bit map
+                if (!tail) {
+                    constexpr int WLAST = (LOOKB + CHUNK - 1) >> 5, BLAST = (LOOKB + CHUNK - 1) & 31;
+                    static_assert(NW - WLAST <= 32, "look-ahead words must fit one per lane");
+                    int cand_e = NW * 32;
+                    if (WLAST + lane < NW) {
+                        uint32_t m = S.nl[WLAST + lane];
+                        if (lane == 0) m &= 0xFFFFFFFFu << BLAST;
+                        if (m) cand_e = 32 * (WLAST + lane) + __ffs(m) - 1;
+                    }
+                    e_last = __reduce_min_sync(0xffffffffu, cand_e);
+                }                  // else the text ends inside this chunk: e_last stays -1, the bit-map walk finds the end
+                __syncwarp();
+            }
             uint32_t status = 0u;
             int cid = -1, pos = 0, s = 0;
             if (lane < n_pass) {
@@ -564,6 +613,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // count | filler flag | state of the chunk's last kept line (0 none, 1 not a candidate, 2 candidate)
             d_tile_tab[2 * (int64_t)chunk + 1] = n_emitted | (filler << 16) | ((uint32_t)(prev_state + 1) << 17);
         }
+        if (last_of_run) prev_state = -1;
+        chunk = next;
+        run_end = next_end;
+        buf ^= 1;
         cur_async = next_async;
     }
 
@@ -607,7 +660,10 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     if (blocks > resident) blocks = resident;
     // 16-byte loads / bulk copies are allowed up to the end of the caller's '\n' padding
     const int64_t text_limit16 = ((nbytes + MC_TEXT_PAD) / 16) * 16;
-    k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, *ref, dense, d_rec,
+    // run length: as long as possible (fewer run-first "filler" passes) while every warp still gets >= 8 runs to balance on
+    int run_len = MC_SCAN_RUN;
+    while (run_len > 1 && n_chunks < blocks * WARPS * 8 * (int64_t)run_len) run_len >>= 1;
+    k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense, d_rec,
                                                                      (unsigned long long)rec_cap, d_tile_tab,
                                                                      reinterpret_cast<unsigned long long *>(d_counters));
     MC_LAUNCH_CHECK();
