@@ -187,6 +187,11 @@ int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int d
             mc_record *d_rec, int64_t rec_cap, uint32_t *d_tile_tab /* [2*n_tiles] */,
             uint64_t *d_counters, void *stream);
 
+/* Test / tuning hook: chunks per run of mc_scan (consecutive chunks parsed by one warp, which carries the
+ * "last kept line" state between them).  0 = automatic (32, shortened for small inputs so every warp gets runs to
+ * balance on).  Results do not depend on it.  Returns the previous setting. */
+int mc_scan_set_run_len(int run_len);
+
 /* number of tiles mc_scan uses for nbytes */
 int64_t mc_num_tiles(int64_t nbytes);
 

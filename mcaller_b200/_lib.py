@@ -79,6 +79,7 @@ _PROTOS = {
     "mc_last_error": (C.c_char_p, []),
     "mc_read_u64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mc_scan": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RefIndex), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_scan_set_run_len": (C.c_int, [C.c_int]),
     "mc_num_tiles": (C.c_int64, [C.c_int64]),
     "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
     "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -91,11 +91,6 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t pari
 
 // ---- byte classification ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t gt20_msb(uint32_t w) { return (((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u; }
-__device__ __forceinline__ uint32_t eq0a_msb(uint32_t w) {
-    // low 7 bits of (byte ^ 0x0a) are zero and bit 7 of the byte is clear  <=>  byte == 0x0a
-    const uint32_t t = ((w ^ 0x0a0a0a0au) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    return ~(t | w) & 0x80808080u;
-}
 // 8 msb-form words (0x80 per flagged byte) -> 32 flag bits in byte order.  IDP.4A sums 0x80 * weight per byte: two
 // words fill bits 7..14 of one accumulator.
 __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4, uint32_t m5,
@@ -272,6 +267,14 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     const int n_runs = (n_chunks + run_len - 1) / run_len;       // a run = run_len consecutive chunks parsed by one warp
     const uint32_t lt_mask = (1u << lane) - 1u;
 
+    // byte == 0x0a in three instructions per word: a LOP3 folds only one immediate, so the 0x7f mask is made a run-time
+    // value (nbytes is never negative, which the compiler cannot know) and lives in a register: (w ^ imm) & reg is one LOP3
+    const uint32_t K7F = 0x7f7f7f7fu | ((uint32_t)((unsigned long long)nbytes >> 63) << 7);
+    auto eq0a_r = [&](uint32_t w) -> uint32_t {
+        const uint32_t t = ((w ^ 0x0a0a0a0au) & K7F) + K7F;       // bit 7 set iff the low 7 bits differ from 0x0a
+        return ~(t | w) & 0x80808080u;
+    };
+
     // warp-uniform state
     int hint = -1;
     int64_t hint_base = 0;
@@ -289,7 +292,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     set_hint(0);
     unsigned long long slot_cur = 0ull;                           // next free reserved record slot
     unsigned slot_left = 0u;                                      // slots left in the warp's reserved block
-    unsigned c_lines = 0, c_kept = 0;                             // warp-uniform; rarer events are counted in S.cnt
+    unsigned c_lines = 0, c_kept = 0;                             // c_lines per lane, c_kept warp-uniform; rarer events in S.cnt
     if (lane < 8) S.cnt[lane] = 0u;
 
     if (lane == 0) {
@@ -359,14 +362,15 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         const SmemBytes T{text};
 
         // ---- 1. newline map: lane owns words lane, lane+32, lane+64, lane+96 -------------------------------------------------
+        // byte == 0x0a in three instructions per word (LOP3, IADD, LOP3) with the three masks held in registers
         // (the non-whitespace / field-start map is built only when a pass of this chunk needs the full parse, see 3b)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int w = 32 * r + lane;
             const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
             const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
-            S.nl[w] = pack32(eq0a_msb(va.x), eq0a_msb(va.y), eq0a_msb(va.z), eq0a_msb(va.w), eq0a_msb(vb.x), eq0a_msb(vb.y),
-                             eq0a_msb(vb.z), eq0a_msb(vb.w));
+            S.nl[w] = pack32(eq0a_r(va.x), eq0a_r(va.y), eq0a_r(va.z), eq0a_r(va.w), eq0a_r(vb.x), eq0a_r(vb.y), eq0a_r(vb.z),
+                             eq0a_r(vb.w));
         }
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
@@ -402,32 +406,71 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
         }
         const int my_cnt = __popc(lsv.x) + __popc(lsv.y) + __popc(lsv.z) + __popc(lsv.w);
+        c_lines += (unsigned)my_cnt;                               // per lane; summed over the warp at the end
+
+        // ---- 2a. quick look at every line of the chunk: "<hint contig><ws><digits><ws>" -> position -> candidate bit ----------
+        // A chunk in which every line passes this test on a non-candidate position, entered with the last kept line not a
+        // candidate, emits nothing and leaves that state as it is whatever else its lines hold (kept or not, a line on a
+        // non-candidate position neither gets a record nor changes "last kept line is not a candidate"): it is done here,
+        // without the field-start map, the line list or the per-line parse.  Lanes test the lines that start inside their
+        // own 128 bytes (usually one, so one round).
+        bool quiet_chunk = false;
+        if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 7) {
+            uint32_t w0 = lsv.x, w1 = lsv.y, w2 = lsv.z, w3 = lsv.w;
+            const unsigned long long name_mask = (1ull << (8 * hint_nlen)) - 1ull;
+            bool ok = true;
+            while (__any_sync(0xffffffffu, (w0 | w1 | w2 | w3) != 0u)) {
+                if ((w0 | w1 | w2 | w3) != 0u) {
+                    const int jw = w0 ? 0 : w1 ? 1 : w2 ? 2 : 3;
+                    const uint32_t m = w0 ? w0 : w1 ? w1 : w2 ? w2 : w3;
+                    const int s0 = 32 * (4 * lane + jw) + __ffs(m) - 1;
+                    const uint32_t cl = m & (m - 1u);
+                    if (jw == 0) w0 = cl; else if (jw == 1) w1 = cl; else if (jw == 2) w2 = cl; else w3 = cl;
+                    const unsigned long long k8 = load8(text, s0);
+                    ok = false;
+                    if ((k8 & name_mask) == hint_key && ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull) {
+                        int p0 = 0;
+                        if (parse_pos8(load8(text, s0 + hint_nlen + 1), p0) == 1) {
+                            ok = true;
+                            if (p0 < hint_len) {
+                                const int64_t g = hint_base + p0;
+                                ok = ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) == 0u;
+                            }
+                        }
+                    }
+                }
+                if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+            }
+            quiet_chunk = ok;                                      // warp-uniform
+        }
+
+        // ---- 2b. line list of a chunk that needs the full parse ---------------------------------------------------------------
         // exclusive prefix of the per-lane counts: two ballots when every lane holds at most 3 line starts (always, for
         // ~128-byte lines), a shuffle scan otherwise
-        int my_first, total_lines;
-        if (__ballot_sync(0xffffffffu, my_cnt > 3) == 0u) {
-            const uint32_t b0 = __ballot_sync(0xffffffffu, my_cnt & 1), b1 = __ballot_sync(0xffffffffu, my_cnt & 2);
-            my_first = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask);
-            total_lines = __popc(b0) + 2 * __popc(b1);
-        } else {
-            int incl = my_cnt;
+        int my_first = 0, total_lines = 0;
+        if (!quiet_chunk) {
+            if (__ballot_sync(0xffffffffu, my_cnt > 3) == 0u) {
+                const uint32_t b0 = __ballot_sync(0xffffffffu, my_cnt & 1), b1 = __ballot_sync(0xffffffffu, my_cnt & 2);
+                my_first = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask);
+                total_lines = __popc(b0) + 2 * __popc(b1);
+            } else {
+                int incl = my_cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int tt = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += tt;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int tt = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += tt;
+                }
+                total_lines = __shfl_sync(0xffffffffu, incl, 31);
+                my_first = incl - my_cnt;
             }
-            total_lines = __shfl_sync(0xffffffffu, incl, 31);
-            my_first = incl - my_cnt;
-        }
-        c_lines += (unsigned)total_lines;
-
-        // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
-        if (slot_left < (unsigned)total_lines) {
-            unsigned long long got = 0ull;
-            const unsigned want = total_lines > RESERVE ? (unsigned)total_lines : (unsigned)RESERVE;
-            if (lane == 0) got = atomicAdd(&d_counters[MC_C_RECORDS], (unsigned long long)want);
-            slot_cur = __shfl_sync(0xffffffffu, got, 0);
-            slot_left = want;
+            // record slots for this chunk are taken from the warp's reserved block; make sure it can hold every line
+            if (slot_left < (unsigned)total_lines) {
+                unsigned long long got = 0ull;
+                const unsigned want = total_lines > RESERVE ? (unsigned)total_lines : (unsigned)RESERVE;
+                if (lane == 0) got = atomicAdd(&d_counters[MC_C_RECORDS], (unsigned long long)want);
+                slot_cur = __shfl_sync(0xffffffffu, got, 0);
+                slot_left = want;
+            }
         }
         unsigned n_emitted = 0u;
 
@@ -467,31 +510,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
             __syncwarp();
             const int n_pass = min(32, total_lines - pass0);
-            // ---- 3a. quick look, one lane per line: "<hint contig><ws><digits><ws>" -> position -> candidate bit -------------
-            // A pass in which every line passes this test on a non-candidate position, entered with the last kept line not a
-            // candidate, emits nothing and leaves the state as it is whatever the rest of its lines holds (kept or not, a
-            // non-candidate line neither gets a record nor changes "last kept line is not a candidate") -> skip the full parse.
-            if (!dense && prev_state == 0) {
-                bool quiet = true;
-                if (lane < n_pass) {
-                    const int s0 = S.lstart[lane];
-                    const unsigned long long k8 = load8(text, s0);
-                    quiet = false;
-                    if (hint_nlen >= 1 && hint_nlen <= 7 && (k8 & ((1ull << (8 * hint_nlen)) - 1ull)) == hint_key &&
-                        ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull) {
-                        int p0 = 0;
-                        if (parse_pos8(load8(text, s0 + hint_nlen + 1), p0) == 1) {
-                            quiet = true;
-                            if (p0 < hint_len) {
-                                const int64_t g = hint_base + p0;
-                                quiet = ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) == 0u;
-                            }
-                        }
-                    }
-                }
-                if (__all_sync(0xffffffffu, quiet)) continue;
-            }
-            // ---- 3b. full parse: field-start map of the chunk (once), then one lane per line -------------------------------
+            // ---- 3. full parse: field-start map of the chunk (once), then one lane per line -------------------------------
             if (!full_ready) {
                 full_ready = true;
                 uint32_t prev_top = 0u;                               // was the last byte of word 32r-1 non-whitespace
@@ -622,6 +641,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 
     // ---- counters: one global atomic per warp and counter ------------------------------------------------------------------
     __syncwarp();
+    c_lines = __reduce_add_sync(0xffffffffu, c_lines);
     if (lane == 0) {
         if (c_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)c_lines);
         if (c_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)c_kept);
@@ -635,6 +655,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 }
 
 }  // namespace
+
+static int g_run_len_override = 0;
+extern "C" int mc_scan_set_run_len(int run_len) {
+    const int before = g_run_len_override;
+    g_run_len_override = run_len < 0 ? 0 : (run_len > 4096 ? 4096 : run_len);
+    return before;
+}
 
 extern "C" int64_t mc_num_tiles(int64_t nbytes) { return nbytes <= 0 ? 0 : (nbytes + CHUNK - 1) / CHUNK; }
 
@@ -663,6 +690,7 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     // run length: as long as possible (fewer run-first "filler" passes) while every warp still gets >= 8 runs to balance on
     int run_len = MC_SCAN_RUN;
     while (run_len > 1 && n_chunks < blocks * WARPS * 8 * (int64_t)run_len) run_len >>= 1;
+    if (g_run_len_override > 0) run_len = g_run_len_override;
     k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense, d_rec,
                                                                      (unsigned long long)rec_cap, d_tile_tab,
                                                                      reinterpret_cast<unsigned long long *>(d_counters));
