@@ -227,9 +227,12 @@ int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint
 /*
  * Stage 5 -- window builder: the state machine of extract_contexts.py:169-291 (strand inference, window
  * open/feed/close, skip filter, multi-M carry, orientation flip, np.mean of np.round(ev-model,4) per column in
- * numpy's summation order) run per read segment.  Two passes (count, exclusive scan, write) so rows come out in
- * file order.  d_ncalls[0] receives the number of rows (all kinds); rows beyond call_cap are dropped and
- * d_ncalls[1] is set.  Segments whose quality is below qual_thresh are skipped entirely (:167).
+ * numpy's summation order).  A read is cut into units at its non-candidate records (after which the reference's
+ * state is closed and empty); one thread per unit, two passes (count, exclusive scan, write) so rows come out in
+ * file order.  d_rec must come from mc_order_records (MC_RF_SEGKNOWN / MC_RF_NEWREAD set) and d_seg_start from
+ * mc_segment_reads on the same records.  d_seg_count is scratch of n_seg uint32.  d_ncalls[0] receives the number of
+ * rows (all kinds); rows beyond call_cap are dropped and d_ncalls[1] is set.  Segments whose quality is below
+ * qual_thresh are skipped entirely (:167).  d_ws: mc_workspace_bytes(n_records).
  */
 int mc_build_windows(const mc_record *d_rec, int64_t n_records, const uint32_t *d_seg_start, int64_t n_seg,
                      const double *d_seg_qual, const mc_refindex *ref, int skip_thresh, double qual_thresh, int two_models,

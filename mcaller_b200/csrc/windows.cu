@@ -8,7 +8,14 @@
 // still-open window of the previous read, which the first record of the next read closes (:179, `read_name !=
 // last_read`); that hand-off is resolved here by looking at the first record of the next segment.
 //
-// One thread per read segment, two passes (count rows / write rows) so rows land in file order.  Column sums are
+// Parallel decomposition: a read is cut into UNITS.  A record that is not a candidate (its k-mer touches no target on
+// either strand) leaves the state machine closed and empty (:242-245, :289-291), so the records from the first candidate
+// after such a record up to and including the next non-candidate record (the closer) can be processed on their own; the
+// only read-level state they need is `last_read` / `first_read_ind` (:161-174), i.e. the read's first line with an 'M',
+// which k_first_m finds per read beforehand.  Reads whose first record lies within k of the contig start stay one unit:
+// a window at position 0 never closes (`if mpos and`, :179) and keeps its columns across non-candidate lines.
+// A block of 256 threads owns 1024 consecutive records, compacts the unit starts among them into shared memory and
+// runs one thread per unit; two passes (count rows / write rows) so rows land in file order.  Column sums are
 // accumulated in numpy's pairwise order (8 running lanes + sequential tail) so np.mean is reproduced bit for bit.
 #include "common.cuh"
 
@@ -75,31 +82,118 @@ __device__ __forceinline__ uint8_t comp_base(uint8_t c) {
     }
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(128)
-k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *__restrict__ seg_start, int64_t n_seg,
-          const double *__restrict__ seg_qual, mc_refindex R, int skip_thresh, double qual_thresh, int two_models,
-          mc_call *__restrict__ calls, unsigned long long call_cap, uint32_t *__restrict__ seg_count,
-          const uint32_t *__restrict__ seg_off, unsigned long long *__restrict__ d_ncalls) {
+constexpr int WIN_THREADS = 256, WIN_ITEMS = 4, WIN_RECS = WIN_THREADS * WIN_ITEMS;
+
+// first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
+__global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t n_seg,
+                                                mc_refindex R, uint32_t *__restrict__ first_idx, int32_t *__restrict__ first_ind) {
     const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= n_seg) return;
-    const double myq = seg_qual[seg];
-    uint32_t n_out = 0;
-    if (myq < qual_thresh) {                       // whole read dropped (:167)
-        if (!WRITE) seg_count[seg] = 0;
-        return;
-    }
-    const int k = R.k;
     const uint32_t b = seg_start[seg], e = seg_start[seg + 1];
-    uint32_t out_pos = WRITE ? seg_off[seg] : 0u;
+    uint32_t fi = 0xFFFFFFFFu;
+    int32_t ev = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rec + i)), c = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1);
+        const uint32_t fl = c.w & 0xFFu;
+        if (!(fl & MC_RF_CAND)) continue;
+        const int pos = (int)a.z, cid = (int)(c.z >> 16);
+        const int rev = !(fl & MC_RF_EQ);
+        uint32_t bits = 0u;
+        if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, R.k);
+        if (bits) { fi = i; ev = (int32_t)a.w; break; }
+    }
+    first_idx[seg] = fi;
+    first_ind[seg] = ev;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(WIN_THREADS)
+k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *__restrict__ seg_start, int64_t n_seg,
+          const double *__restrict__ seg_qual, const uint32_t *__restrict__ first_idx, const int32_t *__restrict__ first_ind_arr,
+          mc_refindex R, int skip_thresh, double qual_thresh, int two_models, mc_call *__restrict__ calls,
+          unsigned long long call_cap, uint32_t *__restrict__ unit_cnt /* [n_records], written at unit starts */,
+          uint32_t *__restrict__ blk_tot, const uint32_t *__restrict__ blk_off) {
+    __shared__ uint32_t s_unit[WIN_RECS];
+    __shared__ uint32_t s_off[WIN_RECS];
+    __shared__ int s_warp[WIN_THREADS / 32 + 1];
+    const int k = R.k;
+    // ---- unit starts among this block's records, compacted in record order ------------------------------------------------
+    int nu;
+    {
+        const int64_t i0 = (int64_t)blockIdx.x * WIN_RECS + (int64_t)threadIdx.x * WIN_ITEMS;
+        uint32_t prev_cand = 0u;
+        if (i0 > 0 && i0 <= n_records) prev_cand = __ldg(reinterpret_cast<const uint4 *>(rec + i0 - 1) + 1).w & MC_RF_CAND;
+        uint32_t ustart[WIN_ITEMS];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < WIN_ITEMS; ++j) {
+            const int64_t i = i0 + j;
+            bool u = false;
+            if (i < n_records) {
+                const uint32_t fl = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1).w & 0xFFu;
+                const uint32_t cand = fl & MC_RF_CAND;
+                if (i == 0 || (fl & MC_RF_NEWREAD)) {
+                    u = cand != 0u;
+                    if (!u) u = (int)__ldg(reinterpret_cast<const uint4 *>(rec + i)).z < k;      // whole-read unit (see above)
+                } else {
+                    u = cand != 0u && prev_cand == 0u;
+                }
+                prev_cand = cand;
+            }
+            if (u) ustart[cnt++] = (uint32_t)i;
+        }
+        int total;
+        const int off = mc_block_exscan<WIN_THREADS>(cnt, s_warp, total);
+        for (int j = 0; j < cnt; ++j) s_unit[off + j] = ustart[j];
+        nu = total;
+        __syncthreads();
+    }
+    if (WRITE) {
+        // row offsets of the block's units: counts of the first pass -> exclusive prefix in shared memory
+        for (int u = threadIdx.x; u < WIN_RECS; u += WIN_THREADS) s_off[u] = u < nu ? unit_cnt[s_unit[u]] : 0u;
+        __syncthreads();
+        uint32_t v[WIN_ITEMS];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < WIN_ITEMS; ++j) { v[j] = s_off[threadIdx.x * WIN_ITEMS + j]; sum += (int)v[j]; }
+        int total;
+        uint32_t run = blk_off[blockIdx.x] + (uint32_t)mc_block_exscan<WIN_THREADS>(sum, s_warp, total);
+#pragma unroll
+        for (int j = 0; j < WIN_ITEMS; ++j) { s_off[threadIdx.x * WIN_ITEMS + j] = run; run += v[j]; }
+        __syncthreads();
+    }
+    int my_rows = 0;
+    for (int un = threadIdx.x; un < nu; un += WIN_THREADS) {
+    const uint32_t b = s_unit[un];
+    // the unit's read: last segment starting at or before b
+    int64_t seg;
+    {
+        int64_t lo = 0, hi = n_seg - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (__ldg(seg_start + mid) <= b) lo = mid; else hi = mid - 1;
+        }
+        seg = lo;
+    }
+    const uint32_t seg_b = __ldg(seg_start + seg), e_read = __ldg(seg_start + seg + 1);
+    const bool whole = (int)__ldg(reinterpret_cast<const uint4 *>(rec + seg_b)).z < k;     // the read is one unit
+    uint32_t n_out = 0;
+    const double myq = seg_qual[seg];
+    if (myq < qual_thresh || (whole && b != seg_b)) {          // whole read dropped (:167) / unit covered by the whole-read unit
+        if (!WRITE) unit_cnt[b] = 0u;
+        continue;
+    }
+    uint32_t e = e_read;
+    uint32_t out_pos = WRITE ? s_off[un] : 0u;
+    const uint32_t fidx = __ldg(first_idx + seg);
 
     alignas(16) ColState C;
     int map[MC_MAXK];
 #pragma unroll
     for (int c = 0; c < MC_MAXK; ++c) { C.cnt[c] = 0; map[c] = c; }
-    bool started = false;        // read_name == last_read  (this read already had a line with 'M')
+    bool started = b > fidx;     // read_name == last_read  (this read already had a line with 'M')
     bool has_mpos = false;
-    int mpos = 0, first_ind = 0, last_rev = 0, last_cid = 0;
+    int mpos = 0, first_ind = started ? __ldg(first_ind_arr + seg) : 0, last_rev = 0, last_cid = 0;
     uint32_t name_rec = b;
     uint32_t sticky_err = 0u;
 
@@ -240,6 +334,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     for (;;) {
         // ---- phase 1: advance to the next emission point ---------------------------------------------------------------
         while (!pending_close && i < e) {
+            if (!whole && !(r.flags & MC_RF_CAND)) e = i + 1;      // the closer ends the unit
             const bool same_read = started;
             if (!same_read) {                                      // :161-162
                 first_ind = r.event_idx;
@@ -306,10 +401,16 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
         feed();
         advance();
     }
-    if (!WRITE) seg_count[seg] = n_out;
-    (void)n_records;
-    (void)d_ncalls;
+    if (!WRITE) unit_cnt[b] = n_out;
+    my_rows += (int)n_out;
 #undef MPOS_TRUTHY
+    }
+    if (!WRITE) {
+        __syncthreads();
+        int total;
+        (void)mc_block_exscan<WIN_THREADS>(my_rows, s_warp, total);
+        if (threadIdx.x == 0) blk_tot[blockIdx.x] = (uint32_t)total;
+    }
 }
 
 __global__ void k_check_cap(const unsigned long long *d_ncalls, unsigned long long cap, unsigned long long *d_flag) {
@@ -327,19 +428,29 @@ extern "C" int mc_build_windows(const mc_record *d_rec, int64_t n_records, const
     MC_REQUIRE(skip_thresh >= 0, "skip_thresh must be >= 0");
     cudaStream_t st = (cudaStream_t)stream;
     MC_CUDA_CHECK(cudaMemsetAsync(d_ncalls, 0, 16, st));
-    if (n_seg <= 0) return MC_OK;
-    const unsigned nb = (unsigned)((n_seg + 127) / 128);
-    uint32_t *seg_off = reinterpret_cast<uint32_t *>(d_ws);
-    void *scan_ws = reinterpret_cast<uint8_t *>(d_ws) + ((n_seg * 4 + 255) / 256) * 256;
-    k_windows<false><<<nb, 128, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, *ref, skip_thresh, qual_thresh,
-                                          two_models, d_calls, (unsigned long long)call_cap, d_seg_count, nullptr,
-                                          reinterpret_cast<unsigned long long *>(d_ncalls));
+    if (n_seg <= 0 || n_records <= 0) return MC_OK;
+    MC_REQUIRE(n_records < (1ll << 32), "record count must fit 32 bits");
+    // workspace: [unit_cnt: u32 n_records][first_ind: i32 n_seg][blk_tot, blk_off: u32 nb each][scan sums]
+    const int64_t nb = (n_records + WIN_RECS - 1) / WIN_RECS;
+    auto up = [](int64_t bytes) { return ((bytes + 255) / 256) * 256; };
+    uint8_t *w = reinterpret_cast<uint8_t *>(d_ws);
+    uint32_t *unit_cnt = reinterpret_cast<uint32_t *>(w);
+    int32_t *first_ind = reinterpret_cast<int32_t *>(w + up(n_records * 4));
+    uint32_t *blk_tot = reinterpret_cast<uint32_t *>(w + up(n_records * 4) + up(n_seg * 4));
+    uint32_t *blk_off = blk_tot + nb;
+    void *scan_ws = w + up(n_records * 4) + up(n_seg * 4) + up(2 * nb * 4);
+    uint32_t *first_idx = d_seg_count;                             // caller's n_seg-sized scratch
+    k_first_m<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, n_seg, *ref, first_idx, first_ind);
     MC_LAUNCH_CHECK();
-    int rc = mc_exscan_u32(d_seg_count, seg_off, n_seg, d_ncalls, scan_ws, st);
+    k_windows<false><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
+                                                          skip_thresh, qual_thresh, two_models, d_calls, (unsigned long long)call_cap,
+                                                          unit_cnt, blk_tot, nullptr);
+    MC_LAUNCH_CHECK();
+    int rc = mc_exscan_u32(blk_tot, blk_off, nb, d_ncalls, scan_ws, st);
     if (rc) return rc;
-    k_windows<true><<<nb, 128, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, *ref, skip_thresh, qual_thresh,
-                                         two_models, d_calls, (unsigned long long)call_cap, d_seg_count, seg_off,
-                                         reinterpret_cast<unsigned long long *>(d_ncalls));
+    k_windows<true><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
+                                                         skip_thresh, qual_thresh, two_models, d_calls, (unsigned long long)call_cap,
+                                                         unit_cnt, nullptr, blk_off);
     MC_LAUNCH_CHECK();
     k_check_cap<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
                                  reinterpret_cast<unsigned long long *>(d_ncalls) + 1);

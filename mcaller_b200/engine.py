@@ -166,7 +166,7 @@ class Engine(object):
                                      C.c_void_p(seg_qual.data_ptr()), self.ref.ref(), self.skip_thresh, self.qual_thresh, self.two_models,
                                      C.c_void_p(calls.data_ptr()), call_cap, C.c_void_p(seg_count.data_ptr()),
                                      C.c_void_p(self.d_small.data_ptr() + 8 * 18), C.c_void_p(ws.data_ptr()), st))
-            self.launches += 6                       # 2 window passes + 3 scan kernels + capacity check
+            self.launches += 7                       # first-'M' pre-pass + 2 window passes + 3 scan kernels + capacity check
             v = self._read_small(17, 3)
             res.missing_quality = int(v[0])
             n_calls = int(v[1])

@@ -336,6 +336,77 @@ def test_layout_fuzz_matches_oracle(seed, cuda_lib, oracle):
         assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["errors"] == 0
 
 
+def _junk_blocks(tsv, seed):
+    """Insert blocks of 40-120 lines that are NOT kept (model_kmer NNNNNN, or fewer than 12 columns) but start like any
+    other line of the read (known contig, plain position): the line that closes an open window then lies one or more
+    3840-byte chunks after the window's last event.  Positions of the junk lines are either the previous line's (often a
+    candidate position: full parse) or far from it (usually not a candidate: the quick look passes them)."""
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for ln in tsv.decode().split("\n"):
+        out.append(ln)
+        f = ln.split("\t")
+        if len(f) < 13 or rnd.random() > 0.03:
+            continue
+        far = rnd.random() < 0.7
+        for _ in range(rnd.randint(40, 120)):
+            pos = int(f[1]) + (rnd.randint(30, 60) if far else 0)
+            if rnd.random() < 0.5:
+                g = list(f)
+                g[1], g[9], g[10], g[11], g[12] = str(pos), "NNNNNN", "0.00", "0.00", "inf"
+                out.append("\t".join(g))
+            else:
+                out.append("\t".join([f[0], str(pos)] + f[2:rnd.randint(3, 11)]))
+    return "\n".join(out).encode()
+
+
+@pytest.mark.parametrize("run_len", [0, 1, 3, 64])
+@pytest.mark.parametrize("variant", ["junk", "fuzz", "plain"])
+def test_scan_runs_and_quiet_chunks_match_oracle(variant, run_len, cuda_lib, oracle):
+    """The sparse scan passes over chunks whose lines all sit on non-candidate positions and carries the 'last kept line'
+    state along runs of consecutive chunks (mc_scan_set_run_len forces the run length; small inputs would otherwise use
+    runs of one chunk).  Rows, features and counters must equal the oracle's for every run length, also when the closing
+    line of a window is several chunks away and when line layouts are mutated."""
+    from mcaller_b200 import _lib, engine, models, read_qual, synth
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=211, contigs=[("ctgA", 14000), ("c", 9000)], n_reads=50, len_min=300, len_max=900)
+    tsv, fasta, fastq, quals = synth.generate(spec)
+    quals = {k.split("_")[0]: v for k, v in quals.items()}
+    if variant == "junk":
+        tsv = _junk_blocks(tsv, 9)
+    elif variant == "fuzz":
+        tsv = _mutate_layout(tsv, 12)
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    want = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=1, model=model, base="A", motif="GATC", cap=100000)
+    n_lines = tsv.count(b"\n") + (0 if tsv.endswith(b"\n") else 1)
+    L = _lib.lib()
+    before = L.mc_scan_set_run_len(run_len)
+    try:
+        outs = []
+        for dense in (False, True):
+            eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=1, two_models=True, dense=dense)
+            res = eng.run_chunk(eng.upload(tsv), len(tsv))
+            assert res.missing_quality == 0 and res.counters["lines"] == n_lines and res.counters["kept"] > 0
+            calls = res.calls()
+            mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
+            assert len(mine) == len(want["calls"]) > 30
+            for c, w in zip(mine, want["calls"]):
+                assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"] and int(c["empty_mask"]) == w["empty_mask"]
+                assert tsv[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
+                assert [float(x) for x in c["feat"][:7]] == w["feat"]
+                assert abs(float(c["prob"]) - w["prob"]) < 1e-12
+            st = eng.count_rows(res)
+            assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["errors"] == 0
+            outs.append(res.n_records)
+        assert outs[0] < outs[1]                      # sparse mode really recorded fewer lines than dense mode
+    finally:
+        L.mc_scan_set_run_len(before)
+
+
 def test_fastq_quality_on_device_matches_host(tmp_path, cuda_lib):
     """mc_fastq_index + mc_fastq_quality == read_qual.extract_read_quality (keys, means bit-equal, last duplicate wins)."""
     import gzip, random
