@@ -14,7 +14,7 @@
 // only read-level state they need is `last_read` / `first_read_ind` (:161-174), i.e. the read's first line with an 'M',
 // which k_first_m finds per read beforehand.  Reads whose first record lies within k of the contig start stay one unit:
 // a window at position 0 never closes (`if mpos and`, :179) and keeps its columns across non-candidate lines.
-// A block of 256 threads owns 1024 consecutive records, compacts the unit starts among them into shared memory and
+// A block of 256 threads owns 4096 consecutive records, compacts the unit starts among them into shared memory and
 // runs one thread per unit; two passes (count rows / write rows) so rows land in file order.  Column sums are
 // accumulated in numpy's pairwise order (8 running lanes + sequential tail) so np.mean is reproduced bit for bit.
 #include "common.cuh"
@@ -82,7 +82,8 @@ __device__ __forceinline__ uint8_t comp_base(uint8_t c) {
     }
 }
 
-constexpr int WIN_THREADS = 256, WIN_ITEMS = 4, WIN_RECS = WIN_THREADS * WIN_ITEMS;
+constexpr int WIN_THREADS = 256, WIN_ITEMS = 16, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 4096 records per block: ~300 units
+static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
 
 // first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
 __global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t n_seg,
@@ -113,39 +114,57 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
           mc_refindex R, int skip_thresh, double qual_thresh, int two_models, mc_call *__restrict__ calls,
           unsigned long long call_cap, uint32_t *__restrict__ unit_cnt /* [n_records], written at unit starts */,
           uint32_t *__restrict__ blk_tot, const uint32_t *__restrict__ blk_off) {
-    __shared__ uint32_t s_unit[WIN_RECS];
-    __shared__ uint32_t s_off[WIN_RECS];
+    __shared__ uint32_t s_unit[WIN_RECS];         // record index of each unit start of the block, in record order
+    __shared__ uint32_t s_off[WIN_RECS];          // write pass: row offset of each unit
+    __shared__ uint16_t s_seg[WIN_RECS];          // read segment of each unit, relative to the block's first record's
     __shared__ int s_warp[WIN_THREADS / 32 + 1];
+    __shared__ int64_t s_seg0;
     const int k = R.k;
     // ---- unit starts among this block's records, compacted in record order ------------------------------------------------
     int nu;
     {
-        const int64_t i0 = (int64_t)blockIdx.x * WIN_RECS + (int64_t)threadIdx.x * WIN_ITEMS;
+        const int64_t base = (int64_t)blockIdx.x * WIN_RECS;
+        if (threadIdx.x == 0) {                   // segment of the block's first record: last segment starting at or before it
+            int64_t lo = 0, hi = n_seg - 1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi + 1) >> 1;
+                if ((int64_t)__ldg(seg_start + mid) <= base) lo = mid; else hi = mid - 1;
+            }
+            s_seg0 = lo;
+        }
+        const int64_t i0 = base + (int64_t)threadIdx.x * WIN_ITEMS;
         uint32_t prev_cand = 0u;
         if (i0 > 0 && i0 <= n_records) prev_cand = __ldg(reinterpret_cast<const uint4 *>(rec + i0 - 1) + 1).w & MC_RF_CAND;
-        uint32_t ustart[WIN_ITEMS];
-        int cnt = 0;
+        uint32_t umask = 0u, nmask = 0u;          // unit starts / read starts among this thread's records
 #pragma unroll
         for (int j = 0; j < WIN_ITEMS; ++j) {
             const int64_t i = i0 + j;
-            bool u = false;
             if (i < n_records) {
                 const uint32_t fl = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1).w & 0xFFu;
                 const uint32_t cand = fl & MC_RF_CAND;
+                bool u;
                 if (i == 0 || (fl & MC_RF_NEWREAD)) {
+                    if (i != base) nmask |= 1u << j;
                     u = cand != 0u;
                     if (!u) u = (int)__ldg(reinterpret_cast<const uint4 *>(rec + i)).z < k;      // whole-read unit (see above)
                 } else {
                     u = cand != 0u && prev_cand == 0u;
                 }
+                if (u) umask |= 1u << j;
                 prev_cand = cand;
             }
-            if (u) ustart[cnt++] = (uint32_t)i;
         }
         int total;
-        const int off = mc_block_exscan<WIN_THREADS>(cnt, s_warp, total);
-        for (int j = 0; j < cnt; ++j) s_unit[off + j] = ustart[j];
-        nu = total;
+        const int off = mc_block_exscan<WIN_THREADS>(__popc(umask) | (__popc(nmask) << 16), s_warp, total);
+        int ou = off & 0xFFFF;
+        const int on = off >> 16;
+        for (uint32_t m = umask; m; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            s_unit[ou] = (uint32_t)(i0 + j);
+            s_seg[ou] = (uint16_t)(on + __popc(nmask & ((2u << j) - 1u)));
+            ++ou;
+        }
+        nu = total & 0xFFFF;
         __syncthreads();
     }
     if (WRITE) {
@@ -165,16 +184,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     int my_rows = 0;
     for (int un = threadIdx.x; un < nu; un += WIN_THREADS) {
     const uint32_t b = s_unit[un];
-    // the unit's read: last segment starting at or before b
-    int64_t seg;
-    {
-        int64_t lo = 0, hi = n_seg - 1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (__ldg(seg_start + mid) <= b) lo = mid; else hi = mid - 1;
-        }
-        seg = lo;
-    }
+    const int64_t seg = s_seg0 + s_seg[un];
     const uint32_t seg_b = __ldg(seg_start + seg), e_read = __ldg(seg_start + seg + 1);
     const bool whole = (int)__ldg(reinterpret_cast<const uint4 *>(rec + seg_b)).z < k;     // the read is one unit
     uint32_t n_out = 0;
