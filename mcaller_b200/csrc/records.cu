@@ -122,7 +122,7 @@ int mc_exscan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_
 extern "C" int64_t mc_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
     const int64_t a = ((n * 4 + 255) / 256) * 256;
-    // + the per-block row totals / offsets of the window builder (2 uint32 per 4096 records; sized for 1024)
+    // + the per-block row totals / offsets of the window builder (2 uint32 per block of records; sized for blocks of 1024)
     return 2 * a + ((8 * ((n + 1023) / 1024) + 255) / 256) * 256 + mc_exscan_ws_bytes(n) + 512;
 }
 static inline uint32_t *ws_a(void *ws) { return reinterpret_cast<uint32_t *>(ws); }

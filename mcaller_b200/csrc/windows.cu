@@ -14,7 +14,7 @@
 // only read-level state they need is `last_read` / `first_read_ind` (:161-174), i.e. the read's first line with an 'M',
 // which k_first_m finds per read beforehand.  Reads whose first record lies within k of the contig start stay one unit:
 // a window at position 0 never closes (`if mpos and`, :179) and keeps its columns across non-candidate lines.
-// A block of 256 threads owns 4096 consecutive records, compacts the unit starts among them into shared memory and
+// A block of 256 threads owns 3072 consecutive records, compacts the unit starts among them into shared memory and
 // runs one thread per unit; two passes (count rows / write rows) so rows land in file order.  Column sums are
 // accumulated in numpy's pairwise order (8 running lanes + sequential tail) so np.mean is reproduced bit for bit.
 #include "common.cuh"
@@ -82,7 +82,10 @@ __device__ __forceinline__ uint8_t comp_base(uint8_t c) {
     }
 }
 
-constexpr int WIN_THREADS = 256, WIN_ITEMS = 16, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 4096 records per block: ~300 units
+#ifndef MC_WIN_ITEMS
+#define MC_WIN_ITEMS 12
+#endif
+constexpr int WIN_THREADS = 256, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 3072 records per block: ~230 units, one per thread
 static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
 
 // first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
