@@ -132,9 +132,10 @@ static inline void *ws_s(void *ws, int64_t n) { return reinterpret_cast<uint8_t 
 namespace {
 
 // ---- stage 2: gather records into file order ----------------------------------------------------------------
-// Stage 1 always records the first kept line of a chunk because the line before it belongs to another warp.  With all
-// chunks done the predecessor is known: the record is dropped unless the previous kept line was a candidate (or there
-// is none, so the first kept line of the text stays: it may close a window handed over by the caller).
+// Stage 1 records the first kept line of a run of chunks blindly because the line before it belongs to another warp.
+// With all chunks done the predecessor is known (every chunk reports the state of the last kept line seen so far in its
+// run): the record is dropped unless the previous kept line was a candidate (or there is none, so the first kept line of
+// the text stays: it may close a window handed over by the caller).
 __global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ tile_tab, int64_t n_tiles, uint32_t *__restrict__ cnt_clean) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_tiles) return;
@@ -174,10 +175,6 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ til
 // k-mer equality flag (3 vs 10).  Columns split on runs of bytes <= 0x20 like str.split() (extract_contexts.py:150).
 // The walk classifies 16 aligned bytes per step (SWAR compare + IDP.4A packing, as in stage 1) instead of looping bytes.
 __device__ __forceinline__ uint32_t fin_gt20(uint32_t w) { return (((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u; }
-__device__ __forceinline__ uint32_t fin_eq0a(uint32_t w) {
-    const uint32_t t = ((w ^ 0x0a0a0a0au) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    return ~(t | w) & 0x80808080u;
-}
 __device__ __forceinline__ uint32_t fin_pack16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
     const uint32_t lo = 0x08040201u, hi = 0x80402010u;
     const uint32_t a = __dp4a(m1, hi, __dp4a(m0, lo, 0u)), b = __dp4a(m3, hi, __dp4a(m2, lo, 0u));
@@ -195,6 +192,59 @@ __device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) 
     if (sh == 0) return lo;
     const unsigned long long hi = __ldg(q + 1);
     return (lo >> sh) | (hi << (64 - sh));
+}
+
+// ---- 8-byte register fast paths for the values of a record (any other shape falls back to the byte loops of parse.cuh) ----
+// 0x80 per byte of v that is not an ASCII digit
+__device__ __forceinline__ unsigned long long nondigit8(unsigned long long v) {
+    const unsigned long long x = v ^ 0x3030303030303030ull;
+    return (((x & 0x7f7f7f7f7f7f7f7full) + 0x7676767676767676ull) | v) & 0x8080808080808080ull;
+}
+// n (1..7) digit bytes at the low end of v -> value
+__device__ __forceinline__ uint32_t digits_value(unsigned long long v, int n) {
+    const unsigned long long x = (v ^ 0x3030303030303030ull) << (64 - 8 * n);      // right-aligned digit values, zeros below
+    const uint32_t L = (uint32_t)x, H = (uint32_t)(x >> 32);
+    auto conv4 = [](uint32_t h) {                                 // 4 digit values, most significant in byte 0 -> 0..9999
+        const uint32_t t = ((h * 2561u) >> 8) & 0x00ff00ffu;
+        return (t * 6553601u) >> 16;
+    };
+    return conv4(L) * 10000u + conv4(H);
+}
+// "<1..7 digits><ws>" -> value; false for any other shape
+__device__ __forceinline__ bool fast_uint8(unsigned long long v, int &out) {
+    const unsigned long long nd = nondigit8(v);
+    if (nd == 0ull) return false;
+    const int n = (__ffsll((long long)nd) - 1) >> 3;
+    if (n == 0 || ((v >> (8 * n)) & 0xFFull) > 0x20ull) return false;
+    out = (int)digits_value(v, n);
+    return true;
+}
+// "<digits>.<digits><ws>" with at most 7 bytes before the whitespace -> mantissa and number of fraction digits
+__device__ __forceinline__ bool fast_decimal8(unsigned long long v, uint32_t &mant, int &nfrac) {
+    const unsigned long long nd = nondigit8(v);
+    if (nd == 0ull) return false;
+    const int p1 = (__ffsll((long long)nd) - 1) >> 3;             // first non-digit: must be the point
+    if (p1 == 0 || p1 > 6 || ((v >> (8 * p1)) & 0xFFull) != 0x2eull) return false;
+    const unsigned long long low = (1ull << (8 * p1)) - 1ull;
+    const unsigned long long w = (v & low) | ((v >> 8) & ~low);    // the point removed: 7 bytes
+    const unsigned long long nd2 = ((nd & low) | ((nd >> 8) & ~low)) & 0x0080808080808080ull;
+    if (nd2 == 0ull) return false;
+    const int p2 = (__ffsll((long long)nd2) - 1) >> 3;            // first non-digit after it: must be whitespace
+    if (((w >> (8 * p2)) & 0xFFull) > 0x20ull) return false;
+    mant = digits_value(w, p2);
+    nfrac = p2 - p1;
+    return true;
+}
+// token at pa == token at pb for tokens of up to 7 bytes: 1 / 0, or -1 when one of them is longer (byte loop decides)
+__device__ __forceinline__ int fast_tokens_equal8(unsigned long long a, unsigned long long b) {
+    auto ws8 = [](unsigned long long v) {                          // 0x80 per byte <= 0x20
+        return ~((((v & 0x7f7f7f7f7f7f7f7full) + 0x5f5f5f5f5f5f5f5full) | v)) & 0x8080808080808080ull;
+    };
+    const unsigned long long wa = ws8(a), wb = ws8(b);
+    if (wa == 0ull || wb == 0ull) return -1;
+    const int la = (__ffsll((long long)wa) - 1) >> 3, lb = (__ffsll((long long)wb) - 1) >> 3;
+    if (la != lb) return 0;
+    return (((a ^ b) & ((1ull << (8 * la)) - 1ull)) == 0ull) ? 1 : 0;
 }
 
 // do the L bytes at pa and pb differ (the '\n' padding after the text keeps the 8-byte loads legal).  Both sides are
@@ -242,24 +292,17 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
     int nf = 0, f2 = 0, f3 = 0, name_end = -1, f5 = 0, f6 = 0, f9 = 0, f10 = 0;
     uint32_t prev_nonws = 0u;          // was the byte before this step non-whitespace (the byte before the line is '\n')
     bool done = false;
-    for (int step = 0; step < (1 << 16) && !done; ++step) {
+    constexpr int MAX_STEPS = 256;     // 4 KB: twice the documented limit for the first 12 columns of a line
+    for (int step = 0; step < MAX_STEPS && !done; ++step) {
         const int64_t g = a0 + 16ll * step;
         if (g >= limit) break;
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + g));
         uint32_t nonws = fin_pack16(fin_gt20(v.x), fin_gt20(v.y), fin_gt20(v.z), fin_gt20(v.w));
-        uint32_t nl = fin_pack16(fin_eq0a(v.x), fin_eq0a(v.y), fin_eq0a(v.z), fin_eq0a(v.w));
-        if (step == 0) {                // ignore the bytes before the line start
-            const uint32_t keep = 0xFFFFu << skip;
-            nonws &= keep;
-            nl &= keep;
-        }
-        uint32_t valid = 0xFFFFu;
-        if (nl) {                       // stop at the newline
-            valid = (1u << (__ffs(nl) - 1)) - 1u;
-            done = true;
-        }
+        if (step == 0) nonws &= 0xFFFFu << skip;                 // ignore the bytes before the line start
+        // no newline test: a recorded line is a kept line, its first 12 columns start before its end (stage 1 checked), so
+        // the walk stops at the 11th column; MAX_STEPS bounds it for records that did not come from stage 1
         const int base = 16 * step - skip;                       // line-relative offset of byte 0 of this step
-        uint32_t fs = nonws & ~((nonws << 1) | prev_nonws) & valid;
+        uint32_t fs = nonws & ~((nonws << 1) | prev_nonws);
         if (name_end < 0 && nf >= 4) {                           // first whitespace (or the newline) after the read name
             const uint32_t z = ~nonws & 0xFFFFu & ((step == 0) ? (0xFFFFu << skip) : 0xFFFFu);
             const uint32_t zz = z & ~((1u << max(f3 - base, 0)) - 1u);
@@ -292,7 +335,22 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
     int ev_idx = 0;
     double diff = 0.0;
     if (nf < 11 || name_end < 0 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;   // cannot happen for a kept line
-    else if (lane > 0) parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+    else if (lane > 0) {
+        // usual shapes ("1234", "87.41", 6-mers) from 8-byte register loads; anything else takes the byte loops
+        const uint8_t *lp = text + line;
+        uint32_t m_ev = 0u, m_md = 0u;
+        int n_ev = 0, n_md = 0;
+        const int teq = fast_tokens_equal8(load8_unaligned(lp + f2), load8_unaligned(lp + f9));
+        if (line + f10 + 16 < limit && teq >= 0 && fast_uint8(load8_unaligned(lp + f5), ev_idx) &&
+            fast_decimal8(load8_unaligned(lp + f6), m_ev, n_ev) && fast_decimal8(load8_unaligned(lp + f10), m_md, n_md)) {
+            const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
+            diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
+            if (teq) fl |= MC_RF_EQ;
+        } else {
+            ev_idx = 0;
+            parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+        }
+    }
     r.name_off = (uint16_t)f3;
     r.name_len = (uint16_t)(name_end < 0 ? 0 : name_end - f3);
     r.event_idx = ev_idx;

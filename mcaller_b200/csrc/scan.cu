@@ -1,29 +1,34 @@
 // Stage 1 (K1): eventalign TSV tokeniser + line filter.  One WARP per 3840-byte text chunk, no block barriers,
-// text staged by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the parse.
+// text staged by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the parse; chunks that provably hold
+// nothing of interest are passed over after a look at the first two columns of their lines.
 //
 // Replaces the reader / tokeniser / per-line filters of the reference's extract_features
 // (extract_contexts.py:140-176): readlines + line.split()[:12], the '<12 fields' drop (:149-152),
 // the contig lookup (:154-160), the NNNNNN drop (:167) and the "does this k-mer touch an 'M'"
 // test that gates everything after (:176, :242, :269).
 //
-// Per chunk (persistent warps stride over the chunks of the text):
+// Persistent warps take RUNS of consecutive chunks (dynamic claim, one atomic per run) and carry "was the last kept line
+// a candidate" from chunk to chunk.  Per chunk:
 //   0. lane 0 has already asked the TMA engine for the 4096 staged bytes of this chunk (32 B look-behind, the
 //      3840-byte chunk, 224 B look-ahead) while the previous chunk was being parsed; it now issues the copy of the
 //      warp's next chunk into the other buffer and the warp waits on this buffer's mbarrier;
-//   1. each lane classifies 4 x 32 B in registers (SWAR compare + IDP.4A bit packing) into two bit maps --
-//      non-whitespace (byte > 0x20) and newline (byte == 0x0a); field starts = nonws & ~(nonws << 1);
-//   2. line starts inside the chunk come from the newline map; per-lane counts are prefix-summed with two ballots and
-//      the starts are compacted into a 32-entry list;
-//   3. one lane per line: rank/select on the field-start bits finds columns 1, 2, 10 and 12 without touching the bytes
-//      in between (the ~58 B read name is never walked); the contig and the NNNNNN test are 8-byte register compares
-//      against a warp-uniform hint, column 2 is decoded from one 8-byte register load and the per-position candidate
-//      bitmap (L1/L2 resident) is tested;
-//   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the chunk, or
+//   1. each lane builds the newline bit map of 4 x 32 B in registers (SWAR compare, 3 instructions per word, + IDP.4A bit
+//      packing) and derives the line starts inside its own 128 bytes;
+//   2a. quiet test (only when the last kept line was not a candidate): every lane looks at the line(s) starting in its
+//      128 bytes -- 8-byte register compare with the warp's contig hint, position decoded from one 8-byte register load,
+//      one bit test in the per-position candidate bitmap (L1/L2 resident).  If every line is "hint contig, plain position,
+//      not a candidate" the chunk is done: none of its lines can get a record or change the carried state, whatever the
+//      rest of the line holds.  (~91 % of the chunks for GATC.)
+//   3. otherwise the full parse: non-whitespace map -> field starts = nonws & ~(nonws << 1); per-lane line counts
+//      prefix-summed with two ballots into a 32-entry line list; one lane per line: rank/select on the field-start bits
+//      finds columns 1, 2, 10 and 12 without touching the bytes in between (the ~58 B read name is never walked); 12-column
+//      check, contig lookup, NNNNNN test, position, candidate bit;
+//   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the run, or
 //      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags}.  Their
 //      values (event index, currents, k-mer equality, read-name span) are parsed in stage 2 at full lane occupancy.
 //      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
-// Algorithmic HBM traffic: the text itself (once) + 32 B per record (~2 B per line in sparse mode).
+// Algorithmic HBM traffic: the text itself (once) + 32 B per record (~1 B per line in sparse mode).
 #include "parse.cuh"
 
 namespace {
@@ -586,7 +591,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 else {
                     const uint32_t below = kept_m & lt_mask;
                     const int st = below ? (int)((cand_m >> (31 - __clz(below))) & 1u) : prev_state;
-                    emit = (st != 0);            // predecessor is a candidate, or this is the first kept line of the chunk
+                    emit = (st != 0);            // predecessor is a candidate, or this is the first kept line of the run
                     if (st < 0) filler_lane = true;
                 }
             }

@@ -21,40 +21,62 @@
 
 namespace {
 
+// Column values live in local memory; the column counts (8 x 8 bits, saturating at 255 -- more than 128 events in a column is
+// reported as MC_CE_COLUMN anyway) and the column map (8 x 4 bits) are packed in registers, so the count pass and the
+// control flow of the write pass touch no memory.
+#ifndef MC_WIN_SMEM_ROWS
+#define MC_WIN_SMEM_ROWS 2
+#endif
+constexpr int SROWS = MC_WIN_SMEM_ROWS;           // first values of every column kept in shared memory (0: all in local memory)
 struct ColState {
     double lane[MC_MAXK][8];
     double pend[MC_MAXK][8];
-    int cnt[MC_MAXK];
+    double *sm;                                   // this thread's [SROWS][MC_MAXK] slice of shared memory, thread-interleaved
+    __device__ __forceinline__ double get(int c, int j) const {
+        if (SROWS > 0 && j < SROWS) return sm[(j * MC_MAXK + c) * SM_STRIDE];
+        return pend[c][j];
+    }
+    __device__ __forceinline__ void put(int c, int j, double v) {
+        if (SROWS > 0 && j < SROWS) sm[(j * MC_MAXK + c) * SM_STRIDE] = v;
+        else pend[c][j] = v;
+    }
+    static constexpr int SM_STRIDE = 256;         // = WIN_THREADS (asserted below): element e of thread t sits at [e][t]
 };
+__device__ __forceinline__ int cnt_get(unsigned long long cnts, int c) { return (int)((cnts >> (8 * c)) & 0xFFull); }
+__device__ __forceinline__ void cnt_inc(unsigned long long &cnts, int c) {
+    if (cnt_get(cnts, c) < 255) cnts += 1ull << (8 * c);
+}
+__device__ __forceinline__ void cnt_clear(unsigned long long &cnts, int c) { cnts &= ~(0xFFull << (8 * c)); }
+__device__ __forceinline__ int map_get(uint32_t mp, int c) { return (int)((mp >> (4 * c)) & 0xFu); }
 
-__device__ __forceinline__ void col_push(ColState &C, int c, double v) {
-    const int n = C.cnt[c];
+__device__ __forceinline__ void col_push(ColState &C, unsigned long long &cnts, int c, double v) {
+    const int n = cnt_get(cnts, c);
     const int j = n & 7;
-    C.pend[c][j] = v;
-    C.cnt[c] = n + 1;
+    C.put(c, j, v);
+    cnt_inc(cnts, c);
     if (j == 7) {
         if (n == 7) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) C.lane[c][i] = C.pend[c][i];
+            for (int i = 0; i < 8; ++i) C.lane[c][i] = C.get(c, i);
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) C.lane[c][i] = __dadd_rn(C.lane[c][i], C.pend[c][i]);
+            for (int i = 0; i < 8; ++i) C.lane[c][i] = __dadd_rn(C.lane[c][i], C.get(c, i));
         }
     }
 }
 
 // numpy add.reduce pairwise order for n <= 128 (see oracle/mcaller_oracle.c np_pairwise), then / n
-__device__ __forceinline__ double col_mean(const ColState &C, int c) {
-    const int n = C.cnt[c];
+__device__ __forceinline__ double col_mean(const ColState &C, unsigned long long cnts, int c) {
+    const int n = cnt_get(cnts, c);
     double res;
     if (n < 8) {
         res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, C.pend[c][i]);
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, C.get(c, i));
     } else {
         const double *r = C.lane[c];
         res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (int i = 0; i < (n & 7); ++i) res = __dadd_rn(res, C.pend[c][i]);
+        for (int i = 0; i < (n & 7); ++i) res = __dadd_rn(res, C.get(c, i));
     }
     return __ddiv_rn(res, (double)n);
 }
@@ -87,6 +109,7 @@ __device__ __forceinline__ uint8_t comp_base(uint8_t c) {
 #endif
 constexpr int WIN_THREADS = 256, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 3072 records per block: ~230 units, one per thread
 static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
+static_assert(ColState::SM_STRIDE == WIN_THREADS, "shared-memory column slices are interleaved by thread");
 
 // first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
 __global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t n_seg,
@@ -122,6 +145,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     __shared__ uint16_t s_seg[WIN_RECS];          // read segment of each unit, relative to the block's first record's
     __shared__ int s_warp[WIN_THREADS / 32 + 1];
     __shared__ int64_t s_seg0;
+    extern __shared__ __align__(16) double s_cols[];              // write pass: [SROWS][MC_MAXK][WIN_THREADS] first values of each column
     const int k = R.k;
     // ---- unit starts among this block's records, compacted in record order ------------------------------------------------
     int nu;
@@ -201,9 +225,9 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     const uint32_t fidx = __ldg(first_idx + seg);
 
     alignas(16) ColState C;
-    int map[MC_MAXK];
-#pragma unroll
-    for (int c = 0; c < MC_MAXK; ++c) { C.cnt[c] = 0; map[c] = c; }
+    C.sm = WRITE ? s_cols + threadIdx.x : nullptr;
+    unsigned long long cnts = 0ull;                // events per column slot
+    uint32_t mp = 0x76543210u;                     // window column -> column slot (the multi-M carry permutes it)
     bool started = b > fidx;     // read_name == last_read  (this read already had a line with 'M')
     bool has_mpos = false;
     int mpos = 0, first_ind = started ? __ldg(first_ind_arr + seg) : 0, last_rev = 0, last_cid = 0;
@@ -215,7 +239,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     // emits the row(s) for the open window; `close_idx` = ordered index of the closing record (or ~0u)
     auto emit_window = [&](uint32_t close_idx, int chrom_cid) {
         int n_empty = 0;
-        for (int c = 0; c < k; ++c) n_empty += (C.cnt[map[c]] == 0);
+        for (int c = 0; c < k; ++c) n_empty += (cnt_get(cnts, map_get(mp, c)) == 0);
         if (WRITE) {
             if (out_pos < call_cap) {
                 mc_call &o = calls[out_pos];
@@ -246,11 +270,11 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
                 if (n_empty <= skip_thresh) {
                     o.kind = MC_CALL;
                     for (int c = 0; c < k; ++c) {                 // :186-188 (forward reads are flipped)
-                        const int src = map[last_rev ? c : (k - 1 - c)];
-                        if (C.cnt[src] == 0) { o.feat[c] = 0.0; empty_mask |= 1u << c; }
+                        const int src = map_get(mp, last_rev ? c : (k - 1 - c));
+                        if (cnt_get(cnts, src) == 0) { o.feat[c] = 0.0; empty_mask |= 1u << c; }
                         else {
-                            if (C.cnt[src] > 128) err |= MC_CE_COLUMN;
-                            o.feat[c] = col_mean(C, src);
+                            if (cnt_get(cnts, src) > 128) err |= MC_CE_COLUMN;
+                            o.feat[c] = col_mean(C, cnts, src);
                         }
                     }
                     o.feat[k] = myq;                              // :189-193
@@ -306,10 +330,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
         }
         ++n_out;
     };
-    auto reset_cols = [&]() {
-#pragma unroll
-        for (int c = 0; c < MC_MAXK; ++c) C.cnt[c] = 0;
-    };
+    auto reset_cols = [&]() { cnts = 0ull; };
 
     // The row-producing code (column means, divisions, context look-ups) is by far the heaviest path and a lane needs it
     // only once per ~20 records.  Run in rounds so the warp executes it together: each lane advances through its records
@@ -337,8 +358,8 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
             last_cid = cid;
             name_rec = i;
             if (r.flags & MC_RF_BADNUM) sticky_err |= MC_CE_BADNUM;
-            if (WRITE) col_push(C, map[first_m], r.diff);
-            else C.cnt[map[first_m]] += 1;
+            if (WRITE) col_push(C, cnts, map_get(mp, first_m), r.diff);
+            else cnt_inc(cnts, map_get(mp, first_m));
         } else if (MPOS_TRUTHY) {                                  // :289-291
             has_mpos = false;
             reset_cols();
@@ -403,12 +424,14 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
             int sp = mpos - last_mpos;
             if (sp > k) sp = k;
             if (sp <= 0) { sticky_err |= MC_CE_SPACING; sp = k; }
-            int nm[MC_MAXK];
+            uint32_t nmp = 0u;
             for (int c = 0; c < k; ++c) {
-                if (c < sp) { nm[c] = map[k - sp + c]; C.cnt[nm[c]] = 0; }
-                else nm[c] = map[c - sp];
+                int slot;
+                if (c < sp) { slot = map_get(mp, k - sp + c); cnt_clear(cnts, slot); }
+                else slot = map_get(mp, c - sp);
+                nmp |= (uint32_t)slot << (4 * c);
             }
-            for (int c = 0; c < k; ++c) map[c] = nm[c];
+            mp = nmp | (mp & ~((k < 8) ? ((1u << (4 * k)) - 1u) : 0xFFFFFFFFu));
         }
         pending_close = false;
         feed();
@@ -461,7 +484,9 @@ extern "C" int mc_build_windows(const mc_record *d_rec, int64_t n_records, const
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(blk_tot, blk_off, nb, d_ncalls, scan_ws, st);
     if (rc) return rc;
-    k_windows<true><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
+    constexpr size_t cols_bytes = sizeof(double) * SROWS * MC_MAXK * WIN_THREADS;
+    MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_bytes));
+    k_windows<true><<<(unsigned)nb, WIN_THREADS, cols_bytes, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
                                                          skip_thresh, qual_thresh, two_models, d_calls, (unsigned long long)call_cap,
                                                          unit_cnt, nullptr, blk_off);
     MC_LAUNCH_CHECK();

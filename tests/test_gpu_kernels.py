@@ -62,6 +62,64 @@ def test_scan_records_match_python_split(tmp_path, cuda_lib):
         assert not (r["flags"] & 12)
 
 
+def test_record_values_of_odd_number_shapes(cuda_lib):
+    """k_finish_records parses the usual shapes ("1234", "87.41", 6-mers) from 8-byte register loads and everything else
+    with byte loops: event index, np.round(float(ev) - float(model), 4) and the k-mer equality flag must equal Python's
+    for mixed shapes (no fraction, 1-5 fraction digits, signs, leading zeros, wide integers, long k-mer tokens)."""
+    import random
+    from mcaller_b200 import engine, synth
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=71, contigs=[("ctg", 8000)], n_reads=12, len_min=200, len_max=500)
+    tsv, fasta, fastq, quals = synth.generate(spec)
+    rnd = random.Random(4)
+
+    def reshape(x):
+        v = float(x)
+        u = rnd.random()
+        if u < 0.5:
+            return x
+        return rnd.choice(["%d" % int(v), "%.1f" % v, "%.3f" % v, "%.5f" % v, "+%.2f" % v, "0%.2f" % v, "%.2f" % (v + 1000.0), "%d." % int(v)])
+
+    out = []
+    for ln in tsv.decode().split("\n"):
+        f = ln.split("\t")
+        if len(f) >= 13 and f[9] != "NNNNNN":
+            f[6], f[10] = reshape(f[6]), reshape(f[10])
+            u = rnd.random()
+            if u < 0.1:
+                f[5] = "+" + f[5]
+            elif u < 0.2:
+                f[5] = "00" + f[5]
+            elif u < 0.25:
+                f[5] = "1234" + f[5]
+            elif u < 0.3:
+                f[5] = "-" + f[5]
+            if rnd.random() < 0.1:
+                f[2] = f[2] + "ACGT"                       # long tokens: equality decided by the byte loop
+                if rnd.random() < 0.5:
+                    f[9] = f[2]
+        out.append("\t".join(f))
+    data = "\n".join(out).encode()
+    seqs = {"ctg": synth.genome(spec, 0).tobytes().decode()}
+    ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
+    from mcaller_b200 import models, read_qual
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    quals = {k.split("_")[0]: v for k, v in quals.items()}
+    eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=1, two_models=True, dense=True)
+    res = eng.run_chunk(eng.upload(data), len(data))
+    rec = eng.records(res.n_records)
+    want = []
+    for ln in data.split(b"\n"):
+        f = ln.split()
+        if len(f) >= 12 and f[9] != b"NNNNNN":
+            want.append((int(f[5]), float(np.round(float(f[6]) - float(f[10]), 4)), f[2] == f[9]))
+    assert len(want) == res.n_records > 3000
+    for r, w in zip(rec, want):
+        assert (int(r["event_idx"]), float(r["diff"]), bool(r["flags"] & 1)) == w
+        assert not (r["flags"] & 12)
+
+
 def test_sparse_records_are_subset_with_same_calls(tmp_path, cuda_lib):
     """Sparse mode (candidates + closers only) must give exactly the rows of dense mode."""
     from mcaller_b200 import engine
