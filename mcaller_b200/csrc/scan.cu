@@ -633,9 +633,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             __syncwarp();
         }
         if (lane == 0) {
-            d_tile_tab[2 * (int64_t)chunk] = (uint32_t)(slot_cur - n_emitted);
-            // count | filler flag | state of the chunk's last kept line (0 none, 1 not a candidate, 2 candidate)
-            d_tile_tab[2 * (int64_t)chunk + 1] = n_emitted | (filler << 16) | ((uint32_t)(prev_state + 1) << 17);
+            // {first slot, count | filler flag | state of the last kept line so far in the run (0 none, 1 not a candidate,
+            // 2 candidate)} as one 8-byte store
+            reinterpret_cast<uint2 *>(d_tile_tab)[chunk] =
+                make_uint2((uint32_t)(slot_cur - n_emitted), n_emitted | (filler << 16) | ((uint32_t)(prev_state + 1) << 17));
         }
         if (last_of_run) prev_state = -1;
         chunk = next;
@@ -675,6 +676,7 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     MC_REQUIRE(d_text && ref && d_rec && d_tile_tab && d_counters, "null pointer");
     MC_REQUIRE(nbytes >= 0 && rec_cap >= 0, "negative size");
     MC_REQUIRE((reinterpret_cast<uintptr_t>(d_text) & 15) == 0, "d_text must be 16-byte aligned");
+    MC_REQUIRE((reinterpret_cast<uintptr_t>(d_tile_tab) & 7) == 0, "d_tile_tab must be 8-byte aligned");
     MC_REQUIRE(ref->k >= 1 && ref->k <= MC_MAXK, "k out of range");
     MC_REQUIRE(ref->n_contigs >= 1 && ref->n_contigs < 65535, "contig count out of range");
     MC_REQUIRE(nbytes < (1ll << 47), "chunk too large");

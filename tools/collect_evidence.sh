@@ -4,6 +4,8 @@
 #   2. ncu launch list of one full-size step                             -> launches_full_step.csv
 #   3. ncu DRAM bytes of the full-size k_scan launch                     -> k_scan_dram_full_size.csv
 #   4. ncu --set full of k_scan on a 2 GB input (+ source page)          -> k_scan_full.ncu-rep
+#   5. ncu --set full of the secondary kernels at full size              -> secondary_full.ncu-rep
+#   6. compute-sanitizer memcheck over parity tests                      -> memcheck.txt
 # Summaries are produced afterwards in the build container with tools/ncu_summary.py, tools/ncu_phases.py and
 # tools/launch_summary.py and copied into profiles/.
 set -u
@@ -17,5 +19,10 @@ timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
     python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/dram.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k k_scan -c 1 -f -o $O/k_scan_full \
     python bench.py --reads 4000 --steps 1 --warmup 0 --no-e2e --no-cpu > $O/full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_finish_records|k_mlp|k_windows|k_gather|k_first_m' -c 6 -f \
+    -o $O/secondary_full python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/secondary.log 2>&1
+CMD="compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_golden.py tests/test_gpu_kernels.py -x -q -k 'diffs_match and (gatc_s1 or adversarial or A_s2) or quiet_chunks and junk or odd_number_shapes'"
+( timeout 1200 bash -c "$CMD" 2>&1 | tail -5; echo "command: $CMD" ) > $O/memcheck.txt
 ls -la $O
 tail -c 600 $O/bench_default.json
+cat $O/memcheck.txt

@@ -8,12 +8,15 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MARKERS = [("helpers: TMA/mbarrier", "// ---- TMA / mbarrier wrappers"), ("A  byte classification + packing", "// ---- byte classification"),
-           ("D  generic field walk / next_bit", "// ---- generic field walk"), ("D  line_fields / nth_bit / load8", "// ---- field location"),
+MARKERS = [("helpers: TMA/mbarrier", "// ---- TMA / mbarrier wrappers"), ("A  gt20 + IDP.4A packing (pack32 is shared with the newline map)", "// ---- byte classification"),
+           ("D  generic field walk / next_bit", "// ---- generic field walk"), ("D  line_fields / nth_bit / load8 / parse_pos8", "// ---- field location"),
            ("D  classify_line (+ global slow path)", "enum { ST_KEPT"), ("Z  kernel prologue / staging lambda", "__global__ void __launch_bounds__(THREADS"),
-           ("B0 prefetch + mbarrier wait", "// ---- 0. prefetch"), ("B1 mask loop body (loads, shuffle, stores)", "// ---- 1. classify"),
-           ("C  line scan + slots + last-line end", "// ---- 2. line list"), ("C  line list write", "// list entries"),
-           ("D  per-line driver", "// ---- 3. structural"), ("E  ballots / emit decision", "// ---- 4. which lines"),
+           ("A  newline test (3 instructions per word)", "// byte == 0x0a in three instructions per word: a LOP3"),
+           ("Z  kernel prologue / staging lambda", "// warp-uniform state"),
+           ("B0 prefetch + run claim + mbarrier wait", "// ---- 0. prefetch"), ("B1 newline map loop (loads, stores)", "// ---- 1. newline map"),
+           ("C  line starts per lane", "// ---- 2. line list: lane owns"), ("Q  quiet test (rounds over the lanes' own lines)", "// ---- 2a. quick look"),
+           ("C  line list prefix + slots (full parse only)", "// ---- 2b. line list"), ("C  line list write (full parse only)", "// list entries"),
+           ("D  full parse: field-start map + per-line driver", "// ---- 3. full parse"), ("E  ballots / emit decision", "// ---- 4. which lines"),
            ("E  record write / chunk table", "// ---- 5. raw records"), ("Z  counters / tail", "// ---- counters")]
 
 
