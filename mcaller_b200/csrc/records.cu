@@ -156,17 +156,27 @@ __global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ 
 __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_cnt,
                                                const uint32_t *__restrict__ tile_dst, int64_t n_tiles, const mc_record *__restrict__ in,
                                                unsigned long long in_cap, mc_record *__restrict__ out, unsigned long long out_cap) {
-    // one thread per chunk: chunks hold a handful of records in sparse mode
+    // a warp owns 32 chunks; most hold no record (sparse mode), so the warp walks the non-empty ones and copies each
+    // chunk's records with one lane per 16-byte half record (coalesced 32-byte records, no per-thread copy loops)
+    const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= n_tiles) return;
-    const unsigned long long src = tile_tab[2 * tile], cnt = tile_cnt[tile], dst = tile_dst[tile];
-    for (unsigned long long j = 0; j < cnt; ++j) {
-        if (src + j >= in_cap || dst + j >= out_cap) break;          // records dropped by a capacity overflow
-        const uint4 *s = reinterpret_cast<const uint4 *>(in + src + j);
-        uint4 *d = reinterpret_cast<uint4 *>(out + dst + j);
-        const uint4 a = s[0], b = s[1];
-        d[0] = a;
-        d[1] = b;
+    unsigned long long src = 0ull, dst = 0ull;
+    uint32_t cnt = 0u;
+    if (tile < n_tiles) {
+        cnt = tile_cnt[tile];
+        if (cnt) { src = tile_tab[2 * tile]; dst = tile_dst[tile]; }
+    }
+    uint32_t busy = __ballot_sync(0xffffffffu, cnt != 0u);
+    while (busy) {
+        const int l = __ffs(busy) - 1;
+        busy &= busy - 1u;
+        const unsigned long long s0 = __shfl_sync(0xffffffffu, src, l), d0 = __shfl_sync(0xffffffffu, dst, l);
+        const uint32_t c = __shfl_sync(0xffffffffu, cnt, l);
+        for (uint32_t h = lane; h < 2u * c; h += 32u) {              // half records
+            const unsigned long long j = h >> 1;
+            if (s0 + j >= in_cap || d0 + j >= out_cap) continue;     // records dropped by a capacity overflow
+            reinterpret_cast<uint4 *>(out + d0 + j)[h & 1u] = __ldg(reinterpret_cast<const uint4 *>(in + s0 + j) + (h & 1u));
+        }
     }
 }
 

@@ -698,6 +698,8 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     int run_len = MC_SCAN_RUN;
     while (run_len > 1 && n_chunks < blocks * WARPS * 8 * (int64_t)run_len) run_len >>= 1;
     if (g_run_len_override > 0) run_len = g_run_len_override;
+    // the run cursor must start at zero whatever the caller did with the counter block
+    MC_CUDA_CHECK(cudaMemsetAsync(d_counters + MC_C_RUN_CURSOR, 0, sizeof(uint64_t), (cudaStream_t)stream));
     k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense, d_rec,
                                                                      (unsigned long long)rec_cap, d_tile_tab,
                                                                      reinterpret_cast<unsigned long long *>(d_counters));
