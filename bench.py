@@ -40,6 +40,9 @@ def parse_args():
     p.add_argument("--e2e-chunk", type=int, default=1 << 30)
     p.add_argument("--cpu-reads", type=int, default=4000, help="reads in the bounded CPU-baseline sample")
     p.add_argument("--skip", type=int, default=0, help="-s skip threshold")
+    p.add_argument("--classifier", default="NN", choices=["NN", "RF"],
+                   help="NN: the shipped r95 MLP pickle (BASELINE configs[1]); RF: a forest with the reference's -c RF hyper-parameters "
+                        "(train_model.py:39-45) fitted on synthetic features (configs[3], tree-walk kernel)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     return p.parse_args()
@@ -117,6 +120,18 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def fit_reference_rf():
+    """{'MG': rf, 'MH': rf} with the hyper-parameters of the reference's -c RF (train_model.py:39-45 minus the arguments
+    current scikit-learn has dropped), fitted on 40 000 synthetic feature rows -- no RF pickle is shipped."""
+    from sklearn.ensemble import RandomForestClassifier
+    rng = np.random.RandomState(0)
+    X = np.column_stack([rng.normal(0.0, 2.4, size=(40000, 6)), rng.uniform(3.0, 24.0, size=40000)])
+    y = np.where(X[:, 2] - 0.6 * X[:, 3] + 0.3 * rng.normal(size=40000) > 0.5, "m6A", "A")
+    rf = RandomForestClassifier(n_estimators=50, criterion="entropy", max_depth=10, max_features=4, min_samples_leaf=2,
+                                min_samples_split=3, random_state=0, n_jobs=-1).fit(X, y)
+    return {"MG": rf, "MH": rf}
+
+
 def build_world(args, rank, world, n_generate=None):
     """Reference index, models, quality table and this rank's synthetic text in HBM."""
     import torch
@@ -135,7 +150,7 @@ def build_world(args, rank, world, n_generate=None):
     torch.cuda.synchronize()
     keys, q = synth_device.quality_table_for(spec, lo, hi)
     qt = read_qual.build_quality_table(dict(zip(keys, q.tolist())))
-    model = models.load_model_file(MODEL)
+    model = models.load_model_file(MODEL) if args.classifier == "NN" else fit_reference_rf()
     e0, e1, two = models.select_models(model, "A")
     dm = models.DeviceModels(e0, e1)
     engine = eng_mod.Engine(ref, models=dm, qual_table=qt, skip_thresh=args.skip, qual_thresh=0.0, two_models=two, histogram=True)
@@ -227,7 +242,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic E. coli 4.6 Mb, 100k reads, -m GATC, NN model (r95), -n 6, -s %d" % args.skip,
+                "config": {"workload": "synthetic E. coli 4.6 Mb, 100k reads, -m GATC, %s, -n 6, -s %d"
+                                       % ("NN model (r95)" if args.classifier == "NN" else "RF model (50 trees, depth 10)", args.skip),
                            "sample": "%d reads (%.2f GB of eventalign TSV) per step" % (n_s, end / 1e9)},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores, "kind": "port",
                                  "sample": "C restatement of the reference (oracle/mcaller_oracle.c) on %d reads, %d host threads; the "
@@ -361,8 +377,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic E. coli 4.6 Mb, %d reads per GPU (%.1f GB eventalign TSV), -m GATC, NN model (r95), -n 6, -s %d"
-                                       % (args.reads, nbytes / 1e9, args.skip),
+                "config": {"workload": "synthetic E. coli 4.6 Mb, %d reads per GPU (%.1f GB eventalign TSV), -m GATC, %s, -n 6, -s %d"
+                                       % (args.reads, nbytes / 1e9, "NN model (r95)" if args.classifier == "NN" else
+                                          "RF model (50 trees, depth 10, fitted on synthetic features)", args.skip),
                            "l2": "inputs (%.1f GB) larger than L2 (126 MB); no flush needed" % (nbytes / 1e9),
                            "parallelism": "reads sharded over %d GPU(s); histogram all-reduce + slice-edge hand-off" % world,
                            "calls_per_step": total_calls // args.steps, "lines_per_step_per_gpu": res.counters["lines"],
