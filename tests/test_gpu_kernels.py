@@ -465,6 +465,50 @@ def test_scan_runs_and_quiet_chunks_match_oracle(variant, run_len, cuda_lib, ora
         L.mc_scan_set_run_len(before)
 
 
+@pytest.mark.parametrize("mode", ["A_dense", "p_one_strand"])
+def test_window_units_in_other_site_regimes(mode, tmp_path, cuda_lib, oracle):
+    """The window builder cuts reads into units at non-candidate records; GATC gives short units.  Two other regimes against
+    the oracle: `-m A` (every fourth position a target: long candidate runs, multi-M carries everywhere, skips allowed) and
+    `-p` with targets on one strand per contig (reads of the other strand are all candidates without a single 'M': the
+    first-'M' pre-pass finds nothing and every unit is a no-op)."""
+    from mcaller_b200 import engine, models, read_qual, synth
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=808, contigs=[("one", 15000), ("two", 11000)], n_reads=120, len_min=300, len_max=1200)
+    tsv, fasta, fastq, quals = synth.generate(spec)
+    quals = {k.split("_")[0]: v for k, v in quals.items()}
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    if mode == "A_dense":
+        kw_ref, kw_orc, s = dict(motif="A"), dict(motif="A"), 2
+    else:
+        import random
+        rnd = random.Random(5)
+        pos_path = os.path.join(str(tmp_path), "pos.txt")
+        with open(pos_path, "w") as fh:
+            for p, c in enumerate(seqs["one"]):
+                if c == "A" and 20 < p < len(seqs["one"]) - 20 and rnd.random() < 0.03:
+                    fh.write("one\t%d\t+\tm6A\n" % p)
+            for p, c in enumerate(seqs["two"]):
+                if c == "T" and 20 < p < len(seqs["two"]) - 20 and rnd.random() < 0.03:
+                    fh.write("two\t%d\t-\tm6A\n" % p)
+        kw_ref, kw_orc, s = dict(positions_file=pos_path), dict(positions=pos_path), 1
+    ref = ReferenceIndex(seqs, "A", k=6, **kw_ref)
+    want = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=s, model=model, base="A", cap=400000, **kw_orc)
+    eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=s, two_models=True)
+    res = eng.run_chunk(eng.upload(tsv), len(tsv))
+    calls = res.calls()
+    mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
+    assert len(mine) == len(want["calls"]) > 100
+    for c, w in zip(mine, want["calls"]):
+        assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"] and int(c["empty_mask"]) == w["empty_mask"]
+        assert tsv[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
+        assert [float(x) for x in c["feat"][:7]] == w["feat"]
+        assert abs(float(c["prob"]) - w["prob"]) < 1e-12
+    st = eng.count_rows(res)
+    assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["multi"] == want["counters"]["multi"] and st["errors"] == 0
+
+
 def test_fastq_quality_on_device_matches_host(tmp_path, cuda_lib):
     """mc_fastq_index + mc_fastq_quality == read_qual.extract_read_quality (keys, means bit-equal, last duplicate wins)."""
     import gzip, random
