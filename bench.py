@@ -43,6 +43,7 @@ def parse_args():
     p.add_argument("--classifier", default="NN", choices=["NN", "RF"],
                    help="NN: the shipped r95 MLP pickle (BASELINE configs[1]); RF: a forest with the reference's -c RF hyper-parameters "
                         "(train_model.py:39-45) fitted on synthetic features (configs[3], tree-walk kernel)")
+    p.add_argument("--contig-name", default="ecoli", help="name of the synthetic contig (column 1 of every line)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     return p.parse_args()
@@ -137,9 +138,9 @@ def build_world(args, rank, world, n_generate=None):
     import torch
     from mcaller_b200 import engine as eng_mod, models, read_qual, refmark, synth, synth_device
     from mcaller_b200.refindex import ReferenceIndex
-    spec = synth.SynthSpec(seed=0, contigs=[("ecoli", 4600000)], n_reads=args.reads * world, len_min=1000, len_max=3000)
+    spec = synth.SynthSpec(seed=0, contigs=[(args.contig_name, 4600000)], n_reads=args.reads * world, len_min=1000, len_max=3000)
     genome = synth.genome(spec, 0)
-    seqs = {"ecoli": genome.tobytes().decode()}
+    seqs = {args.contig_name: genome.tobytes().decode()}
     ref = ReferenceIndex(seqs, "A", motif="GATC", k=6)
     meth = {0: (synth.meth_sites(spec, 0, ref.site_fwd_bits[:4600000]), synth.meth_sites(spec, 0, ref.site_rev_bits[:4600000]))}
     gen = synth_device.DeviceSynth(spec, ref, meth)

@@ -61,6 +61,7 @@ struct WarpSmem {
     alignas(16) uint32_t nl[NW + 4];     // newline bits
     uint16_t lstart[LCAP + 4];
     uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
+    unsigned long long key[4];           // the hint contig's name in 8-byte pieces (quiet test; names of up to 31 bytes)
     alignas(8) unsigned long long bar[2];
 };
 
@@ -293,6 +294,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         hint_nlen = __ldg(R.d_name_off + c + 1) - o0;
         hint_key = 0ull;
         for (int j = 0; j < hint_nlen && j < 7; ++j) hint_key |= (unsigned long long)__ldg(R.d_names + o0 + j) << (8 * j);
+        __syncwarp();
+        if (lane < 4) {
+            unsigned long long kk = 0ull;
+            for (int j = 8 * lane; j < hint_nlen && j < 8 * lane + 8; ++j) kk |= (unsigned long long)__ldg(R.d_names + o0 + j) << (8 * (j & 7));
+            S.key[lane] = kk;
+        }
+        __syncwarp();
     };
     set_hint(0);
     unsigned long long slot_cur = 0ull;                           // next free reserved record slot
@@ -420,9 +428,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         // without the field-start map, the line list or the per-line parse.  Lanes test the lines that start inside their
         // own 128 bytes (usually one, so one round).
         bool quiet_chunk = false;
-        if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 7) {
+        if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 31) {
             uint32_t w0 = lsv.x, w1 = lsv.y, w2 = lsv.z, w3 = lsv.w;
-            const unsigned long long name_mask = (1ull << (8 * hint_nlen)) - 1ull;
             bool ok = true;
             while (__any_sync(0xffffffffu, (w0 | w1 | w2 | w3) != 0u)) {
                 if ((w0 | w1 | w2 | w3) != 0u) {
@@ -431,9 +438,16 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     const int s0 = 32 * (4 * lane + jw) + __ffs(m) - 1;
                     const uint32_t cl = m & (m - 1u);
                     if (jw == 0) w0 = cl; else if (jw == 1) w1 = cl; else if (jw == 2) w2 = cl; else w3 = cl;
-                    const unsigned long long k8 = load8(text, s0);
+                    // the name in 8-byte pieces, then the whitespace byte that must follow it
+                    bool name_ok = true;
+                    for (int j = 0; 8 * j <= hint_nlen; ++j) {
+                        const unsigned long long v = load8(text, s0 + 8 * j), kk = S.key[j];
+                        const int rem = hint_nlen - 8 * j;             // name bytes from this piece on
+                        if (rem >= 8) name_ok = name_ok && v == kk;
+                        else name_ok = name_ok && (v & ((1ull << (8 * rem)) - 1ull)) == kk && ((v >> (8 * rem)) & 0xFFull) <= 0x20ull;
+                    }
                     ok = false;
-                    if ((k8 & name_mask) == hint_key && ((k8 >> (8 * hint_nlen)) & 0xFFull) <= 0x20ull) {
+                    if (name_ok) {
                         int p0 = 0;
                         if (parse_pos8(load8(text, s0 + hint_nlen + 1), p0) == 1) {
                             ok = true;

@@ -428,7 +428,7 @@ def test_scan_runs_and_quiet_chunks_match_oracle(variant, run_len, cuda_lib, ora
     line of a window is several chunks away and when line layouts are mutated."""
     from mcaller_b200 import _lib, engine, models, read_qual, synth
     from mcaller_b200.refindex import ReferenceIndex
-    spec = synth.SynthSpec(seed=211, contigs=[("ctgA", 14000), ("c", 9000)], n_reads=50, len_min=300, len_max=900)
+    spec = synth.SynthSpec(seed=211, contigs=[("NC_000913.3", 14000), ("c", 9000)], n_reads=50, len_min=300, len_max=900)   # 11- and 1-byte names
     tsv, fasta, fastq, quals = synth.generate(spec)
     quals = {k.split("_")[0]: v for k, v in quals.items()}
     if variant == "junk":
@@ -473,7 +473,8 @@ def test_window_units_in_other_site_regimes(mode, tmp_path, cuda_lib, oracle):
     first-'M' pre-pass finds nothing and every unit is a no-op)."""
     from mcaller_b200 import engine, models, read_qual, synth
     from mcaller_b200.refindex import ReferenceIndex
-    spec = synth.SynthSpec(seed=808, contigs=[("one", 15000), ("two", 11000)], n_reads=120, len_min=300, len_max=1200)
+    one, two = "contig_with_a_31_character_name", "a_contig_name_of_32_characters__"      # longest name the quick look handles, and one more
+    spec = synth.SynthSpec(seed=808, contigs=[(one, 15000), (two, 11000)], n_reads=120, len_min=300, len_max=1200)
     tsv, fasta, fastq, quals = synth.generate(spec)
     quals = {k.split("_")[0]: v for k, v in quals.items()}
     seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
@@ -486,17 +487,22 @@ def test_window_units_in_other_site_regimes(mode, tmp_path, cuda_lib, oracle):
         rnd = random.Random(5)
         pos_path = os.path.join(str(tmp_path), "pos.txt")
         with open(pos_path, "w") as fh:
-            for p, c in enumerate(seqs["one"]):
-                if c == "A" and 20 < p < len(seqs["one"]) - 20 and rnd.random() < 0.03:
-                    fh.write("one\t%d\t+\tm6A\n" % p)
-            for p, c in enumerate(seqs["two"]):
-                if c == "T" and 20 < p < len(seqs["two"]) - 20 and rnd.random() < 0.03:
-                    fh.write("two\t%d\t-\tm6A\n" % p)
+            for p, c in enumerate(seqs[one]):
+                if c == "A" and 20 < p < len(seqs[one]) - 20 and rnd.random() < 0.03:
+                    fh.write("%s\t%d\t+\tm6A\n" % (one, p))
+            for p, c in enumerate(seqs[two]):
+                if c == "T" and 20 < p < len(seqs[two]) - 20 and rnd.random() < 0.03:
+                    fh.write("%s\t%d\t-\tm6A\n" % (two, p))
         kw_ref, kw_orc, s = dict(positions_file=pos_path), dict(positions=pos_path), 1
     ref = ReferenceIndex(seqs, "A", k=6, **kw_ref)
     want = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=s, model=model, base="A", cap=400000, **kw_orc)
     eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=s, two_models=True)
-    res = eng.run_chunk(eng.upload(tsv), len(tsv))
+    from mcaller_b200 import _lib
+    before = _lib.lib().mc_scan_set_run_len(16)          # small input: force runs so that chunks are passed over
+    try:
+        res = eng.run_chunk(eng.upload(tsv), len(tsv))
+    finally:
+        _lib.lib().mc_scan_set_run_len(before)
     calls = res.calls()
     mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
     assert len(mine) == len(want["calls"]) > 100
