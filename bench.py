@@ -333,8 +333,10 @@ def main():
         streamer = stream_mod.HostStreamer(engine, chunk_bytes=min(args.e2e_chunk, max(end, 1 << 20)))
         cuts = stream_mod.plan_chunks(offs_all[:n_e], end, streamer.chunk_bytes)
         engine.reset_histogram()
-        streamer.run(host, cuts)                                   # warm-up (buffer growth, pinned result buffer)
+        sink = stream_mod.TextSink(W["ref"], 6, "A")             # rows rendered as .diffs text on host threads, one chunk behind
+        streamer.run(host, cuts, sink=sink)                        # warm-up (buffer growth, pinned result buffers)
         streamer.h2d_bytes = streamer.d2h_bytes = 0
+        sink.text_bytes = 0
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -343,7 +345,7 @@ def main():
         e_steps = max(1, min(args.steps, 3))
         for _ in range(e_steps):
             engine.reset_histogram()
-            tot = streamer.run(host, cuts)
+            tot = streamer.run(host, cuts, sink=sink)
             e_calls += tot["calls"]
             if use_dist:
                 mdist.allreduce_histogram(engine.d_depth, engine.d_meth, engine.d_first)
@@ -357,8 +359,9 @@ def main():
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             e_calls = int(c[0])
         e2e = {"value": e_calls / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // e_steps,
-               "d2h_bytes_per_step": streamer.d2h_bytes // e_steps,
-               "sample": "%d reads (%.2f GB TSV) per GPU streamed from pinned host memory in %d chunks, rows copied back" % (n_e, end / 1e9, len(cuts))}
+               "d2h_bytes_per_step": streamer.d2h_bytes // e_steps, "diffs_text_bytes_per_step": sink.text_bytes // e_steps,
+               "sample": "%d reads (%.2f GB TSV) per GPU streamed from pinned host memory in %d chunks, rows copied back and "
+                         "rendered as .diffs text by the native writer" % (n_e, end / 1e9, len(cuts))}
         del host
 
     # ------------------------------------------------------------------------------------------------ CPU baseline

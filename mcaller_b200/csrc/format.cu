@@ -1,10 +1,14 @@
-// Host-side writer of the `.diffs.<k>` rows (reference extract_contexts.py:216 + writefi :83-86), native so that runs with
-// millions of calls are not bound by Python string formatting.  Floats are printed like str(np.float64) / repr(float):
+// Host-side writer of the `.diffs.<k>` rows (reference extract_contexts.py:216 + writefi :83-86), native and multi-threaded
+// (row ranges formatted by host threads into private buffers, then concatenated in row order) so that runs with millions
+// of calls are not bound by string formatting.  Floats are printed like str(np.float64) / repr(float):
 // the shortest digit string that round-trips (std::to_chars), fixed notation for 1e-4 <= |x| < 1e16, else scientific
 // with a two-digit exponent; empty columns print the integer 0; the probability is np.round(p, 2) (rint(p*100)/100).
 #include <charconv>
 #include <cmath>
 #include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -68,46 +72,112 @@ char comp(char c) {
 
 }  // namespace
 
-extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const char *const *contig_names,
-                                  const char *const *marked_fwd, const char *const *marked_rev, const int64_t *contig_len,
-                                  int32_t n_contigs, int32_t k, const char *base_label, const char *mod_label, int32_t with_prob,
-                                  char *out, int64_t out_cap) {
-    if (!h_calls || !h_text || !contig_names || !marked_fwd || !marked_rev || !contig_len || !out || k < 1 || k > MC_MAXK) {
-        mc_set_error("mc_format_rows: bad argument");
-        return MC_EINVAL;
-    }
-    Out o{out, out + out_cap};
-    for (int64_t i = 0; i < n_calls; ++i) {
-        const mc_call &c = h_calls[i];
+namespace {
+
+struct FormatArgs {
+    const mc_call *h_calls;
+    const uint8_t *h_text;
+    const char *const *contig_names, *const *marked_fwd, *const *marked_rev;
+    const int64_t *contig_len;
+    int32_t n_contigs, k, with_prob;
+    const char *base_label, *mod_label;
+};
+
+// rows [lo, hi) appended to `dst`; returns 0 or a negative error code and leaves the failing row / flags in err_*
+int64_t format_range(const FormatArgs &A, int64_t lo, int64_t hi, std::string &dst, int64_t &err_row, int &err_flags) {
+    char line[4096];
+    for (int64_t i = lo; i < hi; ++i) {
+        const mc_call &c = A.h_calls[i];
         if (c.kind != MC_CALL || c.close_rec == 0xFFFFFFFFu) continue;
-        if (c.err) { mc_set_error("row %lld (position %d) carries error flags 0x%x", (long long)i, c.mpos, (unsigned)c.err); return -100 - (int64_t)c.err; }
-        if (c.chrom_contig >= n_contigs || c.win_contig >= n_contigs) { mc_set_error("mc_format_rows: contig index out of range"); return MC_EINVAL; }
-        o.put(contig_names[c.chrom_contig]);
-        o.put('\t');
-        o.put(reinterpret_cast<const char *>(h_text) + c.read_off, (size_t)c.read_len);
+        if (c.err) { err_row = i; err_flags = c.err; return -100 - (int64_t)c.err; }
+        if (c.chrom_contig >= A.n_contigs || c.win_contig >= A.n_contigs) { err_row = i; err_flags = -1; return MC_EINVAL; }
+        const char *src = c.rev ? A.marked_rev[c.win_contig] : A.marked_fwd[c.win_contig];
+        const int64_t a = (int64_t)c.mpos - A.k + 1, b = (int64_t)c.mpos + A.k;
+        if (a < 0 || b > A.contig_len[c.win_contig]) { err_row = i; err_flags = -2; return MC_EINVAL; }
+        const size_t name_len = strlen(A.contig_names[c.chrom_contig]);
+        if (name_len + (size_t)c.read_len + 1024 > sizeof(line)) {          // unusually long names: straight into the string
+            dst.append(A.contig_names[c.chrom_contig], name_len);
+            dst.push_back('\t');
+            dst.append(reinterpret_cast<const char *>(A.h_text) + c.read_off, (size_t)c.read_len);
+        }
+        Out o{line, line + sizeof(line)};
+        if (name_len + (size_t)c.read_len + 1024 <= sizeof(line)) {
+            o.put(A.contig_names[c.chrom_contig], name_len);
+            o.put('\t');
+            o.put(reinterpret_cast<const char *>(A.h_text) + c.read_off, (size_t)c.read_len);
+        }
         o.put('\t');
         put_int(o, c.mpos);
         o.put('\t');
         // context = revcomp(last_ref[mpos-k+1 : mpos+k], last_rev)   (extract_contexts.py:194)
-        const char *src = c.rev ? marked_rev[c.win_contig] : marked_fwd[c.win_contig];
-        const int64_t a = (int64_t)c.mpos - k + 1, b = (int64_t)c.mpos + k;
-        if (a < 0 || b > contig_len[c.win_contig]) { mc_set_error("mc_format_rows: context out of range"); return MC_EINVAL; }
         for (int64_t j = 0; j < b - a; ++j) o.put(c.rev ? comp(src[b - 1 - j]) : src[a + j]);
         o.put('\t');
-        for (int j = 0; j <= k; ++j) {
+        for (int j = 0; j <= A.k; ++j) {
             if (j) o.put(',');
-            if (j < k && ((c.empty_mask >> j) & 1u)) o.put('0'); else put_repr(o, c.feat[j]);
+            if (j < A.k && ((c.empty_mask >> j) & 1u)) o.put('0'); else put_repr(o, c.feat[j]);
         }
         o.put('\t');
         o.put(c.rev ? '-' : '+');
-        if (with_prob) {
+        if (A.with_prob) {
             o.put('\t');
-            o.put(c.prob >= 0.5 ? mod_label : base_label);
+            o.put(c.prob >= 0.5 ? A.mod_label : A.base_label);
             o.put('\t');
             put_repr(o, std::rint(c.prob * 100.0) / 100.0);
         }
         o.put('\n');
-        if (!o.ok) { mc_set_error("mc_format_rows: output buffer too small"); return MC_ECAPACITY; }
+        if (!o.ok) { err_row = i; err_flags = -3; return MC_ECAPACITY; }       // cannot happen: labels are short
+        dst.append(line, (size_t)(o.p - line));
     }
-    return (int64_t)(o.p - out);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const char *const *contig_names,
+                                  const char *const *marked_fwd, const char *const *marked_rev, const int64_t *contig_len,
+                                  int32_t n_contigs, int32_t k, const char *base_label, const char *mod_label, int32_t with_prob,
+                                  char *out, int64_t out_cap) {
+    if (!h_calls || !h_text || !contig_names || !marked_fwd || !marked_rev || !contig_len || !out || k < 1 || k > MC_MAXK ||
+        !base_label || !mod_label || strlen(base_label) > 256 || strlen(mod_label) > 256) {
+        mc_set_error("mc_format_rows: bad argument");
+        return MC_EINVAL;
+    }
+    const FormatArgs A{h_calls, h_text, contig_names, marked_fwd, marked_rev, contig_len, n_contigs, k, with_prob, base_label, mod_label};
+    // one host thread per ~2k rows (a thread costs ~20 us to start, 2k rows ~2 ms to render), at most the hardware concurrency
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    int nt = (int)((n_calls + 2047) / 2048);
+    if (nt > (int)hw) nt = (int)hw;
+    if (nt < 1) nt = 1;
+    std::vector<std::string> parts((size_t)nt);
+    std::vector<int64_t> rc((size_t)nt, 0), erow((size_t)nt, -1);
+    std::vector<int> eflags((size_t)nt, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n_calls * t / nt, hi = n_calls * (t + 1) / nt;
+        parts[(size_t)t].reserve((size_t)(hi - lo) * 200);
+        rc[(size_t)t] = format_range(A, lo, hi, parts[(size_t)t], erow[(size_t)t], eflags[(size_t)t]);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < nt; ++t) {                                  // the first failing row in row order decides
+        if (rc[(size_t)t] == 0) continue;
+        if (eflags[(size_t)t] > 0)
+            mc_set_error("row %lld (position %d) carries error flags 0x%x", (long long)erow[(size_t)t], h_calls[erow[(size_t)t]].mpos,
+                         (unsigned)eflags[(size_t)t]);
+        else if (eflags[(size_t)t] == -1) mc_set_error("mc_format_rows: contig index out of range");
+        else if (eflags[(size_t)t] == -2) mc_set_error("mc_format_rows: context out of range");
+        else mc_set_error("mc_format_rows: row too long");
+        return rc[(size_t)t];
+    }
+    int64_t total = 0;
+    for (auto &sp : parts) total += (int64_t)sp.size();
+    if (total > out_cap) { mc_set_error("mc_format_rows: output buffer too small"); return MC_ECAPACITY; }
+    char *p = out;
+    for (auto &sp : parts) { memcpy(p, sp.data(), sp.size()); p += sp.size(); }
+    return total;
 }

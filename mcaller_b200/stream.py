@@ -26,6 +26,43 @@ def plan_chunks(read_offsets, total_bytes, chunk_bytes):
     return cuts
 
 
+class TextSink(object):
+    """Renders the rows of a chunk as `.diffs.<k>` text with the native writer (mc_format_rows, host threads) straight from
+    the pinned row buffer and the host copy of the TSV (read names are cut from it).  Used by HostStreamer one chunk behind
+    the GPU, so the formatting overlaps the next chunk's copy and kernels."""
+
+    def __init__(self, refindex, k, base="A", with_prob=True, keep=False):
+        import ctypes as C
+        names = refindex.names
+        n = len(names)
+        self._keep = [nm.encode() for nm in names] + [refindex.marked[nm][0].encode() for nm in names] + \
+                     [refindex.marked[nm][1].encode() for nm in names]
+        self.names, self.fwd, self.rev = (C.c_char_p * n)(*self._keep[:n]), (C.c_char_p * n)(*self._keep[n:2 * n]), (C.c_char_p * n)(*self._keep[2 * n:])
+        self.lens = (C.c_int64 * n)(*[len(refindex.marked[nm][0]) for nm in names])
+        self.n, self.k, self.with_prob = n, int(k), 1 if with_prob else 0
+        self.base, self.mod = base.encode(), (b"m6A" if base == "A" else b"m" + base.encode())
+        self.out = None
+        self.text_bytes = 0
+        self.kept = [] if keep else None      # rendered text per chunk (tests); rows still open at a chunk end are not in it:
+        #                                       extract_features carries those to the next chunk (_RowFormatter.pending)
+
+    def render(self, h_calls, n_calls, host_text_ptr, max_read_len=256):
+        """h_calls: pinned uint8 tensor holding n_calls rows; host_text_ptr: address of the chunk's first byte in host memory."""
+        import ctypes as C
+        from . import _lib
+        cap = n_calls * (96 + 26 * (self.k + 1) + max_read_len) + 4096
+        if self.out is None or len(self.out) < cap:
+            self.out = C.create_string_buffer(int(cap * 1.25))
+        r = _lib.lib().mc_format_rows(C.c_void_p(h_calls.data_ptr()), n_calls, C.c_void_p(host_text_ptr), self.names, self.fwd, self.rev,
+                                      self.lens, self.n, self.k, self.base, self.mod, self.with_prob, self.out, len(self.out))
+        if r < 0:
+            _lib.check(int(r) if r > -100 else -1)
+        self.text_bytes += int(r)
+        if self.kept is not None:
+            self.kept.append(self.out.raw[:r])
+        return int(r)
+
+
 class HostStreamer(object):
     def __init__(self, engine, chunk_bytes=1 << 30):
         self.eng = engine
@@ -36,7 +73,8 @@ class HostStreamer(object):
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
-        self.h_calls = None
+        self.h_calls = [None, None]           # pinned row buffers, alternating so one can be rendered while the other fills
+        self.calls_done = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -51,10 +89,18 @@ class HostStreamer(object):
             self.ready[slot].record(self.copy_stream)
         self.h2d_bytes += n
 
-    def run(self, host_buf, cuts, fetch_calls=True):
+    def run(self, host_buf, cuts, fetch_calls=True, sink=None):
         """host_buf: pinned uint8 CPU tensor; cuts: chunk end offsets from plan_chunks.  Returns dict of totals; rows of
-        every chunk are copied to pinned host memory when fetch_calls (the D2H leg of the end-to-end path)."""
+        every chunk are copied to pinned host memory when fetch_calls (the D2H leg of the end-to-end path) and, with a
+        TextSink, rendered as `.diffs` text one chunk behind the GPU."""
         eng = self.eng
+        fetch_calls = fetch_calls or sink is not None
+        late = None                                   # (slot, n_calls, chunk start) of the chunk whose rows are not rendered yet
+
+        def render(item):
+            slot_c, n_c, start = item
+            self.calls_done[slot_c].synchronize()
+            sink.render(self.h_calls[slot_c], n_c, host_buf.data_ptr() + start)
         cur = torch.cuda.current_stream(self.dev)
         for e in self.free:
             e.record(cur)
@@ -73,10 +119,16 @@ class HostStreamer(object):
             st = eng.count_rows(res)
             if fetch_calls and res.n_calls:
                 nb = res.n_calls * CALL_DTYPE.itemsize
-                if self.h_calls is None or self.h_calls.numel() < nb:
-                    self.h_calls = torch.empty(int(nb * 1.5) + 4096, dtype=torch.uint8, pin_memory=True)
-                self.h_calls[:nb].copy_(res.calls_dev[:nb], non_blocking=True)
+                sc = i & 1
+                if self.h_calls[sc] is None or self.h_calls[sc].numel() < nb:
+                    self.h_calls[sc] = torch.empty(int(nb * 1.5) + 4096, dtype=torch.uint8, pin_memory=True)
+                self.h_calls[sc][:nb].copy_(res.calls_dev[:nb], non_blocking=True)
+                self.calls_done[sc].record(cur)
                 self.d2h_bytes += nb
+                if sink is not None:
+                    if late is not None:
+                        render(late)                  # the previous chunk's rows, while this chunk's copy-back is in flight
+                    late = (sc, res.n_calls, bounds[i])
             self.free[slot].record(cur)
             # a window left open by the previous chunk closes on this chunk's first kept line (any kept line does)
             if (pending_prev or pending_tms_prev) and res.counters["kept"] > 0:
@@ -91,6 +143,8 @@ class HostStreamer(object):
             tot["lines"] += res.counters["lines"]
             tot["rows"] += res.n_calls
         cur.synchronize()
+        if sink is not None and late is not None:
+            render(late)
         tot["calls"] += tot["pending_resolved"]
         tot["dropped_at_eof"] = pending_prev
         return tot
