@@ -240,6 +240,21 @@ def test_native_row_writer_matches_python_repr():
         assert f[:4] == ["c1", "rd", "10", "M"] and f[5] == ("-" if c["rev"] else "+")
         assert f[4] == want_feat + ",11.5"
         assert f[6] == ("m6A" if c["prob"] >= 0.5 else "A") and f[7] == str(np.round(np.float64(c["prob"]), 2))
+    # the 5 022 rows above are rendered by several host threads (one per ~2k rows); slices of 1 000 rows are rendered by one
+    # thread each and must concatenate to the same bytes
+    whole = out.raw[:r]
+    parts = []
+    for a in range(0, n, 1000):
+        sl = np.ascontiguousarray(calls[a:a + 1000])
+        r2 = lib.mc_format_rows(sl.ctypes.data_as(C.c_void_p), len(sl), text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+        assert r2 >= 0
+        parts.append(out.raw[:r2])
+    assert b"".join(parts) == whole
+    # an error flag on a row is reported with the row, whichever thread meets it
+    bad = calls.copy()
+    bad["err"][4321] = 4
+    r3 = lib.mc_format_rows(bad.ctypes.data_as(C.c_void_p), n, text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+    assert r3 == -104 and b"4321" in lib.mc_last_error()
     # k = 3: context is cut from the strand's marked copy and reverse-complemented for '-' rows
     calls2 = np.zeros(2, dtype=_lib.CALL_DTYPE)
     calls2["mpos"], calls2["read_len"], calls2["rev"] = 10, 2, [0, 1]
