@@ -269,7 +269,10 @@ class _RowFormatter(object):
         L = _lib.lib()
         cap = int(closed0.sum()) * (96 + 26 * (self.k + 1) + int(calls["read_len"].max())) + 4096
         out = C.create_string_buffer(cap)
-        tbuf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
+        if isinstance(text, np.ndarray):             # pinned host buffer of the streaming path: no copy
+            tbuf = C.c_void_p(text.ctypes.data)
+        else:
+            tbuf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
         calls_c = np.ascontiguousarray(calls)
         r = L.mc_format_rows(calls_c.ctypes.data_as(C.c_void_p), n, tbuf, a["names"], a["fwd"], a["rev"], a["lens"], a["n"], self.k,
                              self.base.encode(), self.mod_label.encode(), 1 if self.have_model else 0, out, cap)
@@ -373,6 +376,16 @@ def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thr
         pos = lo
         carry = b""
         open(tsv_output, "a").close()
+        if not train:
+            # inference: pipelined path (reader thread -> pinned buffers -> H2D on a side stream -> kernels -> native writer)
+            from . import stream as _stream
+            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before)
+            with open(tsv_output, "ab") as outfi:                  # append, like writefi (:83-86)
+                for res, text, n in fs.chunks(tsv_input, lo, hi):
+                    _raise_on_counters(res)
+                    fk = _first_kept_contig(eng, res, qual_thresh) if fmt.pending is not None else None
+                    outfi.write(fmt.consume_bytes(res.calls(), text, fk, res.n_segments))
+            pos, carry = hi, b""
         while pos < hi or carry:
             want = min(CHUNK_BYTES, hi - pos)
             fh.seek(pos)

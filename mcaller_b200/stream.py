@@ -63,6 +63,153 @@ class TextSink(object):
         return int(r)
 
 
+class FileStreamer(object):
+    """A byte range of an eventalign file -> read-aligned chunks through the Engine, pipelined: a reader thread fills a ring
+    of pinned host buffers with parallel preads (cutting at the last read boundary and carrying the incomplete read into
+    the next buffer), the H2D copy of chunk i+1 runs on a side stream while chunk i is in the kernels, and the caller
+    renders chunk i's rows while the next copy is in flight.  `boundary_before(bytes) -> offset` finds the last read
+    boundary of a buffer (extract_contexts.read_boundary_before)."""
+
+    def __init__(self, engine, chunk_bytes, boundary_before, slots=3, readers=4):
+        self.eng, self.dev = engine, engine.device
+        self.chunk_bytes = int(chunk_bytes)
+        self.boundary_before = boundary_before
+        self.n_slots, self.readers = int(slots), int(readers)
+        self.pin = [None] * self.n_slots          # pinned uint8 tensors, grown on demand
+        self.dbuf = [None, None]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes = 0
+
+    def _ensure_pin(self, slot, nbytes, keep=0):
+        t = self.pin[slot]
+        if t is None or t.numel() < nbytes:
+            nt = torch.empty(int(nbytes * 1.25) + (1 << 16), dtype=torch.uint8, pin_memory=True)
+            if t is not None and keep:
+                nt[:keep].copy_(t[:keep])
+            self.pin[slot] = nt
+        return self.pin[slot]
+
+    def _last_boundary(self, arr, total):
+        """Offset of the last read boundary inside arr[:total] (0: none).  Only a tail is searched (and copied), starting at
+        a line start so that the first line seen is complete; the tail grows until a boundary shows up."""
+        span = 1 << 22
+        while True:
+            a = max(0, total - span)
+            if a > 0:
+                nl = np.flatnonzero(arr[a:min(total, a + (1 << 20))] == 10)
+                if len(nl) == 0:
+                    span *= 4
+                    if span > 4 * total:
+                        return 0
+                    continue
+                a += int(nl[0]) + 1
+            tail = arr[a:total].tobytes()
+            cut = self.boundary_before(tail, len(tail))
+            if cut > 0:
+                return a + cut
+            if a == 0:
+                return 0
+            span *= 4
+
+    def _producer(self, path, lo, hi, q_free, q_ready):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            fd = os.open(path, os.O_RDONLY)
+            try:
+                with ThreadPoolExecutor(max_workers=self.readers) as pool:
+                    def read_into(mv, off):
+                        done = 0
+                        while done < len(mv):
+                            got = os.preadv(fd, [mv[done:]], off + done)
+                            if got <= 0:
+                                raise IOError("short read at offset %d" % (off + done))
+                            done += got
+
+                    pos, carry, slot = lo, 0, q_free.get()
+                    while pos < hi or carry:
+                        want = min(self.chunk_bytes, hi - pos)
+                        arr = self._ensure_pin(slot, carry + want, keep=carry).numpy()
+                        if want:
+                            step = max(1 << 24, (want + self.readers - 1) // self.readers)
+                            futs = [pool.submit(read_into, memoryview(arr[carry + a:carry + min(want, a + step)]), pos + a)
+                                    for a in range(0, want, step)]
+                            for f in futs:
+                                f.result()
+                        pos += want
+                        total = carry + want
+                        if pos < hi:
+                            cut = self._last_boundary(arr, total)
+                            if cut == 0:                     # a single read larger than the chunk: keep reading into this slot
+                                carry = total
+                                continue
+                            nslot = q_free.get()
+                            narr = self._ensure_pin(nslot, total - cut + self.chunk_bytes).numpy()
+                            narr[:total - cut] = arr[cut:total]
+                            q_ready.put((slot, cut))
+                            slot, carry = nslot, total - cut
+                        else:
+                            if total:
+                                q_ready.put((slot, total))
+                            carry = 0
+            finally:
+                os.close(fd)
+            q_ready.put(None)
+        except BaseException as e:                          # surfaces in the consumer
+            q_ready.put(e)
+
+    def _enqueue_copy(self, dslot, slot, n):
+        cap = self.eng.padded_capacity(n)
+        if self.dbuf[dslot] is None or self.dbuf[dslot].numel() < cap:
+            self.free[dslot].synchronize()
+            self.dbuf[dslot] = torch.empty(int(cap * 1.1) + 4096, dtype=torch.uint8, device=self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[dslot])
+            self.dbuf[dslot][:n].copy_(self.pin[slot][:n], non_blocking=True)
+            self.dbuf[dslot][n:n + MC_TEXT_PAD + 16].fill_(10)
+            self.ready[dslot].record(self.copy_stream)
+        self.h2d_bytes += n
+
+    def chunks(self, path, lo, hi):
+        """Yields (ChunkResult, host text of the chunk as a uint8 numpy view, nbytes) in file order.  The view and the
+        result's device buffers are valid until the next item is requested."""
+        import queue
+        import threading
+        q_free, q_ready = queue.Queue(), queue.Queue()
+        for sl in range(self.n_slots):
+            q_free.put(sl)
+        th = threading.Thread(target=self._producer, args=(path, lo, hi, q_free, q_ready), daemon=True)
+        th.start()
+
+        def take():
+            item = q_ready.get()
+            if isinstance(item, BaseException):
+                raise item
+            return item
+        cur = torch.cuda.current_stream(self.dev)
+        for e in self.free:
+            e.record(cur)
+        item = take()
+        if item is not None:
+            self._enqueue_copy(0, item[0], item[1])
+        i = 0
+        while item is not None:
+            nxt = take()
+            if nxt is not None:
+                self._enqueue_copy((i + 1) & 1, nxt[0], nxt[1])
+            slot, n = item
+            cur.wait_event(self.ready[i & 1])
+            res = self.eng.run_chunk(self.dbuf[i & 1], n)
+            yield res, self.pin[slot].numpy()[:n], n
+            self.free[i & 1].record(cur)
+            q_free.put(slot)
+            item = nxt
+            i += 1
+        th.join()
+
+
 class HostStreamer(object):
     def __init__(self, engine, chunk_bytes=1 << 30):
         self.eng = engine
