@@ -18,6 +18,7 @@ from .refmark import comp, revcomp, strand  # noqa: F401  (re-exported, referenc
 base_comps = {"A": "T", "C": "G", "T": "A", "G": "C", "N": "N", "M": "M"}
 
 CHUNK_BYTES = int(os.environ.get("MCALLER_B200_CHUNK_BYTES", str(1 << 30)))
+READ_THREADS = int(os.environ.get("MCALLER_B200_READ_THREADS", str(min(16, os.cpu_count() or 1))))   # parallel preads of the file reader
 
 
 class ReferenceAbort(RuntimeError):
@@ -379,7 +380,7 @@ def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thr
         if not train:
             # inference: pipelined path (reader thread -> pinned buffers -> H2D on a side stream -> kernels -> native writer)
             from . import stream as _stream
-            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before)
+            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before, readers=READ_THREADS)
             with open(tsv_output, "ab") as outfi:                  # append, like writefi (:83-86)
                 for res, text, n in fs.chunks(tsv_input, lo, hi):
                     _raise_on_counters(res)
