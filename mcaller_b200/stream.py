@@ -63,6 +63,27 @@ class TextSink(object):
         return int(r)
 
 
+def last_boundary(arr, total, boundary_before, span=1 << 22):
+    """Offset of the last read boundary inside arr[:total] (uint8 numpy array; 0: none) -- what
+    boundary_before(bytes(arr[:total])) returns, but only a tail is searched (and copied).  The tail starts at a line start,
+    so the first line seen is complete, and grows until it holds a boundary."""
+    while True:
+        a = max(0, total - span)
+        if a > 0:
+            nl = np.flatnonzero(arr[a:min(total, a + (1 << 20))] == 10)
+            if len(nl) == 0:
+                span *= 4
+                continue
+            a += int(nl[0]) + 1
+        tail = arr[a:total].tobytes()
+        cut = boundary_before(tail, len(tail))
+        if cut > 0:
+            return a + cut
+        if a == 0:
+            return 0
+        span *= 4
+
+
 class FileStreamer(object):
     """A byte range of an eventalign file -> read-aligned chunks through the Engine, pipelined: a reader thread fills a ring
     of pinned host buffers with parallel preads (cutting at the last read boundary and carrying the incomplete read into
@@ -92,26 +113,7 @@ class FileStreamer(object):
         return self.pin[slot]
 
     def _last_boundary(self, arr, total):
-        """Offset of the last read boundary inside arr[:total] (0: none).  Only a tail is searched (and copied), starting at
-        a line start so that the first line seen is complete; the tail grows until a boundary shows up."""
-        span = 1 << 22
-        while True:
-            a = max(0, total - span)
-            if a > 0:
-                nl = np.flatnonzero(arr[a:min(total, a + (1 << 20))] == 10)
-                if len(nl) == 0:
-                    span *= 4
-                    if span > 4 * total:
-                        return 0
-                    continue
-                a += int(nl[0]) + 1
-            tail = arr[a:total].tobytes()
-            cut = self.boundary_before(tail, len(tail))
-            if cut > 0:
-                return a + cut
-            if a == 0:
-                return 0
-            span *= 4
+        return last_boundary(arr, total, self.boundary_before)
 
     def _producer(self, path, lo, hi, q_free, q_ready):
         import os

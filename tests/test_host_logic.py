@@ -262,3 +262,29 @@ def test_native_row_writer_matches_python_repr():
     rows = out.raw[:r].decode().split("\n")[:-1]
     assert rows[0].split("\t")[3] == fwd[8:13].decode() and rows[1].split("\t")[3] == refmark.revcomp(rev[8:13].decode())
     assert len(rows[0].split("\t")) == 6
+
+
+def test_tail_search_of_last_read_boundary_equals_full_search():
+    """stream.last_boundary (the file reader's cut point, searched in a growing tail of the pinned buffer) returns what
+    extract_contexts.read_boundary_before gives on the whole buffer: random read lengths incl. reads longer than the
+    first tail, malformed lines, a partial last line, buffers without any boundary."""
+    from mcaller_b200 import extract_contexts as ec, stream
+    rnd = random.Random(11)
+
+    def line(read, pos):
+        return ("ctg\t%d\tACGTAC\t%s\tt\t%d\t90.12\t1.5\t0.003\tACGTAC\t89.9\t1.2\t0.1\n" % (pos, read, pos)).encode()
+
+    for trial in range(40):
+        parts, n_reads = [], rnd.randint(1, 6)
+        for r in range(n_reads):
+            for j in range(rnd.choice([1, 3, 40, 400, 3000])):
+                parts.append(line("read%d_%d" % (trial, r), j))
+                if rnd.random() < 0.02:
+                    parts.append(rnd.choice([b"\n", b"x y z\n", b"ctg\t5\tshort\n"]))
+        buf = b"".join(parts)
+        if rnd.random() < 0.5:
+            buf = buf[:len(buf) - rnd.randint(1, 60)]                  # partial last line
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        want = ec.read_boundary_before(buf, len(buf))
+        for span in (64, 1000, 50000, 1 << 22):
+            assert stream.last_boundary(arr, len(buf), ec.read_boundary_before, span=span) == want, (trial, span)
