@@ -181,7 +181,7 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
  * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
  * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
- * d_counters (MC_C_COUNT uint64) must be zeroed by the caller.
+ * d_counters (MC_C_COUNT uint64) must be zeroed by the caller; d_text must be 16-byte and d_tile_tab 8-byte aligned.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,
             mc_record *d_rec, int64_t rec_cap, uint32_t *d_tile_tab /* [2*n_tiles] */,
