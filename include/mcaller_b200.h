@@ -17,6 +17,9 @@
  *     them as torch tensors); the library never allocates device memory and keeps no state;
  *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*); the only host
  *     synchronisation is mc_read_u64();
+ *   - item counts produced by one stage and consumed by the next (records, read segments, rows) stay in device memory:
+ *     consumers take a device pointer to the count (`d_n_*`) plus a host-side capacity that only sizes the launch, so a
+ *     chunk runs from mc_scan to mc_hist_accumulate without a host round trip;
  *   - no torch / C++ types cross this boundary.
  */
 #ifndef MCALLER_B200_H
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 /* text chunks: one warp tokenises MC_TILE_BYTES of TSV; the caller must keep MC_TEXT_PAD readable bytes,
  * all '\n', after the last text byte (so a final line without newline and tile look-ahead are safe). */
@@ -79,7 +82,8 @@ typedef struct mc_record {
 #define MC_RF_CAND 2u      /* k-mer window touches a target on either strand */
 #define MC_RF_BADNUM 4u    /* event/model mean not a plain decimal (<= 18 digits) */
 #define MC_RF_BADIDX 8u    /* event index not a plain integer */
-#define MC_RF_RAW 16u      /* stage-1 form: event_idx/diff still hold column offsets; cleared by mc_order_records */
+#define MC_RF_RAW 16u      /* stage-1 form of a line mc_scan could not finish from its staged bytes (unusual number shapes, very
+                              long lines): event_idx / diff / name span are filled in by mc_order_records, which clears the flag */
 #define MC_RF_NEWREAD 32u  /* read name differs from the previous record's (valid when MC_RF_SEGKNOWN is set) */
 #define MC_RF_SEGKNOWN 64u /* mc_order_records compared the read name with the previous record's */
 
@@ -122,7 +126,7 @@ typedef struct mc_call {
     uint32_t pad2;
 } mc_call;                 /* 128 bytes */
 
-enum { MC_CALL = 0, MC_TOO_MANY_SKIPS = 1, MC_MULTI_M = 2 };
+enum { MC_CALL = 0, MC_TOO_MANY_SKIPS = 1, MC_MULTI_M = 2, MC_NONE = 3 /* empty slot: every consumer skips it */ };
 #define MC_CE_CONTEXT 1u   /* window within k of a contig end (reference: IndexError / sys.exit, :195, :224) */
 #define MC_CE_MODELKEY 2u  /* base after the target not in ACGTM (reference: KeyError -> sys.exit, :218-223) */
 #define MC_CE_BADNUM 4u    /* a fed line had an unsupported numeric field */
@@ -161,7 +165,8 @@ typedef struct mc_qual_entry {
 /* ---------------------------------------------------------------------------------------------------- */
 
 int mc_version(void);
-/* sizeof of the ABI structs: 0 mc_record, 1 mc_call, 2 mc_refindex, 3 mc_model, 4 mc_qual_entry, 5 mc_synth_spec, 6 mc_locus_entry */
+/* sizeof of the ABI structs: 0 mc_record, 1 mc_call, 2 mc_refindex, 3 mc_model, 4 mc_qual_entry, 5 mc_synth_spec, 6 mc_locus_entry,
+ * 7 mc_diffs_row, 8 mc_carry */
 int mc_sizeof(int what);
 const char *mc_last_error(void);
 
@@ -200,65 +205,121 @@ int64_t mc_workspace_bytes(int64_t n);
 
 /* Stage 2 -- put the records into file order (exclusive scan of the chunk table + gather).  d_rec_in is the stage-1
  * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
- * records, which land densely in d_rec_out (rec_out_cap slots; d_counters[MC_C_RECORDS] is an upper bound).  Records arrive
- * in raw form (column offsets, MC_RF_RAW) and are finished here, one thread per record: event index, the float64
- * np.round(event_mean - model_mean, 4) from exact decimal parsing, and the k-mer equality flag (extract_contexts.py:150,
- * :169, :286). */
+ * records, which land densely in d_rec_out (rec_out_cap slots; rec_in_cap is always enough).  Records that stage 1 left
+ * in raw form (MC_RF_RAW) are finished here, one thread per record: event index, the float64 np.round(event_mean -
+ * model_mean, 4) from exact decimal parsing, and the k-mer equality flag (extract_contexts.py:150, :169, :286); read-name
+ * changes between neighbouring records are flagged (MC_RF_NEWREAD).  d_scan_counters: the counter block mc_scan wrote
+ * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
+ * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
 int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in,
-                     int64_t rec_in_cap, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
+                     int64_t rec_in_cap, const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap,
+                     uint64_t *d_n_out, void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the
  * previous record's (extract_contexts.py:161, `read_name != last_read`).  Writes the first record index of
- * each segment to d_seg_start (capacity n_records+1, terminated by n_records) and the segment count to
- * d_nseg[0].
+ * each segment to d_seg_start (capacity rec_cap+1, terminated by the record count) and the segment count to
+ * d_nseg[0].  d_n_records[0] (device) is the record count written by mc_order_records; rec_cap >= it sizes the launch.
  */
-int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, int64_t n_records,
+int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
                      uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream);
 
 /*
  * Stage 4 -- read quality per segment: read2qual[name] else read2qual[name.split(':')[0].split('_')[0]]
  * (extract_contexts.py:163-166, read_qual.py:6-19).  Missing reads get NaN and are counted in d_err[0]
- * (the reference raises KeyError).
+ * (the reference raises KeyError).  d_nseg[0] (device) segments, seg_cap >= it.
  */
-int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, int64_t n_seg,
-                       const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual, uint64_t *d_err, void *stream);
+int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, const uint64_t *d_nseg,
+                       int64_t seg_cap, const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual, uint64_t *d_err,
+                       void *stream);
 
 /*
  * Stage 5 -- window builder: the state machine of extract_contexts.py:169-291 (strand inference, window
  * open/feed/close, skip filter, multi-M carry, orientation flip, np.mean of np.round(ev-model,4) per column in
- * numpy's summation order).  A read is cut into units at its non-candidate records (after which the reference's
- * state is closed and empty); one thread per unit, two passes (count, exclusive scan, write) so rows come out in
- * file order.  d_rec must come from mc_order_records (MC_RF_SEGKNOWN / MC_RF_NEWREAD set) and d_seg_start from
- * mc_segment_reads on the same records.  d_seg_count is scratch of n_seg uint32.  d_ncalls[0] receives the number of
- * rows (all kinds); rows beyond call_cap are dropped and d_ncalls[1] is set.  Segments whose quality is below
- * qual_thresh are skipped entirely (:167).  d_ws: mc_workspace_bytes(n_records).
+ * numpy's summation order, any number of events per column).  A read is cut into units at its non-candidate records
+ * (after which the reference's state is closed and empty); one thread per unit, two passes (count, exclusive scan,
+ * write) so rows come out in file order.  d_rec must come from mc_order_records (MC_RF_SEGKNOWN / MC_RF_NEWREAD set)
+ * and d_seg_start from mc_segment_reads on the same records.  d_seg_count is scratch of seg_cap uint32.  d_ncalls[0]
+ * receives the number of rows (all kinds); rows beyond call_cap are dropped and d_ncalls[1] is set.  Segments whose
+ * quality is below qual_thresh are skipped entirely (:167).  d_ws: mc_workspace_bytes(rec_cap).
  */
-int mc_build_windows(const mc_record *d_rec, int64_t n_records, const uint32_t *d_seg_start, int64_t n_seg,
-                     const double *d_seg_qual, const mc_refindex *ref, int skip_thresh, double qual_thresh, int two_models,
-                     mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count, uint64_t *d_ncalls, void *d_ws, void *stream);
+int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap, const uint32_t *d_seg_start,
+                     const uint64_t *d_nseg, int64_t seg_cap, const double *d_seg_qual, const mc_refindex *ref, int skip_thresh,
+                     double qual_thresh, int two_models, mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count,
+                     uint64_t *d_ncalls, void *d_ws, void *stream);
+
+/*
+ * Chunk / rank edges.  The reference closes a window when it reads the NEXT kept line (extract_contexts.py:179), so the
+ * window still open at the end of a chunk of text belongs to the rows of the following chunk, and the one open at the
+ * end of a worker's byte range is closed by the first kept line of the next range (mCaller.py:63-68); only the last
+ * window of the file is dropped.  mc_carry is the device-resident state that carries that one row.
+ *
+ * mc_carry_rows: d_rows[0] is a slot reserved by the caller in front of the rows mc_build_windows wrote at d_rows + 1
+ *   (d_ncalls[0] of them).  If the carry holds a row and this chunk has a kept line (first record of the first read
+ *   segment that passes the quality filter), the carried row is completed -- chrom_contig = contig of that line (:216),
+ *   close_rec = its record index, read_off = -1 (the read name lies in the previous chunk's text; the host keeps it) --
+ *   and placed in d_rows[0]; otherwise d_rows[0].kind = MC_NONE.  A row of this chunk that is still pending
+ *   (close_rec == 0xFFFFFFFF, always the last row) becomes the new carry.  d_nrows_out[0] = d_ncalls[0] + 1: the rows
+ *   d_rows[0 .. ] that the classifier, histogram, statistics and the writer consume.  The first kept contig seen since
+ *   mc_carry_reset is remembered in the carry (what the previous rank needs to close ITS last window).  d_abort (may be
+ *   NULL): see mc_chunk_guard.
+ * mc_carry_close: end of a byte range.  closing_contig >= 0: contig of the first kept line after the range (found by the
+ *   host, or -1 with d_next_contigs: first_kept_contig of the following ranks, all-gathered; the first entry >= 0 among
+ *   [from, count) closes).  The completed row goes to d_row_out (kind MC_NONE when there is nothing to close or nobody
+ *   closes it = end of file) and, when it is a call with prob/label already set by mc_classify, into the histogram
+ *   (d_depth may be NULL: no histogram) with first-seen index d_row_base[0] -- the device-side row counter
+ *   mc_hist_accumulate advances, i.e. after every row of the range -- which is then advanced by one.
+ */
+typedef struct mc_carry {
+    mc_call row;                   /* the open window (valid != 0) */
+    uint32_t valid;
+    int32_t first_kept_contig;     /* contig of the first kept line seen since mc_carry_reset, -1 = none yet */
+    uint64_t chunks;               /* chunks seen since the reset (informational) */
+    uint64_t pad[6];
+} mc_carry;                        /* 192 bytes */
+int mc_carry_reset(mc_carry *d_carry, void *stream);
+int mc_carry_rows(mc_call *d_rows, const uint64_t *d_ncalls, const mc_record *d_rec, const uint64_t *d_n_records,
+                  const uint32_t *d_seg_start, const uint64_t *d_nseg, const double *d_seg_qual, double qual_thresh,
+                  mc_carry *d_carry, uint64_t *d_nrows_out, const uint64_t *d_abort, void *stream);
+/* Overflow guard of a chunk: d_abort[0] = 1 when a buffer of the stages so far was too small (mc_scan's overflow counter, reserved
+ * record slots > rec_cap, ordered records > rec_out_cap, rows > call_cap), else 0.  The stages that change state across chunks
+ * (mc_carry_rows, mc_hist_accumulate) take d_abort and do nothing when it is set, so the host can grow its buffers and run the
+ * chunk again without having synchronised in between. */
+int mc_chunk_guard(const uint64_t *d_counters, int64_t rec_cap, const uint64_t *d_n_records, int64_t rec_out_cap,
+                   const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort, void *stream);
+int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64_t *d_next_contigs, int from, int count, mc_call *d_row_out,
+                   uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first, int64_t n_sites, uint64_t *d_row_base, void *stream);
 
 /*
  * Stage 6 -- classifier: model[key].predict_proba([x])[0][1] and the 0.5 label threshold
  * (extract_contexts.py:195-207) for every MC_CALL row; float64 arithmetic.  models[0] = 'MH'/'general',
- * models[1] = 'MG' (only read when a row has model_sel == 1).
+ * models[1] = 'MG' (only read when a row has model_sel == 1).  d_nrows[0] (device) rows, row_cap >= it.
  */
-int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void *stream);
+int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, const mc_model *models, void *stream);
 
 /*
  * Stage 7 -- per-position aggregation (make_bed.py:86-96): depth and methylated counts per site slot, plus the
  * smallest global row index that touched the slot (first-seen order of make_bed.py:134).  d_depth/d_meth are
- * uint32[n_sites], d_first uint64[n_sites] (initialise to ~0); row_base is added to the row index (chunk / rank
- * offset).  Rows whose closing contig differs from the window contig (reference quirk, :216) or that are pending
- * are skipped and counted in d_skipped[0]; the host handles them.
+ * uint32[n_sites], d_first uint64[n_sites] (initialise to ~0); d_row_base[0] (device) is added to the row index and then
+ * advanced by the number of rows, so consecutive chunks keep file order.  Rows whose closing contig differs from the
+ * window contig (reference quirk, :216: column 1 of the row names another contig than the site's) cannot be keyed by
+ * site slot: they are appended to d_odd (capacity odd_cap rows, count in d_n_odd[0], the row's pad1/pad2 receive the
+ * low / high half of its global row index) for the host to merge.  Pending rows and MC_NONE slots are skipped.
  */
-int mc_hist_accumulate(const mc_call *d_calls, int64_t n_calls, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first,
-                       int64_t n_sites, uint64_t row_base, uint64_t *d_skipped, void *stream);
+int mc_hist_accumulate(const mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, uint32_t *d_depth, uint32_t *d_meth,
+                       uint64_t *d_first, int64_t n_sites, uint64_t *d_row_base, mc_call *d_odd, int64_t odd_cap, uint64_t *d_n_odd,
+                       const uint64_t *d_abort /* may be NULL */, void *stream);
+
+/* Thresholds of the summary (check_thresh, make_bed.py:21-28) on the device histogram: d_flags[s] = 1 for the site slots
+ * that make_bed.py -d depth_thresh -t mod_thresh [--control] reports (depth >= depth_thresh and float64 meth / depth >= mod_thresh,
+ * or < with control), d_count[0] = how many.  The host formats only those (mcaller_b200.make_bed.aggregate_from_histogram). */
+int mc_bed_select(const uint32_t *d_depth, const uint32_t *d_meth, int64_t n_sites, int64_t depth_thresh, double mod_thresh,
+                  int control, uint8_t *d_flags, uint64_t *d_count, void *stream);
 
 /* Row statistics on the device (adds to d_out[7], which the caller zeroes): calls closed in the chunk, calls still
  * pending, too-many-skips events closed in the chunk, multi-M events, rows with an error flag, calls labelled
  * methylated, too-many-skips events still pending (counted by the reference only once a later kept line closes them). */
-int mc_count_calls(const mc_call *d_calls, int64_t n_calls, uint64_t *d_out, void *stream);
+int mc_count_calls(const mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, uint64_t *d_out, void *stream);
 
 /*
  * make_bed drop-in: aggregate a `.diffs.<k>` text file (make_bed.py:75-98, default mode).  d_table is an open-addressing
@@ -279,7 +340,8 @@ int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_
 /*
  * make_bed variants that need per-read lists (make_bed.py -p and --vo).
  *
- * mc_diffs_aggregate_ex: mc_diffs_aggregate with the `-p` filter of make_bed.py:73-74/:84 -- d_posset (may be NULL) is an
+ * mc_diffs_aggregate_ex: mc_diffs_aggregate with the `-p` filter of make_bed.py:73-74/:84 and a base offset, so a file can be
+ *   streamed in line-aligned pieces into one table (first_off = base_off + offset inside the piece) -- d_posset (may be NULL) is an
  *   open-addressing set (power-of-two entries, 0 = empty) of FNV-1a hashes of "chrom\tpos\tstrand" built by the host from
  *   the positions file (entries whose end column is not start + 1 can never match and are left out).
  *   d_counters[8]: rows, malformed, centre-not-'M', table-full drops, rows outside the positions set, old-format rows
@@ -301,8 +363,11 @@ typedef struct mc_diffs_row {
     uint32_t prob_len;
     uint32_t pad;
 } mc_diffs_row;                /* 32 bytes */
-int mc_diffs_aggregate_ex(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,
+int mc_diffs_aggregate_ex(const uint8_t *d_text, int64_t nbytes, int64_t base_off, const uint64_t *d_posset, int64_t posset_size,
                           mc_locus_entry *d_table, int64_t table_size, uint64_t *d_counters, void *stream);
+/* moves the used entries of d_old into the (initialised, larger) table d_table; table-full drops are counted in d_counters[3] */
+int mc_diffs_rehash(const mc_locus_entry *d_old, int64_t old_size, mc_locus_entry *d_table, int64_t table_size,
+                    uint64_t *d_counters, void *stream);
 int mc_diffs_rows(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,
                   const mc_locus_entry *d_table, int64_t table_size, mc_diffs_row *d_rows, int64_t row_cap, uint64_t *d_nrows,
                   void *stream);
@@ -315,12 +380,17 @@ int mc_diffs_colstats(const uint8_t *d_text, const mc_diffs_row *d_rows, const u
  * pending are skipped) as `.diffs.<k>` text exactly like the reference (extract_contexts.py:216, :83-86): chrom, read,
  * position, 2k-1 context cut from the marked reference copies, comma-joined features (shortest round-trip repr, integer 0
  * for empty columns) + read quality, strand, and -- with_prob -- label and np.round(prob, 2).  h_text is the host copy
- * of the chunk (read names).  Returns the number of bytes written, MC_ECAPACITY when out_cap is too small, or
- * -100 - err when a row carries MC_CE_* error flags.
+ * of the chunk (read names); a row with read_off < 0 (a window carried over from the previous chunk, mc_carry_rows) takes
+ * its read name from carry_name[0 .. carry_name_len).  Returns the number of bytes written, MC_ECAPACITY when out_cap is
+ * too small, -100 - err when a row carries MC_CE_* error flags, or MC_EINVAL when a context covers a reference letter
+ * outside ACGTNM (the reference raises KeyError in revcomp, extract_contexts.py:11-15).  max_threads <= 0: one host
+ * thread per hardware thread.
  */
-int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const char *const *contig_names,
-                       const char *const *marked_fwd, const char *const *marked_rev, const int64_t *contig_len, int32_t n_contigs,
-                       int32_t k, const char *base_label, const char *mod_label, int32_t with_prob, char *out, int64_t out_cap);
+int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const uint8_t *carry_name,
+                       int32_t carry_name_len, const char *const *contig_names, const char *const *marked_fwd,
+                       const char *const *marked_rev, const int64_t *contig_len, int32_t n_contigs, int32_t k,
+                       const char *base_label, const char *mod_label, int32_t with_prob, int32_t max_threads, char *out,
+                       int64_t out_cap);
 
 /*
  * FASTQ read-quality ingest (reference read_qual.py:6-19) on the device.  mc_fastq_index builds the byte offset of every

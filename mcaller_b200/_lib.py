@@ -17,7 +17,8 @@ MC_MAXK = 8
 MC_C_COUNT = 16
 COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor"]
 
-MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M = 0, 1, 2
+MC_ABI_VERSION = 2
+MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M, MC_NONE = 0, 1, 2, 3
 MC_CE_CONTEXT, MC_CE_MODELKEY, MC_CE_BADNUM, MC_CE_COLUMN, MC_CE_SPACING = 1, 2, 4, 8, 16
 MC_MLP, MC_LR, MC_GNB, MC_RF = 0, 1, 2, 3
 PENDING = 0xFFFFFFFF
@@ -60,6 +61,8 @@ class LocusEntry(C.Structure):
     _fields_ = [("hash", C.c_uint64), ("first_off", C.c_uint64), ("depth", C.c_uint32), ("meth", C.c_uint32)]
 
 
+CARRY_BYTES = 192          # sizeof(mc_carry): the row (128 B), valid, first_kept_contig, chunk count, padding
+
 QUAL_DTYPE = np.dtype([("hash", "<u8"), ("check", "<u4"), ("len", "<u4"), ("qual", "<f8")])
 assert QUAL_DTYPE.itemsize == 24
 DIFFS_ROW_DTYPE = np.dtype([("line_off", "<u8"), ("slot", "<u4"), ("values_off", "<u4"), ("values_len", "<u4"), ("prob_off", "<u4"),
@@ -82,17 +85,39 @@ _PROTOS = {
     "mc_scan_set_run_len": (C.c_int, [C.c_int]),
     "mc_num_tiles": (C.c_int64, [C.c_int64]),
     "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
-    "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]),
-    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mc_build_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RefIndex), C.c_int, C.c_double,
-                                   C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mc_classify": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Model), C.c_void_p]),
-    "mc_hist_accumulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
-    "mc_count_calls": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "mc_format_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                   C.c_char_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]),
+    # d_text, nbytes, d_tile_tab, n_tiles, d_rec_in, rec_in_cap, d_scan_counters, d_rec_out, rec_out_cap, d_n_out, d_ws, stream
+    "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    # d_text, d_rec, d_n_records, rec_cap, d_seg_start, d_nseg, d_ws, stream
+    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # d_text, d_rec, d_seg_start, d_nseg, seg_cap, d_table, table_size, d_seg_qual, d_err, stream
+    "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    # d_rec, d_n_records, rec_cap, d_seg_start, d_nseg, seg_cap, d_seg_qual, ref, skip, qual, two_models, d_calls, call_cap,
+    # d_seg_count, d_ncalls, d_ws, stream
+    "mc_build_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RefIndex),
+                                   C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_carry_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    # d_rows, d_ncalls, d_rec, d_n_records, d_seg_start, d_nseg, d_seg_qual, qual_thresh, d_carry, d_nrows_out, d_abort, stream
+    "mc_carry_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    # d_counters, rec_cap, d_n_records, rec_out_cap, d_ncalls, call_cap, d_abort, stream
+    "mc_chunk_guard": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    # d_carry, closing_contig, d_next_contigs, from, count, d_row_out, d_depth, d_meth, d_first, n_sites, d_row_base, stream
+    "mc_carry_close": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_void_p, C.c_void_p]),
+    # d_calls, d_nrows, row_cap, models, stream
+    "mc_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Model), C.c_void_p]),
+    # d_calls, d_nrows, row_cap, d_depth, d_meth, d_first, n_sites, d_row_base, d_odd, odd_cap, d_n_odd, d_abort, stream
+    "mc_hist_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_count_calls": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    # d_depth, d_meth, n_sites, depth_thresh, mod_thresh, control, d_flags, d_count, stream
+    "mc_bed_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # h_calls, n_calls, h_text, carry_name, carry_name_len, contig_names, marked_fwd, marked_rev, contig_len, n_contigs, k,
+    # base_label, mod_label, with_prob, max_threads, out, out_cap
+    "mc_format_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "mc_fastq_tiles": (C.c_int64, [C.c_int64]),
     "mc_fastq_index": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_fastq_quality": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -101,7 +126,8 @@ _PROTOS = {
     "mc_synth_sizes": (C.c_int, [C.POINTER(SynthSpec), C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mc_synth_write": (C.c_int, [C.POINTER(SynthSpec), C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_diffs_aggregate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "mc_diffs_aggregate_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mc_diffs_aggregate_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mc_diffs_rehash": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mc_diffs_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_void_p]),
     "mc_diffs_colstats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
@@ -128,7 +154,7 @@ def lib():
     global _lib
     if _lib is None:
         _lib = load()
-        if _lib.mc_version() != 1:
+        if _lib.mc_version() != MC_ABI_VERSION:
             raise McallerCudaError("ABI version mismatch")
     return _lib
 

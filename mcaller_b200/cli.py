@@ -5,7 +5,11 @@
 
 The reference's own mCaller.py / make_bed.py can be used unchanged instead; these entry points exist
 so the path can be run where the reference checkout is absent.  `-t N` splits the TSV into N read-aligned byte ranges
-handled one after another on this process's GPU (one process per GPU is the multi-GPU model, see bench.py).
+like the reference (mCaller.py:63-68); range i is handled on GPU i mod n_gpus, one after another in this process.
+`--gpus N` (extension) runs N ranks at once, one process per GPU (mcaller_b200.multigpu): rows are written per rank and
+concatenated, the per-site histograms are all-reduced over NCCL, and with `--bed` rank 0 writes make_bed.py's BED / GFF
+straight from the combined histogram (`--bed_min_read_depth`, `--bed_mod_threshold`, `--bed_control`, `--bed_gff`,
+`--bed_ref` mirror make_bed.py's -d / -t / --control / --gff / --ref).
 """
 import math
 import os
@@ -33,6 +37,13 @@ def mcaller_main(argv=None):
     p.add_argument("-c", "--classifier", type=str, default="NN")
     p.add_argument("--plot_training", action="store_true", default=False)
     p.add_argument("-v", "--version", action="version", version="%(prog)s v1.0 (mcaller_b200)")
+    p.add_argument("--gpus", type=int, default=0, help="run N ranks, one process per GPU (0: single process, -t ranges in turn)")
+    p.add_argument("--bed", action="store_true", help="with --gpus: write the make_bed.py summary from the all-reduced histogram")
+    p.add_argument("--bed_min_read_depth", type=int, default=15)
+    p.add_argument("--bed_mod_threshold", type=float, default=0.5)
+    p.add_argument("--bed_control", action="store_true")
+    p.add_argument("--bed_gff", action="store_true")
+    p.add_argument("--bed_ref", type=str)
     a = p.parse_args(argv)
     if a.train or a.training_tsv:
         raise NotImplementedError("training stays with the reference (out of scope of the accelerated path)")
@@ -48,10 +59,19 @@ def mcaller_main(argv=None):
     base = a.motif if (a.motif and len(a.motif) == 1) else a.base
     assert a.skip_thresh < a.num_variables / 2, "too many skips with only " + str(a.num_variables) + " variables - try < half"
     assert os.path.isfile(a.fastq), "fastq file not found at " + a.fastq
+    k = a.num_variables
+    if a.gpus and a.gpus > 0:
+        from . import multigpu
+        print("%d contigs" % len(refmark.read_fasta(a.reference)))
+        print("%d GPUs" % a.gpus)
+        multigpu.run(dict(tsv=a.tsv, reference=a.reference, fastq=a.fastq, modelfile=modelfile, k=k, skip=a.skip_thresh, qual=a.qual_thresh,
+                          base=base, motif=a.motif, positions=a.positions, bed=a.bed, bed_depth=a.bed_min_read_depth,
+                          bed_thresh=a.bed_mod_threshold, bed_control=a.bed_control, bed_gff=a.bed_gff, bed_ref=a.bed_ref), a.gpus)
+        print("Finished extracting signals")
+        return 0
     read2qual = read_qual.extract_read_quality_device(a.fastq)        # FASTQ scanned on the GPU (same mapping as read_qual.py)
     print("%d contigs" % len(refmark.read_fasta(a.reference)))
     print("%d threads" % a.threads)
-    k = a.num_variables
     out = ".".join(a.tsv.split(".")[:-1]) + ".diffs." + str(k)
     size = os.path.getsize(a.tsv)
     n = max(1, a.threads)

@@ -75,7 +75,7 @@ __device__ __forceinline__ int classify_row(const uint8_t *__restrict__ text, in
 }
 
 __global__ void __launch_bounds__(256)
-k_diffs_aggregate(const uint8_t *__restrict__ text, int64_t nbytes, const unsigned long long *__restrict__ posset,
+k_diffs_aggregate(const uint8_t *__restrict__ text, int64_t nbytes, unsigned long long base_off, const unsigned long long *__restrict__ posset,
                   unsigned long long posmask, mc_locus_entry *__restrict__ table, unsigned long long mask,
                   unsigned long long *__restrict__ counters) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,12 +101,34 @@ k_diffs_aggregate(const uint8_t *__restrict__ text, int64_t nbytes, const unsign
         if (cur == h) {
             atomicAdd(&table[slot].depth, 1u);
             if (is_m) atomicAdd(&table[slot].meth, 1u);
-            atomicMin(&table[slot].first_off, (unsigned long long)p);
+            atomicMin(&table[slot].first_off, base_off + (unsigned long long)p);
             return;
         }
         slot = (slot + 1) & mask;
     }
     atomicAdd(&counters[3], 1ull);                               // table full
+}
+
+// move every used entry of a table into a larger one (the file is streamed in pieces and the table grows with the loci seen)
+__global__ void __launch_bounds__(256)
+k_diffs_rehash(const mc_locus_entry *__restrict__ old_table, unsigned long long old_size, mc_locus_entry *__restrict__ table,
+               unsigned long long mask, unsigned long long *__restrict__ counters) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= old_size) return;
+    const mc_locus_entry e = old_table[i];
+    if (e.hash == 0ull) return;
+    unsigned long long slot = e.hash & mask;
+    for (unsigned long long probe = 0; probe <= mask; ++probe) {
+        const unsigned long long cur = atomicCAS(&table[slot].hash, 0ull, e.hash);
+        if (cur == 0ull) {                                       // keys are distinct in the old table: the slot is ours
+            table[slot].first_off = e.first_off;
+            table[slot].depth = e.depth;
+            table[slot].meth = e.meth;
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicAdd(&counters[3], 1ull);
 }
 
 // second pass: one index entry per used row (any order; the host sorts by line offset)
@@ -315,22 +337,36 @@ static int check_sets(const void *d_posset, int64_t posset_size, int64_t table_s
     return MC_OK;
 }
 
-extern "C" int mc_diffs_aggregate_ex(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,
-                                     mc_locus_entry *d_table, int64_t table_size, uint64_t *d_counters, void *stream) {
+extern "C" int mc_diffs_aggregate_ex(const uint8_t *d_text, int64_t nbytes, int64_t base_off, const uint64_t *d_posset,
+                                     int64_t posset_size, mc_locus_entry *d_table, int64_t table_size, uint64_t *d_counters,
+                                     void *stream) {
     MC_REQUIRE(d_text && d_table && d_counters, "null pointer");
+    MC_REQUIRE(base_off >= 0, "negative base offset");
     int rc = check_sets(d_posset, posset_size, table_size);
     if (rc) return rc;
     if (nbytes <= 0) return MC_OK;
     k_diffs_aggregate<<<(unsigned)((nbytes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_text, nbytes, reinterpret_cast<const unsigned long long *>(d_posset), (unsigned long long)(d_posset ? posset_size - 1 : 0), d_table,
-        (unsigned long long)(table_size - 1), reinterpret_cast<unsigned long long *>(d_counters));
+        d_text, nbytes, (unsigned long long)base_off, reinterpret_cast<const unsigned long long *>(d_posset),
+        (unsigned long long)(d_posset ? posset_size - 1 : 0), d_table, (unsigned long long)(table_size - 1),
+        reinterpret_cast<unsigned long long *>(d_counters));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
 extern "C" int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_table, int64_t table_size,
                                   uint64_t *d_counters, void *stream) {
-    return mc_diffs_aggregate_ex(d_text, nbytes, nullptr, 0, d_table, table_size, d_counters, stream);
+    return mc_diffs_aggregate_ex(d_text, nbytes, 0, nullptr, 0, d_table, table_size, d_counters, stream);
+}
+
+extern "C" int mc_diffs_rehash(const mc_locus_entry *d_old, int64_t old_size, mc_locus_entry *d_table, int64_t table_size,
+                               uint64_t *d_counters, void *stream) {
+    MC_REQUIRE(d_old && d_table && d_counters, "null pointer");
+    MC_REQUIRE(table_size > 0 && (table_size & (table_size - 1)) == 0, "table size must be a power of two");
+    if (old_size <= 0) return MC_OK;
+    k_diffs_rehash<<<(unsigned)((old_size + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_old, (unsigned long long)old_size, d_table, (unsigned long long)(table_size - 1), reinterpret_cast<unsigned long long *>(d_counters));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
 }
 
 extern "C" int mc_diffs_rows(const uint8_t *d_text, int64_t nbytes, const uint64_t *d_posset, int64_t posset_size,

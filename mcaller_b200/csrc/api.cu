@@ -33,6 +33,7 @@ extern "C" int mc_sizeof(int what) {
         case 5: return (int)sizeof(mc_synth_spec);
         case 6: return (int)sizeof(mc_locus_entry);
         case 7: return (int)sizeof(mc_diffs_row);
+        case 8: return (int)sizeof(mc_carry);
         default: return -1;
     }
 }

@@ -32,8 +32,10 @@ __device__ __forceinline__ double activate(double v, int act) {
 // reads the weights through the read-only cache instead.
 template <bool STAGED>
 __global__ void __launch_bounds__(WARPS * 32)
-k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int width, int nw0, int nb0, int nw1, int nb1, int alias) {
+k_mlp(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n, mc_model m0, mc_model m1, int width, int nw0,
+      int nb0, int nw1, int nb1, int alias) {
     extern __shared__ __align__(16) double s_mlp[];          // [weights 0][biases 0][weights 1][biases 1][WARPS][2][width]
+    const int64_t n = mc_dev_count(d_n, n_cap);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *s_act = s_mlp;
     if (STAGED) {
@@ -133,8 +135,11 @@ k_mlp(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int widt
 // shuffles.  Same arithmetic as k_mlp: dot product in input order, then the intercept, activation, logistic output.
 constexpr int MLP_MAX_IN = MC_MAXK + 1;
 __global__ void __launch_bounds__(WARPS * 32)
-k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int nw0, int nb0, int nw1, int nb1, int alias) {
+k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n, mc_model m0, mc_model m1, int nw0,
+              int nb0, int nw1, int nb1, int alias) {
     extern __shared__ __align__(16) double s_mlp[];          // [weights 0][biases 0][weights 1][biases 1]
+    const int64_t n = mc_dev_count(d_n, n_cap);
+    if ((int64_t)blockIdx.x * WARPS * 8 >= n) return;        // nothing for this block: skip staging the weights
     for (int j = threadIdx.x; j < nw0; j += WARPS * 32) s_mlp[j] = __ldg(m0.d_weights + j);
     for (int j = threadIdx.x; j < nb0; j += WARPS * 32) s_mlp[nw0 + j] = __ldg(m0.d_biases + j);
     for (int j = threadIdx.x; j < nw1; j += WARPS * 32) s_mlp[nw0 + nb0 + j] = __ldg(m1.d_weights + j);
@@ -197,7 +202,9 @@ k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, 
 }
 
 // LogisticRegression.predict_proba (binary): expit(x.w + b); GaussianNB.predict_proba: exp(jll_1 - logsumexp(jll))
-__global__ void __launch_bounds__(256) k_linear(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1) {
+__global__ void __launch_bounds__(256) k_linear(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n,
+                                               mc_model m0, mc_model m1) {
+    const int64_t n = mc_dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     mc_call &c = calls[i];
@@ -233,8 +240,10 @@ __global__ void __launch_bounds__(256) k_linear(mc_call *__restrict__ calls, int
 // with the float64 threshold (sklearn tree/_tree.pyx).  A block owns 256 calls and streams the trees through shared
 // memory (node table of one tree at a time), so every node read in the walk is an smem read.
 __global__ void __launch_bounds__(256)
-k_rf(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int max_nodes) {
+k_rf(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n, mc_model m0, mc_model m1, int max_nodes) {
     extern __shared__ __align__(16) uint8_t rf_smem[];
+    const int64_t n = mc_dev_count(d_n, n_cap);
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;       // block-uniform
     double *s_thr = reinterpret_cast<double *>(rf_smem);
     double *s_p1 = s_thr + max_nodes;
     int32_t *s_left = reinterpret_cast<int32_t *>(s_p1 + max_nodes);
@@ -282,28 +291,55 @@ k_rf(mc_call *__restrict__ calls, int64_t n, mc_model m0, mc_model m1, int max_n
 
 // ---- stage 7 (K4): per-site histogram (make_bed.py:86-96) ----------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_hist(const mc_call *__restrict__ calls, int64_t n, uint32_t *__restrict__ depth, uint32_t *__restrict__ meth,
-       unsigned long long *__restrict__ first, int64_t n_sites, unsigned long long row_base,
-       unsigned long long *__restrict__ d_skipped) {
+k_hist(const mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ depth,
+       uint32_t *__restrict__ meth, unsigned long long *__restrict__ first, int64_t n_sites, const unsigned long long *__restrict__ d_row_base,
+       mc_call *__restrict__ d_odd, unsigned long long odd_cap, unsigned long long *__restrict__ d_n_odd,
+       const unsigned long long *__restrict__ d_abort) {
+    if (d_abort && *d_abort) return;                          // a buffer overflowed earlier in this chunk: the host redoes it
+    const int64_t n = mc_dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const mc_call &c = calls[i];
-    if (c.kind != MC_CALL) return;
-    if (c.close_rec == 0xFFFFFFFFu || c.chrom_contig != c.win_contig || c.site < 0 || c.site >= n_sites || c.err) {
-        atomicAdd(d_skipped, 1ull);
+    if (c.kind != MC_CALL || c.close_rec == 0xFFFFFFFFu || c.err) return;     // other kinds, pending rows, error rows (the host raises)
+    const unsigned long long row = *d_row_base + (unsigned long long)i;
+    if (c.chrom_contig != c.win_contig || c.site < 0 || c.site >= n_sites) {
+        // column 1 names another contig than the site's (reference quirk, :216): keyed by the host
+        const unsigned long long slot = atomicAdd(d_n_odd, 1ull);
+        if (slot < odd_cap) {
+            mc_call o = c;
+            o.pad1 = (uint32_t)(row & 0xFFFFFFFFull);
+            o.pad2 = (uint32_t)(row >> 32);
+            d_odd[slot] = o;
+        }
         return;
     }
     atomicAdd(depth + c.site, 1u);
     if (c.label) atomicAdd(meth + c.site, 1u);
-    atomicMin(first + c.site, row_base + (unsigned long long)i);
+    atomicMin(first + c.site, row);
+}
+__global__ void k_advance_base(unsigned long long *d_row_base, const unsigned long long *d_n, const unsigned long long *d_abort) {
+    if (d_abort && *d_abort) return;
+    *d_row_base += *d_n;
+}
+// any overflow of the chunk's buffers so far -> d_abort[0] = 1 (the stages that change state across chunks then do nothing)
+__global__ void k_chunk_guard(const unsigned long long *__restrict__ counters, unsigned long long rec_cap,
+                              const unsigned long long *__restrict__ d_n_records, unsigned long long rec_out_cap,
+                              const unsigned long long *__restrict__ d_ncalls, unsigned long long call_cap,
+                              unsigned long long *__restrict__ d_abort) {
+    const bool bad = counters[MC_C_OVERFLOW] != 0ull || counters[MC_C_RECORDS] > rec_cap || *d_n_records > rec_out_cap ||
+                     d_ncalls[0] > call_cap || d_ncalls[1] != 0ull;
+    *d_abort = bad ? 1ull : 0ull;
 }
 
 // row statistics without a D2H copy of the rows: [0] calls closed in this chunk, [1] calls still pending,
 // [2] too-many-skips events closed in this chunk, [3] multi-M events, [4] rows with an error flag, [5] calls labelled
 // methylated, [6] too-many-skips events still pending (a window open at the end of the chunk is closed -- and only then
 // counted, extract_contexts.py:179/:238 -- by the next kept line of the file; the last one of a file never is)
-__global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__ calls, int64_t n, unsigned long long *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n,
+                                                    unsigned long long *__restrict__ out) {
     __shared__ unsigned int s[7];
+    const int64_t n = mc_dev_count(d_n, n_cap);
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;       // block-uniform
     if (threadIdx.x < 7) s[threadIdx.x] = 0u;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,30 +347,212 @@ __global__ void __launch_bounds__(256) k_count_calls(const mc_call *__restrict__
         const mc_call &c = calls[i];
         if (c.kind == MC_CALL) {
             atomicAdd(&s[c.close_rec == 0xFFFFFFFFu ? 1 : 0], 1u);
-            if (c.label) atomicAdd(&s[5], 1u);
+            if (c.label && c.close_rec != 0xFFFFFFFFu) atomicAdd(&s[5], 1u);
         } else if (c.kind == MC_TOO_MANY_SKIPS) atomicAdd(&s[c.close_rec == 0xFFFFFFFFu ? 6 : 2], 1u);
-        else atomicAdd(&s[3], 1u);
-        if (c.err) atomicAdd(&s[4], 1u);
+        else if (c.kind == MC_MULTI_M) atomicAdd(&s[3], 1u);
+        if (c.kind != MC_NONE && c.err) atomicAdd(&s[4], 1u);
     }
     __syncthreads();
     if (threadIdx.x < 7 && s[threadIdx.x]) atomicAdd(out + threadIdx.x, (unsigned long long)s[threadIdx.x]);
 }
 
+// check_thresh of make_bed.py:21-28 per site slot: len(list) >= depth_thresh, then np.mean(0/1 list) = meth / depth in float64
+// compared with mod_thresh (>= for methylated loci, < with --control)
+__global__ void __launch_bounds__(256)
+k_bed_select(const uint32_t *__restrict__ depth, const uint32_t *__restrict__ meth, int64_t n_sites, long long depth_thresh,
+             double mod_thresh, int control, uint8_t *__restrict__ flags, unsigned long long *__restrict__ d_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n_sites) {
+        const uint32_t d = depth[i];
+        if (d > 0u && (long long)d >= depth_thresh) {
+            const double frac = __ddiv_rn((double)meth[i], (double)d);
+            keep = control ? (frac < mod_thresh) : (frac >= mod_thresh);
+        }
+        flags[i] = keep ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(d_count, (unsigned long long)__popc(m));
+}
+
+// ---- chunk / rank edges: the one window that is still open when the text ends (see mc_carry in the header) -------------------
+__device__ __forceinline__ void copy_row(mc_call *dst, const mc_call *src) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d4[j] = s4[j];
+}
+
+// one warp: first kept record of the chunk (first record of the first segment that passes the quality filter, :167)
+__global__ void __launch_bounds__(32)
+k_carry_rows(mc_call *__restrict__ rows, const unsigned long long *__restrict__ d_ncalls, const mc_record *__restrict__ rec,
+             const unsigned long long *__restrict__ d_n_records, const uint32_t *__restrict__ seg_start,
+             const unsigned long long *__restrict__ d_nseg, const double *__restrict__ seg_qual, double qual_thresh,
+             mc_carry *__restrict__ carry, unsigned long long *__restrict__ d_nrows_out, const unsigned long long *__restrict__ d_abort) {
+    const int lane = threadIdx.x;
+    if (d_abort && *d_abort) {                                // overflow earlier in this chunk: leave the carry as it is
+        if (lane == 0) *d_nrows_out = 0ull;
+        return;
+    }
+    const unsigned long long n_rows = *d_ncalls, n_rec = *d_n_records, n_seg = *d_nseg;
+    long long fk_rec = -1;
+    if (n_rec > 0 && n_seg > 0) {
+        if (!(qual_thresh > 0.0)) fk_rec = 0;
+        else {
+            for (unsigned long long s0 = 0; s0 < n_seg && fk_rec < 0; s0 += 32) {
+                const unsigned long long sg = s0 + lane;
+                const bool ok = sg < n_seg && !(seg_qual[sg] < qual_thresh);
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (m) fk_rec = (long long)seg_start[s0 + (__ffs(m) - 1)];
+            }
+        }
+    }
+    if (lane != 0) return;
+    int fk_contig = -1;
+    if (fk_rec >= 0) fk_contig = (int)rec[fk_rec].contig;
+    mc_call *slot0 = rows;
+    bool resolved = false;
+    if (carry->valid && fk_contig >= 0) {
+        copy_row(slot0, &carry->row);
+        slot0->chrom_contig = (uint16_t)fk_contig;
+        slot0->close_rec = (uint32_t)fk_rec;
+        slot0->read_off = -1;
+        slot0->seg = 0xFFFFFFFFu;                 // not a segment of this chunk
+        carry->valid = 0u;
+        resolved = true;
+    }
+    if (!resolved) {
+        mc_call z;
+        memset(&z, 0, sizeof(z));
+        z.kind = MC_NONE;
+        z.site = -1;
+        copy_row(slot0, &z);
+    }
+    // the chunk's own open window: always its last row (the hand-off at the end of the last read that passed the filter)
+    if (n_rows > 0) {
+        const mc_call *last = rows + n_rows;      // rows[1 .. n_rows] hold the chunk's rows
+        if (last->close_rec == 0xFFFFFFFFu && (last->kind == MC_CALL || last->kind == MC_TOO_MANY_SKIPS)) {
+            copy_row(&carry->row, last);
+            carry->valid = 1u;
+        }
+    }
+    if (carry->first_kept_contig < 0 && fk_contig >= 0) carry->first_kept_contig = fk_contig;
+    carry->chunks += 1ull;
+    *d_nrows_out = n_rows + 1ull;
+}
+
+__global__ void k_carry_reset(mc_carry *carry) {
+    memset(carry, 0, sizeof(*carry));
+    carry->first_kept_contig = -1;
+    carry->row.kind = MC_NONE;
+}
+
+__global__ void k_carry_close(mc_carry *__restrict__ carry, int closing_contig, const long long *__restrict__ d_next, int from, int count,
+                              mc_call *__restrict__ out, uint32_t *__restrict__ depth, uint32_t *__restrict__ meth,
+                              unsigned long long *__restrict__ first, int64_t n_sites, unsigned long long *__restrict__ d_row_base) {
+    const unsigned long long row_index = d_row_base ? *d_row_base : 0ull;
+    int cc = closing_contig;
+    if (cc < 0 && d_next) {
+        for (int j = from; j < count; ++j) {
+            if (d_next[j] >= 0) { cc = (int)d_next[j]; break; }
+        }
+    }
+    mc_call z;
+    memset(&z, 0, sizeof(z));
+    z.kind = MC_NONE;
+    z.site = -1;
+    if (!carry->valid || cc < 0) {                // nothing open, or nobody closes it (end of the file: dropped)
+        copy_row(out, &z);
+        carry->valid = 0u;
+        return;
+    }
+    copy_row(out, &carry->row);
+    out->chrom_contig = (uint16_t)cc;
+    out->close_rec = 0u;
+    out->read_off = -1;
+    out->seg = 0xFFFFFFFFu;
+    out->pad1 = (uint32_t)(row_index & 0xFFFFFFFFull);
+    out->pad2 = (uint32_t)(row_index >> 32);
+    carry->valid = 0u;
+    if (out->kind == MC_CALL && !out->err && depth && out->chrom_contig == out->win_contig && out->site >= 0 && out->site < n_sites) {
+        atomicAdd(depth + out->site, 1u);
+        if (out->label) atomicAdd(meth + out->site, 1u);
+        atomicMin(first + out->site, row_index);
+    }
+    if (d_row_base) *d_row_base = row_index + 1ull;
+}
+
 }  // namespace
 
-extern "C" int mc_count_calls(const mc_call *d_calls, int64_t n_calls, uint64_t *d_out, void *stream) {
-    MC_REQUIRE(d_calls && d_out, "null pointer");
-    if (n_calls <= 0) return MC_OK;
-    k_count_calls<<<(unsigned)((n_calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_calls, n_calls,
-                                                                                       reinterpret_cast<unsigned long long *>(d_out));
+extern "C" int mc_count_calls(const mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, uint64_t *d_out, void *stream) {
+    MC_REQUIRE(d_calls && d_nrows && d_out, "null pointer");
+    if (row_cap <= 0) return MC_OK;
+    k_count_calls<<<(unsigned)((row_cap + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_calls, row_cap, reinterpret_cast<const unsigned long long *>(d_nrows), reinterpret_cast<unsigned long long *>(d_out));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
-extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *models, void *stream) {
-    MC_REQUIRE(d_calls && models, "null pointer");
+extern "C" int mc_carry_reset(mc_carry *d_carry, void *stream) {
+    MC_REQUIRE(d_carry, "null pointer");
+    k_carry_reset<<<1, 1, 0, (cudaStream_t)stream>>>(d_carry);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_carry_rows(mc_call *d_rows, const uint64_t *d_ncalls, const mc_record *d_rec, const uint64_t *d_n_records,
+                             const uint32_t *d_seg_start, const uint64_t *d_nseg, const double *d_seg_qual, double qual_thresh,
+                             mc_carry *d_carry, uint64_t *d_nrows_out, const uint64_t *d_abort, void *stream) {
+    MC_REQUIRE(d_rows && d_ncalls && d_rec && d_n_records && d_seg_start && d_nseg && d_seg_qual && d_carry && d_nrows_out, "null pointer");
+    k_carry_rows<<<1, 32, 0, (cudaStream_t)stream>>>(d_rows, reinterpret_cast<const unsigned long long *>(d_ncalls), d_rec,
+                                                     reinterpret_cast<const unsigned long long *>(d_n_records), d_seg_start,
+                                                     reinterpret_cast<const unsigned long long *>(d_nseg), d_seg_qual, qual_thresh, d_carry,
+                                                     reinterpret_cast<unsigned long long *>(d_nrows_out),
+                                                     reinterpret_cast<const unsigned long long *>(d_abort));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_bed_select(const uint32_t *d_depth, const uint32_t *d_meth, int64_t n_sites, int64_t depth_thresh, double mod_thresh,
+                             int control, uint8_t *d_flags, uint64_t *d_count, void *stream) {
+    MC_REQUIRE(d_depth && d_meth && d_flags && d_count, "null pointer");
+    MC_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, (cudaStream_t)stream));
+    if (n_sites <= 0) return MC_OK;
+    k_bed_select<<<(unsigned)((n_sites + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_depth, d_meth, n_sites, (long long)depth_thresh, mod_thresh,
+                                                                                      control, d_flags, reinterpret_cast<unsigned long long *>(d_count));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_chunk_guard(const uint64_t *d_counters, int64_t rec_cap, const uint64_t *d_n_records, int64_t rec_out_cap,
+                              const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort, void *stream) {
+    MC_REQUIRE(d_counters && d_n_records && d_ncalls && d_abort, "null pointer");
+    k_chunk_guard<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(d_counters), (unsigned long long)rec_cap,
+                                                    reinterpret_cast<const unsigned long long *>(d_n_records), (unsigned long long)rec_out_cap,
+                                                    reinterpret_cast<const unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
+                                                    reinterpret_cast<unsigned long long *>(d_abort));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64_t *d_next_contigs, int from, int count,
+                              mc_call *d_row_out, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first, int64_t n_sites,
+                              uint64_t *d_row_base, void *stream) {
+    MC_REQUIRE(d_carry && d_row_out, "null pointer");
+    MC_REQUIRE(!d_depth || (d_meth && d_first), "histogram needs depth, meth and first");
+    k_carry_close<<<1, 1, 0, (cudaStream_t)stream>>>(d_carry, closing_contig, reinterpret_cast<const long long *>(d_next_contigs), from, count,
+                                                    d_row_out, d_depth, d_meth, reinterpret_cast<unsigned long long *>(d_first), n_sites,
+                                                    reinterpret_cast<unsigned long long *>(d_row_base));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+}
+
+extern "C" int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t n_calls /* capacity */, const mc_model *models,
+                           void *stream) {
+    MC_REQUIRE(d_calls && d_nrows && models, "null pointer");
     if (n_calls <= 0) return MC_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_nrows);
     const mc_model &m0 = models[0], &m1 = models[1];
     MC_REQUIRE(m0.n_in >= 1 && m0.n_in <= MC_MAXK + 1, "model input width out of range");
     switch (m0.kind) {
@@ -371,18 +589,18 @@ extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *mo
                 int64_t b2 = (n_calls + WARPS * 8 - 1) / (WARPS * 8);
                 if (b2 > (int64_t)sms * 8) b2 = (int64_t)sms * 8;
                 MC_CUDA_CHECK(cudaFuncSetAttribute(k_mlp_1hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)weight_bytes));
-                k_mlp_1hidden<<<(unsigned)b2, WARPS * 32, weight_bytes, st>>>(d_calls, n_calls, m0, m1, nw0, nb0, nw1, nb1, alias);
+                k_mlp_1hidden<<<(unsigned)b2, WARPS * 32, weight_bytes, st>>>(d_calls, n_calls, dn, m0, m1, nw0, nb0, nw1, nb1, alias);
             } else if (staged_bytes <= 100 * 1024) {
                 MC_CUDA_CHECK(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
-                k_mlp<true><<<(unsigned)blocks, WARPS * 32, staged_bytes, st>>>(d_calls, n_calls, m0, m1, width, nw0, nb0, nw1, nb1, alias);
+                k_mlp<true><<<(unsigned)blocks, WARPS * 32, staged_bytes, st>>>(d_calls, n_calls, dn, m0, m1, width, nw0, nb0, nw1, nb1, alias);
             } else {
-                k_mlp<false><<<(unsigned)blocks, WARPS * 32, act_bytes, st>>>(d_calls, n_calls, m0, m1, width, 0, 0, 0, 0, 0);
+                k_mlp<false><<<(unsigned)blocks, WARPS * 32, act_bytes, st>>>(d_calls, n_calls, dn, m0, m1, width, 0, 0, 0, 0, 0);
             }
             break;
         }
         case MC_LR:
         case MC_GNB:
-            k_linear<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(d_calls, n_calls, m0, m1);
+            k_linear<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(d_calls, n_calls, dn, m0, m1);
             break;
         case MC_RF: {
             int mx = m0.max_nodes > m1.max_nodes ? m0.max_nodes : m1.max_nodes;
@@ -390,7 +608,7 @@ extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *mo
             const size_t smem = (size_t)mx * (8 + 8 + 4 + 4 + 4);
             MC_REQUIRE(smem <= 200 * 1024, "RF tree too large for shared-memory staging");
             MC_CUDA_CHECK(cudaFuncSetAttribute(k_rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_rf<<<(unsigned)((n_calls + 255) / 256), 256, smem, st>>>(d_calls, n_calls, m0, m1, mx);
+            k_rf<<<(unsigned)((n_calls + 255) / 256), 256, smem, st>>>(d_calls, n_calls, dn, m0, m1, mx);
             break;
         }
         default:
@@ -400,13 +618,19 @@ extern "C" int mc_classify(mc_call *d_calls, int64_t n_calls, const mc_model *mo
     return MC_OK;
 }
 
-extern "C" int mc_hist_accumulate(const mc_call *d_calls, int64_t n_calls, uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first,
-                                  int64_t n_sites, uint64_t row_base, uint64_t *d_skipped, void *stream) {
-    MC_REQUIRE(d_calls && d_depth && d_meth && d_first && d_skipped, "null pointer");
-    if (n_calls <= 0) return MC_OK;
-    k_hist<<<(unsigned)((n_calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_calls, n_calls, d_depth, d_meth, reinterpret_cast<unsigned long long *>(d_first), n_sites,
-        (unsigned long long)row_base, reinterpret_cast<unsigned long long *>(d_skipped));
+extern "C" int mc_hist_accumulate(const mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, uint32_t *d_depth, uint32_t *d_meth,
+                                  uint64_t *d_first, int64_t n_sites, uint64_t *d_row_base, mc_call *d_odd, int64_t odd_cap,
+                                  uint64_t *d_n_odd, const uint64_t *d_abort, void *stream) {
+    MC_REQUIRE(d_calls && d_nrows && d_depth && d_meth && d_first && d_row_base && d_odd && d_n_odd, "null pointer");
+    if (row_cap <= 0) return MC_OK;
+    k_hist<<<(unsigned)((row_cap + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_calls, row_cap, reinterpret_cast<const unsigned long long *>(d_nrows), d_depth, d_meth,
+        reinterpret_cast<unsigned long long *>(d_first), n_sites, reinterpret_cast<const unsigned long long *>(d_row_base), d_odd,
+        (unsigned long long)odd_cap, reinterpret_cast<unsigned long long *>(d_n_odd), reinterpret_cast<const unsigned long long *>(d_abort));
+    MC_LAUNCH_CHECK();
+    k_advance_base<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(d_row_base),
+                                                      reinterpret_cast<const unsigned long long *>(d_nrows),
+                                                      reinterpret_cast<const unsigned long long *>(d_abort));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

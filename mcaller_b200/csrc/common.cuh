@@ -68,4 +68,12 @@ __device__ __forceinline__ int mc_block_exscan(int v, int *s_warp /* [THREADS/32
 // generic device exclusive scan (uint32 in -> uint32 out), see scan_util.cu
 int mc_exscan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total /* may be null */, void *d_ws,
                   cudaStream_t st);
+int mc_exscan_u32_dev(const uint32_t *d_in, uint32_t *d_out, int64_t n_cap, const uint64_t *d_n, uint64_t *d_total, void *d_ws,
+                      cudaStream_t st);
 int64_t mc_exscan_ws_bytes(int64_t n);
+
+// item count kept on the device (stage outputs), clamped to the capacity the launch was sized for
+__device__ __forceinline__ int64_t mc_dev_count(const unsigned long long *d_n, int64_t cap) {
+    const unsigned long long v = *d_n;
+    return v < (unsigned long long)cap ? (int64_t)v : cap;
+}

@@ -77,6 +77,8 @@ namespace {
 struct FormatArgs {
     const mc_call *h_calls;
     const uint8_t *h_text;
+    const uint8_t *carry_name;
+    int32_t carry_name_len;
     const char *const *contig_names, *const *marked_fwd, *const *marked_rev;
     const int64_t *contig_len;
     int32_t n_contigs, k, with_prob;
@@ -95,22 +97,34 @@ int64_t format_range(const FormatArgs &A, int64_t lo, int64_t hi, std::string &d
         const int64_t a = (int64_t)c.mpos - A.k + 1, b = (int64_t)c.mpos + A.k;
         if (a < 0 || b > A.contig_len[c.win_contig]) { err_row = i; err_flags = -2; return MC_EINVAL; }
         const size_t name_len = strlen(A.contig_names[c.chrom_contig]);
-        if (name_len + (size_t)c.read_len + 1024 > sizeof(line)) {          // unusually long names: straight into the string
+        // the read name: bytes of this chunk's text, or (a window carried over a chunk edge) the name the caller kept
+        const char *read = reinterpret_cast<const char *>(A.h_text) + c.read_off;
+        size_t read_len = (size_t)c.read_len;
+        if (c.read_off < 0) {
+            if (!A.carry_name) { err_row = i; err_flags = -4; return MC_EINVAL; }
+            read = reinterpret_cast<const char *>(A.carry_name);
+            read_len = (size_t)A.carry_name_len;
+        }
+        if (name_len + read_len + 1024 > sizeof(line)) {                    // unusually long names: straight into the string
             dst.append(A.contig_names[c.chrom_contig], name_len);
             dst.push_back('\t');
-            dst.append(reinterpret_cast<const char *>(A.h_text) + c.read_off, (size_t)c.read_len);
+            dst.append(read, read_len);
         }
         Out o{line, line + sizeof(line)};
-        if (name_len + (size_t)c.read_len + 1024 <= sizeof(line)) {
+        if (name_len + read_len + 1024 <= sizeof(line)) {
             o.put(A.contig_names[c.chrom_contig], name_len);
             o.put('\t');
-            o.put(reinterpret_cast<const char *>(A.h_text) + c.read_off, (size_t)c.read_len);
+            o.put(read, read_len);
         }
         o.put('\t');
         put_int(o, c.mpos);
         o.put('\t');
         // context = revcomp(last_ref[mpos-k+1 : mpos+k], last_rev)   (extract_contexts.py:194)
-        for (int64_t j = 0; j < b - a; ++j) o.put(c.rev ? comp(src[b - 1 - j]) : src[a + j]);
+        for (int64_t j = 0; j < b - a; ++j) {
+            const char ch = c.rev ? comp(src[b - 1 - j]) : src[a + j];
+            if (ch == 0) { err_row = i; err_flags = -5; return MC_EINVAL; }   // revcomp of a letter outside ACGTNM (:11-15 KeyError)
+            o.put(ch);
+        }
         o.put('\t');
         for (int j = 0; j <= A.k; ++j) {
             if (j) o.put(',');
@@ -133,19 +147,22 @@ int64_t format_range(const FormatArgs &A, int64_t lo, int64_t hi, std::string &d
 
 }  // namespace
 
-extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const char *const *contig_names,
-                                  const char *const *marked_fwd, const char *const *marked_rev, const int64_t *contig_len,
-                                  int32_t n_contigs, int32_t k, const char *base_label, const char *mod_label, int32_t with_prob,
-                                  char *out, int64_t out_cap) {
+extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const uint8_t *h_text, const uint8_t *carry_name,
+                                  int32_t carry_name_len, const char *const *contig_names, const char *const *marked_fwd,
+                                  const char *const *marked_rev, const int64_t *contig_len, int32_t n_contigs, int32_t k,
+                                  const char *base_label, const char *mod_label, int32_t with_prob, int32_t max_threads, char *out,
+                                  int64_t out_cap) {
     if (!h_calls || !h_text || !contig_names || !marked_fwd || !marked_rev || !contig_len || !out || k < 1 || k > MC_MAXK ||
         !base_label || !mod_label || strlen(base_label) > 256 || strlen(mod_label) > 256) {
         mc_set_error("mc_format_rows: bad argument");
         return MC_EINVAL;
     }
-    const FormatArgs A{h_calls, h_text, contig_names, marked_fwd, marked_rev, contig_len, n_contigs, k, with_prob, base_label, mod_label};
+    const FormatArgs A{h_calls, h_text, carry_name, carry_name_len, contig_names, marked_fwd, marked_rev, contig_len, n_contigs, k, with_prob,
+                       base_label, mod_label};
     // one host thread per ~2k rows (a thread costs ~20 us to start, 2k rows ~2 ms to render), at most the hardware concurrency
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
+    if (max_threads > 0 && (unsigned)max_threads < hw) hw = (unsigned)max_threads;
     int nt = (int)((n_calls + 2047) / 2048);
     if (nt > (int)hw) nt = (int)hw;
     if (nt < 1) nt = 1;
@@ -171,6 +188,10 @@ extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const
                          (unsigned)eflags[(size_t)t]);
         else if (eflags[(size_t)t] == -1) mc_set_error("mc_format_rows: contig index out of range");
         else if (eflags[(size_t)t] == -2) mc_set_error("mc_format_rows: context out of range");
+        else if (eflags[(size_t)t] == -4) mc_set_error("mc_format_rows: row %lld was carried over a chunk edge but no read name was given", (long long)erow[(size_t)t]);
+        else if (eflags[(size_t)t] == -5)
+            mc_set_error("mc_format_rows: the context of row %lld (position %d) covers a reference letter outside ACGTNM", (long long)erow[(size_t)t],
+                         h_calls[erow[(size_t)t]].mpos);
         else mc_set_error("mc_format_rows: row too long");
         return rc[(size_t)t];
     }

@@ -9,9 +9,18 @@ constexpr int SCAN_IPT = 8;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_IPT;
 
 // ---- generic exclusive scan over uint32 (input may be strided) -----------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ in, int64_t stride, int64_t n,
+// the item count may live on the device (d_n != nullptr): n is then only the capacity the grid was sized for
+__device__ __forceinline__ int64_t dev_count(const unsigned long long *d_n, int64_t cap) {
+    if (!d_n) return cap;
+    const unsigned long long v = *d_n;
+    return v < (unsigned long long)cap ? (int64_t)v : cap;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ in, int64_t stride, int64_t n_cap,
+                                                            const unsigned long long *__restrict__ d_n,
                                                             unsigned long long *__restrict__ block_sums) {
     __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    const int64_t n = dev_count(d_n, n_cap);
     const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
     unsigned long long acc = 0ull;
 #pragma unroll
@@ -68,10 +77,13 @@ __global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long *__restri
     if (threadIdx.x == 0 && d_total) *d_total = s_carry;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const uint32_t *__restrict__ in, int64_t stride, int64_t n,
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const uint32_t *__restrict__ in, int64_t stride, int64_t n_cap,
+                                                          const unsigned long long *__restrict__ d_n,
                                                           const unsigned long long *__restrict__ block_sums,
                                                           uint32_t *__restrict__ out) {
     __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    const int64_t n = dev_count(d_n, n_cap);
+    if ((int64_t)blockIdx.x * SCAN_BLOCK >= n) return;           // whole block beyond the count (block-uniform)
     // thread owns SCAN_IPT consecutive items so the scan order is the index order
     const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
@@ -97,25 +109,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const uint32_t *__re
 
 int64_t mc_exscan_ws_bytes(int64_t n) { return ((n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 8 + 256; }
 
-static int exscan_strided(const uint32_t *d_in, int64_t stride, uint32_t *d_out, int64_t n, uint64_t *d_total, void *d_ws,
-                          cudaStream_t st) {
+static int exscan_strided(const uint32_t *d_in, int64_t stride, uint32_t *d_out, int64_t n, const uint64_t *d_n, uint64_t *d_total,
+                          void *d_ws, cudaStream_t st) {
     if (n <= 0) {
         if (d_total) MC_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 8, st));
         return MC_OK;
     }
     const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     unsigned long long *sums = reinterpret_cast<unsigned long long *>(d_ws);
-    k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, sums);
+    const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n);
+    k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, dn, sums);
     MC_LAUNCH_CHECK();
     k_scan_sums<<<1, 1024, 0, st>>>(sums, nb, reinterpret_cast<unsigned long long *>(d_total));
     MC_LAUNCH_CHECK();
-    k_scan_down<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, sums, d_out);
+    k_scan_down<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, stride, n, dn, sums, d_out);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
 int mc_exscan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total, void *d_ws, cudaStream_t st) {
-    return exscan_strided(d_in, 1, d_out, n, d_total, d_ws, st);
+    return exscan_strided(d_in, 1, d_out, n, nullptr, d_total, d_ws, st);
+}
+// n = capacity, the item count is read from d_n on the device (items beyond it count as zero)
+int mc_exscan_u32_dev(const uint32_t *d_in, uint32_t *d_out, int64_t n_cap, const uint64_t *d_n, uint64_t *d_total, void *d_ws,
+                      cudaStream_t st) {
+    return exscan_strided(d_in, 1, d_out, n_cap, d_n, d_total, d_ws, st);
 }
 
 // workspace layout used by the stages: [A: uint32 n][B: uint32 n][scan sums]
@@ -136,9 +154,16 @@ namespace {
 // With all chunks done the predecessor is known (every chunk reports the state of the last kept line seen so far in its
 // run): the record is dropped unless the previous kept line was a candidate (or there is none, so the first kept line of
 // the text stays: it may close a window handed over by the caller).
-__global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ tile_tab, int64_t n_tiles, uint32_t *__restrict__ cnt_clean) {
+__global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ tile_tab, int64_t n_tiles, uint32_t *__restrict__ cnt_clean,
+                                                        const unsigned long long *__restrict__ scan_counters, unsigned long long rec_in_cap) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_tiles) return;
+    // stage 1 ran out of record slots: its buffer has unwritten records.  Nothing is ordered (zero records come out), the
+    // caller sees the overflow in the counters and runs the chunk again with a larger buffer.
+    if (scan_counters && (scan_counters[MC_C_OVERFLOW] != 0ull || scan_counters[MC_C_RECORDS] > rec_in_cap)) {
+        cnt_clean[c] = 0u;
+        return;
+    }
     const uint32_t v = tile_tab[2 * c + 1];
     uint32_t count = v & 0xFFFFu;
     if ((v >> 16) & 1u) {
@@ -280,14 +305,14 @@ __device__ __forceinline__ bool bytes_differ(const uint8_t *pa, const uint8_t *p
 }
 
 __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
-                                                       const unsigned long long *__restrict__ d_n) {
+                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap) {
     // A warp finishes 31 records; lane 0 re-walks the record before them (the previous warp's last) only to know its
     // read-name span, so that every lane can compare its read name with its predecessor's, handed over by one shuffle
     // while both lines are still in L1.  That comparison is the read segmentation flag (MC_RF_NEWREAD).
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long i = warp * 31 + lane - 1;
-    const bool active = i >= 0 && (unsigned long long)i < *d_n;
+    const bool active = i >= 0 && i < dev_count(d_n, rec_cap);
     alignas(16) mc_record r;
     if (active) r = rec[i];
     else { r.line_lo = 0u; r.line_hi = 0; r.name_off = 0; r.name_len = 0; r.flags = 0; r.pos = 0; r.contig = 0; r.event_idx = 0; r.diff = 0.0; }
@@ -383,8 +408,9 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
 }
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n,
-                                                  uint32_t *__restrict__ flags) {
+__global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n_cap,
+                                                  const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ flags) {
+    const int64_t n = dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t f = 1u;
@@ -401,8 +427,10 @@ __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ t
     flags[i] = f;
 }
 
-__global__ void __launch_bounds__(256) k_seg_starts(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ excl, int64_t n,
-                                                   uint32_t *__restrict__ seg_start, const unsigned long long *__restrict__ d_nseg) {
+__global__ void __launch_bounds__(256) k_seg_starts(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ excl, int64_t n_cap,
+                                                   const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ seg_start,
+                                                   const unsigned long long *__restrict__ d_nseg) {
+    const int64_t n = dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flags[i]) seg_start[excl[i]] = (uint32_t)i;
     if (i == 0) seg_start[*d_nseg] = (uint32_t)n;
@@ -410,9 +438,11 @@ __global__ void __launch_bounds__(256) k_seg_starts(const uint32_t *__restrict__
 
 // ---- stage 4: quality lookup -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec,
-                                                    const uint32_t *__restrict__ seg_start, int64_t n_seg,
+                                                    const uint32_t *__restrict__ seg_start, int64_t seg_cap,
+                                                    const unsigned long long *__restrict__ d_nseg,
                                                     const mc_qual_entry *__restrict__ table, unsigned long long mask,
                                                     double *__restrict__ seg_qual, unsigned long long *__restrict__ d_err) {
+    const int64_t n_seg = dev_count(d_nseg, seg_cap);
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const mc_record r = rec[seg_start[s]];
@@ -443,8 +473,8 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 }  // namespace
 
 extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles,
-                                const mc_record *d_rec_in, int64_t rec_in_cap, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out,
-                                void *d_ws, void *stream) {
+                                const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters, mc_record *d_rec_out,
+                                int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
     MC_REQUIRE(d_text && d_tile_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles <= 0) {
@@ -453,7 +483,8 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t 
     }
     uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_tiles);
     const unsigned nb = (unsigned)((n_tiles + 255) / 256);
-    k_resolve_fillers<<<nb, 256, 0, st>>>(d_tile_tab, n_tiles, cnt);
+    k_resolve_fillers<<<nb, 256, 0, st>>>(d_tile_tab, n_tiles, cnt, reinterpret_cast<const unsigned long long *>(d_scan_counters),
+                                          (unsigned long long)rec_in_cap);
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(cnt, dst, n_tiles, d_n_out, ws_s(d_ws, n_tiles), st);
     if (rc) return rc;
@@ -463,40 +494,41 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t 
     // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
     // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
     k_finish_records<<<(unsigned)((rec_out_cap + 247) / 248), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
-                                                                            reinterpret_cast<const unsigned long long *>(d_n_out));
+                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
-extern "C" int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, int64_t n_records, uint32_t *d_seg_start,
-                                uint64_t *d_nseg, void *d_ws, void *stream) {
-    MC_REQUIRE(d_text && d_rec && d_seg_start && d_nseg && d_ws, "null pointer");
+extern "C" int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
+                                uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream) {
+    MC_REQUIRE(d_text && d_rec && d_n_records && d_seg_start && d_nseg && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_records <= 0) {
+    if (rec_cap <= 0) {
         MC_CUDA_CHECK(cudaMemsetAsync(d_nseg, 0, 8, st));
         MC_CUDA_CHECK(cudaMemsetAsync(d_seg_start, 0, 4, st));
         return MC_OK;
     }
-    uint32_t *flags = ws_a(d_ws), *excl = ws_b(d_ws, n_records);
-    const unsigned nb = (unsigned)((n_records + 255) / 256);
-    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, n_records, flags);
+    uint32_t *flags = ws_a(d_ws), *excl = ws_b(d_ws, rec_cap);
+    const unsigned nb = (unsigned)((rec_cap + 255) / 256);
+    const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n_records);
+    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, rec_cap, dn, flags);
     MC_LAUNCH_CHECK();
-    int rc = mc_exscan_u32(flags, excl, n_records, d_nseg, ws_s(d_ws, n_records), st);
+    int rc = mc_exscan_u32_dev(flags, excl, rec_cap, d_n_records, d_nseg, ws_s(d_ws, rec_cap), st);
     if (rc) return rc;
-    k_seg_starts<<<nb, 256, 0, st>>>(flags, excl, n_records, d_seg_start, reinterpret_cast<const unsigned long long *>(d_nseg));
+    k_seg_starts<<<nb, 256, 0, st>>>(flags, excl, rec_cap, dn, d_seg_start, reinterpret_cast<const unsigned long long *>(d_nseg));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
-extern "C" int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, int64_t n_seg,
-                                  const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual, uint64_t *d_err,
-                                  void *stream) {
-    MC_REQUIRE(d_text && d_rec && d_seg_start && d_table && d_seg_qual && d_err, "null pointer");
+extern "C" int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint32_t *d_seg_start, const uint64_t *d_nseg,
+                                  int64_t seg_cap, const mc_qual_entry *d_table, int64_t table_size, double *d_seg_qual,
+                                  uint64_t *d_err, void *stream) {
+    MC_REQUIRE(d_text && d_rec && d_seg_start && d_nseg && d_table && d_seg_qual && d_err, "null pointer");
     MC_REQUIRE(table_size > 0 && (table_size & (table_size - 1)) == 0, "table size must be a power of two");
-    if (n_seg <= 0) return MC_OK;
-    k_seg_quality<<<(unsigned)((n_seg + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_text, d_rec, d_seg_start, n_seg, d_table, (unsigned long long)(table_size - 1), d_seg_qual,
-        reinterpret_cast<unsigned long long *>(d_err));
+    if (seg_cap <= 0) return MC_OK;
+    k_seg_quality<<<(unsigned)((seg_cap + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_text, d_rec, d_seg_start, seg_cap, reinterpret_cast<const unsigned long long *>(d_nseg), d_table,
+        (unsigned long long)(table_size - 1), d_seg_qual, reinterpret_cast<unsigned long long *>(d_err));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

@@ -112,8 +112,10 @@ static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 
 static_assert(ColState::SM_STRIDE == WIN_THREADS, "shared-memory column slices are interleaved by thread");
 
 // first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
-__global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t n_seg,
-                                                mc_refindex R, uint32_t *__restrict__ first_idx, int32_t *__restrict__ first_ind) {
+__global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t seg_cap,
+                                                const unsigned long long *__restrict__ d_nseg, mc_refindex R,
+                                                uint32_t *__restrict__ first_idx, int32_t *__restrict__ first_ind) {
+    const int64_t n_seg = mc_dev_count(d_nseg, seg_cap);
     const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= n_seg) return;
     const uint32_t b = seg_start[seg], e = seg_start[seg + 1];
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ r
 
 template <bool WRITE>
 __global__ void __launch_bounds__(WIN_THREADS)
-k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *__restrict__ seg_start, int64_t n_seg,
+k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned long long *__restrict__ d_n_records,
+          const uint32_t *__restrict__ seg_start, int64_t seg_cap, const unsigned long long *__restrict__ d_nseg,
           const double *__restrict__ seg_qual, const uint32_t *__restrict__ first_idx, const int32_t *__restrict__ first_ind_arr,
           mc_refindex R, int skip_thresh, double qual_thresh, int two_models, mc_call *__restrict__ calls,
           unsigned long long call_cap, uint32_t *__restrict__ unit_cnt /* [n_records], written at unit starts */,
@@ -147,6 +150,12 @@ k_windows(const mc_record *__restrict__ rec, int64_t n_records, const uint32_t *
     __shared__ int64_t s_seg0;
     extern __shared__ __align__(16) double s_cols[];              // write pass: [SROWS][MC_MAXK][WIN_THREADS] first values of each column
     const int k = R.k;
+    // the record / segment counts live on the device; the grid was sized for rec_cap records
+    const int64_t n_records = mc_dev_count(d_n_records, rec_cap), n_seg = mc_dev_count(d_nseg, seg_cap);
+    if ((int64_t)blockIdx.x * WIN_RECS >= n_records || n_seg <= 0) {       // block-uniform
+        if (!WRITE && threadIdx.x == 0) blk_tot[blockIdx.x] = 0u;
+        return;
+    }
     // ---- unit starts among this block's records, compacted in record order ------------------------------------------------
     int nu;
     {
@@ -455,40 +464,44 @@ __global__ void k_check_cap(const unsigned long long *d_ncalls, unsigned long lo
 
 }  // namespace
 
-extern "C" int mc_build_windows(const mc_record *d_rec, int64_t n_records, const uint32_t *d_seg_start, int64_t n_seg,
-                                const double *d_seg_qual, const mc_refindex *ref, int skip_thresh, double qual_thresh,
-                                int two_models, mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count, uint64_t *d_ncalls,
-                                void *d_ws, void *stream) {
-    MC_REQUIRE(d_rec && d_seg_start && d_seg_qual && ref && d_calls && d_seg_count && d_ncalls && d_ws, "null pointer");
+extern "C" int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap, const uint32_t *d_seg_start,
+                                const uint64_t *d_nseg, int64_t seg_cap, const double *d_seg_qual, const mc_refindex *ref,
+                                int skip_thresh, double qual_thresh, int two_models, mc_call *d_calls, int64_t call_cap,
+                                uint32_t *d_seg_count, uint64_t *d_ncalls, void *d_ws, void *stream) {
+    MC_REQUIRE(d_rec && d_n_records && d_seg_start && d_nseg && d_seg_qual && ref && d_calls && d_seg_count && d_ncalls && d_ws,
+               "null pointer");
     MC_REQUIRE(ref->k >= 1 && ref->k <= MC_MAXK, "k out of range");
     MC_REQUIRE(skip_thresh >= 0, "skip_thresh must be >= 0");
     cudaStream_t st = (cudaStream_t)stream;
     MC_CUDA_CHECK(cudaMemsetAsync(d_ncalls, 0, 16, st));
-    if (n_seg <= 0 || n_records <= 0) return MC_OK;
-    MC_REQUIRE(n_records < (1ll << 32), "record count must fit 32 bits");
-    // workspace: [unit_cnt: u32 n_records][first_ind: i32 n_seg][blk_tot, blk_off: u32 nb each][scan sums]
-    const int64_t nb = (n_records + WIN_RECS - 1) / WIN_RECS;
+    if (seg_cap <= 0 || rec_cap <= 0) return MC_OK;
+    MC_REQUIRE(rec_cap < (1ll << 32), "record count must fit 32 bits");
+    if (seg_cap > rec_cap) seg_cap = rec_cap;                       // a segment holds at least one record
+    const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n_records);
+    const unsigned long long *ds = reinterpret_cast<const unsigned long long *>(d_nseg);
+    // workspace: [unit_cnt: u32 rec_cap][first_ind: i32 seg_cap][blk_tot, blk_off: u32 nb each][scan sums]
+    const int64_t nb = (rec_cap + WIN_RECS - 1) / WIN_RECS;
     auto up = [](int64_t bytes) { return ((bytes + 255) / 256) * 256; };
     uint8_t *w = reinterpret_cast<uint8_t *>(d_ws);
     uint32_t *unit_cnt = reinterpret_cast<uint32_t *>(w);
-    int32_t *first_ind = reinterpret_cast<int32_t *>(w + up(n_records * 4));
-    uint32_t *blk_tot = reinterpret_cast<uint32_t *>(w + up(n_records * 4) + up(n_seg * 4));
+    int32_t *first_ind = reinterpret_cast<int32_t *>(w + up(rec_cap * 4));
+    uint32_t *blk_tot = reinterpret_cast<uint32_t *>(w + up(rec_cap * 4) + up(seg_cap * 4));
     uint32_t *blk_off = blk_tot + nb;
-    void *scan_ws = w + up(n_records * 4) + up(n_seg * 4) + up(2 * nb * 4);
-    uint32_t *first_idx = d_seg_count;                             // caller's n_seg-sized scratch
-    k_first_m<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, n_seg, *ref, first_idx, first_ind);
+    void *scan_ws = w + up(rec_cap * 4) + up(seg_cap * 4) + up(2 * nb * 4);
+    uint32_t *first_idx = d_seg_count;                             // caller's seg_cap-sized scratch
+    k_first_m<<<(unsigned)((seg_cap + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, seg_cap, ds, *ref, first_idx, first_ind);
     MC_LAUNCH_CHECK();
-    k_windows<false><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
-                                                          skip_thresh, qual_thresh, two_models, d_calls, (unsigned long long)call_cap,
-                                                          unit_cnt, blk_tot, nullptr);
+    k_windows<false><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx, first_ind,
+                                                          *ref, skip_thresh, qual_thresh, two_models, d_calls,
+                                                          (unsigned long long)call_cap, unit_cnt, blk_tot, nullptr);
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(blk_tot, blk_off, nb, d_ncalls, scan_ws, st);
     if (rc) return rc;
     constexpr size_t cols_bytes = sizeof(double) * SROWS * MC_MAXK * WIN_THREADS;
     MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_bytes));
-    k_windows<true><<<(unsigned)nb, WIN_THREADS, cols_bytes, st>>>(d_rec, n_records, d_seg_start, n_seg, d_seg_qual, first_idx, first_ind, *ref,
-                                                         skip_thresh, qual_thresh, two_models, d_calls, (unsigned long long)call_cap,
-                                                         unit_cnt, nullptr, blk_off);
+    k_windows<true><<<(unsigned)nb, WIN_THREADS, cols_bytes, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx,
+                                                                  first_ind, *ref, skip_thresh, qual_thresh, two_models, d_calls,
+                                                                  (unsigned long long)call_cap, unit_cnt, nullptr, blk_off);
     MC_LAUNCH_CHECK();
     k_check_cap<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
                                  reinterpret_cast<unsigned long long *>(d_ncalls) + 1);

@@ -178,7 +178,10 @@ def _fmt(x):
 
 
 class _RowFormatter(object):
-    """Turns device rows into the reference's `.diffs.<k>` text rows (writer :216) and keeps the counters (:295-301)."""
+    """Turns device rows into the reference's `.diffs.<k>` text rows (writer :216) and keeps the counters (:295-301).
+
+    Row 0 of every chunk is the slot of the window carried over the chunk edge (mc_carry_rows): kind MC_NONE when empty,
+    else the completed row whose read name (read_off < 0) was kept here when the open row went by."""
 
     def __init__(self, refindex, k, base, train, pos_label, have_model):
         self.ref, self.k, self.base = refindex, k, base
@@ -187,7 +190,7 @@ class _RowFormatter(object):
         self.n_obs = 0
         self.pos_set, self.multi, self.wskips, self.toomany = set(), set(), set(), set()
         self.signals, self.contexts = {}, {}
-        self.pending = None        # (call fields, read name, segment key) awaiting the contig of the next kept line
+        self.pending = None        # (read name, segment key) of the window that is open across a chunk edge
         self.seg_base = 0
         self._native = None        # ctypes argument pack of mc_format_rows, built on first use
 
@@ -199,8 +202,6 @@ class _RowFormatter(object):
             raise ReferenceAbort("base after target %d is not one of ACGTM (reference: KeyError -> sys.exit, :218-223)" % mpos)
         if err & 4:
             raise ValueError("unsupported numeric field in a line feeding the window at %d" % mpos)
-        if err & 8:
-            raise ReferenceAbort("more than 128 events in one column at %d" % mpos)
         if err & 16:
             raise ReferenceAbort("n diffs off (multi-M spacing 0) at %d" % mpos)
 
@@ -235,79 +236,94 @@ class _RowFormatter(object):
         if self._native is None:
             names = self.ref.names
             n = len(names)
-            keep = [nm.encode() for nm in names] + [self.ref.marked[nm][0].encode() for nm in names] + [self.ref.marked[nm][1].encode() for nm in names]
+            keep = [nm.encode() for nm in names] + list(self.ref.marked_bytes(0)) + list(self.ref.marked_bytes(1))
             self._native = dict(keep=keep, names=(C.c_char_p * n)(*keep[:n]), fwd=(C.c_char_p * n)(*keep[n:2 * n]),
-                                rev=(C.c_char_p * n)(*keep[2 * n:]), lens=(C.c_int64 * n)(*[len(self.ref.marked[nm][0]) for nm in names]), n=n)
+                                rev=(C.c_char_p * n)(*keep[2 * n:]), lens=(C.c_int64 * n)(*[len(x) for x in keep[n:2 * n]]), n=n)
         return self._native
 
-    def consume_bytes(self, calls, text, first_kept_contig, n_segments):
-        """Like consume() but returns the rows as bytes, rendered by the native writer (mc_format_rows); counters are
-        updated with vectorised numpy operations.  Inference mode only."""
+    def _segkeys(self, calls):
+        """Segment key of every row: chunk-local segment + the segments of earlier chunks; the carried row keeps the key it
+        had when it was opened."""
+        segkey = calls["seg"].astype(np.int64) + self.seg_base
+        carried = calls["read_off"] < 0
+        if carried.any():
+            segkey[carried] = self.pending[1] if self.pending is not None else -1
+        return segkey
+
+    def consume_bytes(self, calls, text, n_segments):
+        """Rows of one chunk (host structured array, slot 0 first) -> bytes of `.diffs` text rendered by the native writer
+        (mc_format_rows); counters are updated with vectorised numpy operations.  Inference mode only."""
         import ctypes as C
         from . import _lib
-        head = b""
-        if self.pending is not None and first_kept_contig is not None:
-            rows = self.consume(calls[:0], text, first_kept_contig, 0)
-            head = b"".join(("\t".join(r) + "\n").encode() for r in rows)
         n = len(calls)
         if n == 0:
             self.seg_base += n_segments
-            return head
+            return b""
         kind = calls["kind"]
-        pend = calls["close_rec"] == 0xFFFFFFFF
-        segkey = calls["seg"].astype(np.int64) + self.seg_base
+        pend = calls["close_rec"] == _lib.PENDING
+        segkey = self._segkeys(calls)
         pair = (segkey << 32) | calls["mpos"].astype(np.int64)
-        closed0 = (kind == 0) & ~pend
-        self.multi.update(np.unique(pair[kind == 2]).tolist())
-        self.toomany.update(np.unique(pair[(kind == 1) & ~pend]).tolist())
+        closed0 = (kind == _lib.MC_CALL) & ~pend
+        self.multi.update(np.unique(pair[kind == _lib.MC_MULTI_M]).tolist())
+        self.toomany.update(np.unique(pair[(kind == _lib.MC_TOO_MANY_SKIPS) & ~pend]).tolist())
         self.wskips.update(np.unique(pair[closed0 & (calls["n_empty"] > 0)]).tolist())
         self.pos_set.update(np.unique(calls["mpos"][closed0]).tolist())
         self.n_obs += int(closed0.sum())
-        for c in calls[pend & (kind != 2)]:                      # at most one per chunk: keep for the next chunk
-            ro = int(c["read_off"])
-            self.pending = (c.copy(), bytes(text[ro:ro + int(c["read_len"])]), self.seg_base + int(c["seg"]))
+        name, nlen = (self.pending[0], len(self.pending[0])) if self.pending is not None else (None, 0)
         a = self._native_args()
         L = _lib.lib()
-        cap = int(closed0.sum()) * (96 + 26 * (self.k + 1) + int(calls["read_len"].max())) + 4096
+        cap = int(closed0.sum()) * (96 + 26 * (self.k + 1) + max(int(calls["read_len"].max()), nlen)) + 4096
         out = C.create_string_buffer(cap)
         if isinstance(text, np.ndarray):             # pinned host buffer of the streaming path: no copy
             tbuf = C.c_void_p(text.ctypes.data)
         else:
-            tbuf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
+            tbuf = (C.c_char * max(len(text), 1)).from_buffer_copy(text or b"\0") if not isinstance(text, (bytes, bytearray)) else text
         calls_c = np.ascontiguousarray(calls)
-        r = L.mc_format_rows(calls_c.ctypes.data_as(C.c_void_p), n, tbuf, a["names"], a["fwd"], a["rev"], a["lens"], a["n"], self.k,
-                             self.base.encode(), self.mod_label.encode(), 1 if self.have_model else 0, out, cap)
+        r = L.mc_format_rows(calls_c.ctypes.data_as(C.c_void_p), n, tbuf, name, nlen, a["names"], a["fwd"], a["rev"], a["lens"], a["n"], self.k,
+                             self.base.encode(), self.mod_label.encode(), 1 if self.have_model else 0, 0, out, cap)
         if r <= -100:
             bad = calls[closed0 & (calls["err"] != 0)][0]
             self._check(int(bad["err"]), int(bad["mpos"]))
         if r < 0:
-            _lib.check(int(r))
+            try:
+                _lib.check(int(r))
+            except _lib.McallerCudaError as e:
+                if "outside ACGTNM" in str(e):
+                    raise KeyError(str(e))               # the reference: KeyError in revcomp (:11-15)
+                raise
+        if kind[0] != _lib.MC_NONE and calls["read_off"][0] < 0:
+            self.pending = None                          # the carried window is written (or counted)
+        last = calls[n - 1]
+        if pend[n - 1] and kind[n - 1] != _lib.MC_MULTI_M and last["read_off"] >= 0:
+            ro = int(last["read_off"])
+            self.pending = (bytes(text[ro:ro + int(last["read_len"])]), int(segkey[n - 1]))
         self.seg_base += n_segments
-        return head + out.raw[:r]
+        return out.raw[:r]
 
-    def consume(self, calls, text, first_kept_contig, n_segments):
-        """Rows of one chunk (host structured array) -> list of row lists.  `first_kept_contig`: contig index of the
-        first kept line of this chunk (it closes a window left pending by the previous chunk), or None."""
+    def consume(self, calls, text, n_segments):
+        """Rows of one chunk (host structured array, slot 0 first) -> list of row lists (Python path: training mode)."""
+        from . import _lib
         out = []
-        if self.pending is not None and first_kept_contig is not None:
-            pc, pread, pkey = self.pending
-            if int(pc["kind"]) == 0:
-                out.append(self._row(pc, pread, pkey, first_kept_contig))
-            else:
-                self.toomany.add((pkey << 32) | int(pc["mpos"]))
-            self.pending = None
         for c in calls:
             kind = int(c["kind"])
-            segkey = self.seg_base + int(c["seg"])
-            if kind == 2:
+            if kind == _lib.MC_NONE:
+                continue
+            carried = int(c["read_off"]) < 0
+            if carried:
+                read, segkey = self.pending
+                self.pending = None
+            else:
+                segkey = self.seg_base + int(c["seg"])
+            if kind == _lib.MC_MULTI_M:
                 self.multi.add((segkey << 32) | int(c["mpos"]))
                 continue
-            ro = int(c["read_off"])
-            read = bytes(text[ro:ro + int(c["read_len"])])
-            if int(c["close_rec"]) == 0xFFFFFFFF:
-                self.pending = (c.copy(), read, segkey)      # still open at the end of the chunk
+            if not carried:
+                ro = int(c["read_off"])
+                read = bytes(text[ro:ro + int(c["read_len"])])
+            if int(c["close_rec"]) == _lib.PENDING:
+                self.pending = (read, segkey)                # still open at the end of the chunk
                 continue
-            if kind == 1:
+            if kind == _lib.MC_TOO_MANY_SKIPS:
                 self.toomany.add((segkey << 32) | int(c["mpos"]))
                 continue
             out.append(self._row(c, read, segkey, int(c["chrom_contig"])))
@@ -315,22 +331,154 @@ class _RowFormatter(object):
         return out
 
 
-def _first_kept_contig(engine, res, qual_thresh):
-    """Contig index of the first kept line of the chunk just processed (first ordered record of a segment that
-    passes the quality filter), or None."""
-    if res.n_records == 0:
-        return None
-    if qual_thresh <= 0:
-        return int(engine.records(1)[0]["contig"])
+def _select_device(startline, endline):
+    """the reference's `-t N` workers (mCaller.py:63-70) own the byte ranges [chunk*i, chunk*(i+1)); worker i
+    runs on GPU i mod n_gpus.  MCALLER_B200_DEVICE pins the device instead (one process per GPU launchers set it)."""
     import torch
-    nseg = res.n_segments
-    q = engine._bufs["seg_qual"][: 8 * nseg].view(torch.float64)
-    ok = (~(q < qual_thresh)).nonzero()
-    if ok.numel() == 0:
-        return None
-    s = int(ok[0])
-    start = int(engine._bufs["seg_start"][: 4 * (nseg + 1)].view(torch.int32)[s])
-    return int(engine.records(start + 1)[start]["contig"])
+    n = torch.cuda.device_count()
+    env = os.environ.get("MCALLER_B200_DEVICE")
+    if env is not None:
+        idx = int(env) % max(n, 1)
+    elif endline is not None and endline > startline and n > 1:
+        idx = int(startline // (endline - startline)) % n
+    else:
+        idx = torch.cuda.current_device()
+    torch.cuda.set_device(idx)
+    return idx
+
+
+class RangeRun(object):
+    """One worker's byte range of an eventalign file on one GPU: reference index, models, engine and row formatter, the
+    streaming of the range into `<prefix>.diffs.<k>[.train].tmp<startline>` and the ways its last open window gets closed
+    (probing the text after the range -- forked workers that cannot talk to each other -- or the next rank's first kept
+    line in a multi-GPU run, mcaller_b200.multigpu)."""
+
+    def __init__(self, tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thresh, modelfile, startline, endline=None, train=False,
+                 pos_label=None, base=None, motif=None, positions_list=None, histogram=False, row_base=0):
+        from . import engine as _engine, models as _models, read_qual as _rq
+        from .refindex import ReferenceIndex
+        _engine.require_cuda()
+        self.device_index = _select_device(startline, endline)
+        self.k = k = int(k)
+        self.train, self.tsv_input, self.qual_thresh = train, tsv_input, qual_thresh
+        seqs = refmark.read_fasta(fasta_input)
+        try:
+            self.ref = ReferenceIndex(seqs, base, motif=motif, positions_file=positions_list, k=k)
+        except refmark.MarkError as e:
+            print(str(e) + " - quitting thread now")
+            raise ReferenceAbort(str(e))
+        dm, two = None, False
+        stem = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k)
+        if not train:
+            self.tsv_output = stem + ".tmp" + str(startline)
+            model = _models.load_model_file(modelfile)
+            e0, e1, two = _models.select_models(model, base)
+            dm = _models.DeviceModels(e0, e1)
+            if dm.n_in != k + 1:
+                raise ValueError("model expects %d inputs but -n %d gives %d" % (dm.n_in, k, k + 1))
+        else:
+            self.tsv_output = stem + ".train.tmp" + str(startline)
+        # read2qual: the reference's dict, or a read_qual.DeviceQualityTable built on the GPU from the FASTQ
+        qt = read2qual if isinstance(read2qual, _rq.DeviceQualityTable) else _rq.build_quality_table(read2qual)
+        if isinstance(qt, _rq.DeviceQualityTable) and qt.table.device.index != self.device_index:
+            qt = _rq.DeviceQualityTable(qt.table.to("cuda:%d" % self.device_index), qt.size, qt.n_records, qt.bad_headers)
+        self.eng = _engine.Engine(self.ref, models=dm, qual_table=qt, skip_thresh=skip_thresh, qual_thresh=qual_thresh, two_models=two,
+                                  histogram=histogram and dm is not None)
+        if row_base:
+            self.eng.reset_stream_state(row_base)
+        self.fmt = _RowFormatter(self.ref, k, base, train, pos_label, dm is not None)
+        self.fsize = os.path.getsize(tsv_input)
+        if endline is None:
+            endline = self.fsize
+        with open(tsv_input, "rb") as fh:
+            self.lo = read_boundary_after(fh, startline, self.fsize)
+            self.hi = read_boundary_after(fh, min(endline, self.fsize), self.fsize)
+        self.bytes_done = 0
+
+    def _write(self, rows):
+        if isinstance(rows, bytes):
+            with open(self.tsv_output, "ab") as outfi:          # append, like writefi (:83-86)
+                outfi.write(rows)
+        else:
+            writefi(rows, self.tsv_output)
+
+    def stream(self):
+        """Rows of the reads whose first line lies in [lo, hi) -> the tmp file."""
+        eng, fmt = self.eng, self.fmt
+        open(self.tsv_output, "a").close()
+        if not self.train:
+            # inference: pipelined path (reader thread -> pinned buffers -> H2D on a side stream -> kernels -> native writer)
+            from . import stream as _stream
+            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before, readers=READ_THREADS)
+            with open(self.tsv_output, "ab") as outfi:
+                for res, text, n in fs.chunks(self.tsv_input, self.lo, self.hi):
+                    _raise_on_counters(res)
+                    outfi.write(fmt.consume_bytes(res.calls(), text, res.n_segments))
+                    self.bytes_done += n
+            return
+        with open(self.tsv_input, "rb") as fh:                  # training export: rows as Python lists (labels, matrices)
+            pos, carry = self.lo, b""
+            while pos < self.hi or carry:
+                want = min(CHUNK_BYTES, self.hi - pos)
+                fh.seek(pos)
+                data = carry + fh.read(want)
+                pos += want
+                if pos < self.hi:
+                    cut = read_boundary_before(data, len(data))
+                    if cut == 0:            # a single read larger than the chunk: keep reading
+                        carry = data
+                        continue
+                    carry, data = data[cut:], data[:cut]
+                else:
+                    carry = b""
+                if not data:
+                    continue
+                res = eng.run_chunk(eng.upload(data), len(data))
+                _raise_on_counters(res)
+                self._write(fmt.consume(res.calls(), data, res.n_segments))
+                self.bytes_done += len(data)
+
+    def close_by_probe(self):
+        """A window still open at the end of the range is closed by the first kept line after it, which lies in the next
+        worker's range (mCaller.py:63-68): keep feeding text from there -- line-aligned pieces, growing -- until the carried
+        window comes back completed as slot 0 (mc_carry_rows); the pieces' own rows belong to the next worker and are
+        ignored, as are its input problems.  At the end of the file nothing closes it (reference: dropped)."""
+        from . import _lib
+        eng, fmt = self.eng, self.fmt
+        if fmt.pending is None or self.hi >= self.fsize:
+            return
+        with open(self.tsv_input, "rb") as fh:
+            ppos, size = self.hi, 4 << 20
+            while fmt.pending is not None and ppos < self.fsize:
+                fh.seek(ppos)
+                probe = fh.read(size)
+                at_eof = ppos + len(probe) >= self.fsize
+                cutp = len(probe) if at_eof else probe.rfind(b"\n") + 1
+                if cutp <= 0:                                  # no complete line in the piece: look at a larger one
+                    size *= 4
+                    continue
+                res = eng.run_chunk(eng.upload(probe[:cutp]), cutp)
+                row0 = res.calls()[:1]
+                if len(row0) and row0[0]["kind"] != _lib.MC_NONE:
+                    self.consume_closed(row0)
+                    return
+                ppos += cutp
+                size = min(size * 2, 1 << 28)
+
+    def consume_closed(self, row):
+        """The carried window, completed (by close_by_probe or Engine.close_carry), goes to the end of the tmp file."""
+        from . import _lib
+        if len(row) and row[0]["kind"] != _lib.MC_NONE:
+            self._write(self.fmt.consume(row, b"", 0) if self.train else self.fmt.consume_bytes(row, b"", 0))
+
+    def print_counters(self):
+        fmt = self.fmt
+        print("thread finished processing...:")
+        print("%d observations" % fmt.n_obs)
+        print("%d positions" % len(fmt.pos_set))
+        print("%d regions with multiple methylated bases" % len(fmt.multi))
+        print("%d observations with skips included" % len(fmt.wskips))
+        print("%d observations with too many skips" % len(fmt.toomany))
 
 
 def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thresh, modelfile, classifier, startline, endline=None,
@@ -340,94 +488,15 @@ def extract_features(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thr
     startline/endline are byte offsets like the reference's (mCaller.py:58, :63-68); a worker owns the reads whose
     first line starts inside [startline, endline) (ranges are snapped to read boundaries instead of the reference's
     '-500 characters / 8 MB overrun' overlap), so concatenating the workers' files in offset order gives
-    exactly the -t 1 output.
+    exactly the -t 1 output.  Worker i of a `-t N` run uses GPU i mod n_gpus.
     """
-    from . import engine as _engine, models as _models, read_qual as _rq
-    from .refindex import ReferenceIndex
-    _engine.require_cuda()
-    k = int(k)
-    seqs = refmark.read_fasta(fasta_input)
-    try:
-        ref = ReferenceIndex(seqs, base, motif=motif, positions_file=positions_list, k=k)
-    except refmark.MarkError as e:
-        print(str(e) + " - quitting thread now")
-        raise ReferenceAbort(str(e))
-    dm, two = None, False
-    if not train:
-        tsv_output = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k) + ".tmp" + str(startline)
-        model = _models.load_model_file(modelfile)
-        e0, e1, two = _models.select_models(model, base)
-        dm = _models.DeviceModels(e0, e1)
-        if dm.n_in != k + 1:
-            raise ValueError("model expects %d inputs but -n %d gives %d" % (dm.n_in, k, k + 1))
-    else:
-        tsv_output = ".".join(tsv_input.split(".")[:-1]) + ".diffs." + str(k) + ".train.tmp" + str(startline)
-    # read2qual: the reference's dict, or a read_qual.DeviceQualityTable built on the GPU from the FASTQ
-    qt = read2qual if isinstance(read2qual, _rq.DeviceQualityTable) else _rq.build_quality_table(read2qual)
-    eng = _engine.Engine(ref, models=dm, qual_table=qt, skip_thresh=skip_thresh, qual_thresh=qual_thresh, two_models=two, histogram=False)
-    fmt = _RowFormatter(ref, k, base, train, pos_label, dm is not None)
-
-    fsize = os.path.getsize(tsv_input)
-    if endline is None:
-        endline = fsize
-    towrite_total = 0
-    with open(tsv_input, "rb") as fh:
-        lo = read_boundary_after(fh, startline, fsize)
-        hi = read_boundary_after(fh, min(endline, fsize), fsize)
-        pos = lo
-        carry = b""
-        open(tsv_output, "a").close()
-        if not train:
-            # inference: pipelined path (reader thread -> pinned buffers -> H2D on a side stream -> kernels -> native writer)
-            from . import stream as _stream
-            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before, readers=READ_THREADS)
-            with open(tsv_output, "ab") as outfi:                  # append, like writefi (:83-86)
-                for res, text, n in fs.chunks(tsv_input, lo, hi):
-                    _raise_on_counters(res)
-                    fk = _first_kept_contig(eng, res, qual_thresh) if fmt.pending is not None else None
-                    outfi.write(fmt.consume_bytes(res.calls(), text, fk, res.n_segments))
-            pos, carry = hi, b""
-        while pos < hi or carry:
-            want = min(CHUNK_BYTES, hi - pos)
-            fh.seek(pos)
-            data = carry + fh.read(want)
-            pos += want
-            if pos < hi:
-                cut = read_boundary_before(data, len(data))
-                if cut == 0:            # a single read larger than the chunk: keep reading
-                    carry = data
-                    continue
-                carry, data = data[cut:], data[:cut]
-            else:
-                carry = b""
-            if not data:
-                continue
-            rows = _run_text(eng, fmt, data, qual_thresh)
-            if isinstance(rows, bytes):
-                with open(tsv_output, "ab") as outfi:          # append, like writefi (:83-86)
-                    outfi.write(rows)
-            else:
-                writefi(rows, tsv_output)
-        # a window still open at the end of my range is closed by the first kept line after it (next worker's range)
-        if fmt.pending is not None and hi < fsize:
-            fh.seek(hi)
-            probe = fh.read(1 << 22)
-            cutp = probe.rfind(b"\n")
-            if cutp >= 0:
-                d_text = eng.upload(probe[:cutp + 1])
-                res = eng.run_chunk(d_text, cutp + 1)
-                _raise_on_counters(res)
-                fk = _first_kept_contig(eng, res, qual_thresh)
-                rows = fmt.consume(np.zeros(0, dtype=_engine.CALL_DTYPE), b"", fk, 0)
-                writefi(rows, tsv_output)
-    print("thread finished processing...:")
-    print("%d observations" % fmt.n_obs)
-    print("%d positions" % len(fmt.pos_set))
-    print("%d regions with multiple methylated bases" % len(fmt.multi))
-    print("%d observations with skips included" % len(fmt.wskips))
-    print("%d observations with too many skips" % len(fmt.toomany))
+    run = RangeRun(tsv_input, fasta_input, read2qual, k, skip_thresh, qual_thresh, modelfile, startline, endline=endline, train=train,
+                   pos_label=pos_label, base=base, motif=motif, positions_list=positions_list)
+    run.stream()
+    run.close_by_probe()
+    run.print_counters()
     if train:
-        return fmt.signals, fmt.contexts
+        return run.fmt.signals, run.fmt.contexts
 
 
 def _raise_on_counters(res):
@@ -436,13 +505,3 @@ def _raise_on_counters(res):
         raise ValueError("%d lines on known contigs have a non-integer position column" % c["badpos"])
     if res.missing_quality:
         raise KeyError("%d reads of the eventalign file are missing from the fastq" % res.missing_quality)
-
-
-def _run_text(eng, fmt, data, qual_thresh):
-    d_text = eng.upload(data)
-    res = eng.run_chunk(d_text, len(data))
-    _raise_on_counters(res)
-    fk = _first_kept_contig(eng, res, qual_thresh) if fmt.pending is not None else None
-    if fmt.train:
-        return fmt.consume(res.calls(), data, fk, res.n_segments)
-    return fmt.consume_bytes(res.calls(), data, fk, res.n_segments)

@@ -88,40 +88,74 @@ def _pos_hash_set(pos_set):
     return tab
 
 
-class _Aggregation(object):
-    """GPU passes over one `.diffs.<k>` file."""
+STREAM_BYTES = int(os.environ.get("MCALLER_B200_BED_CHUNK_BYTES", str(256 << 20)))     # piece size of the streamed `.diffs` file
 
-    def __init__(self, meth_fi, pos_set=None):
+
+def _empty_table(torch, size, dev):
+    init = np.zeros(size, dtype=LOCUS_DTYPE)
+    init["first_off"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    return torch.from_numpy(init.view(np.uint8).reshape(-1)).to(dev)
+
+
+class _Aggregation(object):
+    """GPU passes over one `.diffs.<k>` file.  The default mode streams the file in line-aligned pieces into one device
+    locus table that grows with the loci seen (the reference streams line by line, make_bed.py:75); the modes that need
+    per-read lists (-p, --vo) keep the whole file on the device for their second pass."""
+
+    def __init__(self, meth_fi, pos_set=None, keep_text=False):
         import torch
         from . import _lib, engine
         engine.require_cuda()
         self.torch, self._lib, self.L = torch, _lib, _lib.lib()
         self.path = meth_fi
-        self.data = open(meth_fi, "rb").read()
-        self.n = len(self.data)
-        self.dev = torch.device("cuda")
+        self.n = os.path.getsize(meth_fi)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
         self.loci = []            # (chrom, pos, context, strand, depth, meth) in first-seen order
         self.slots = np.zeros(0, dtype=np.int64)
         self.counters = np.zeros(8, dtype=np.int64)
+        self.data = None
         if self.n == 0:
             return
-        self.d_text = torch.from_numpy(np.frombuffer(self.data, dtype=np.uint8).copy()).to(self.dev)
         self.d_posset = None
         self.posset_size = 0
         if pos_set is not None:
             tab = _pos_hash_set(pos_set)
             self.d_posset = torch.from_numpy(tab.view(np.int64)).to(self.dev)
             self.posset_size = len(tab)
-        size = 1024
-        while size < 2 * (self.n // 48 + 16):
-            size *= 2
-        self.table_size = size
-        init = np.zeros(size, dtype=LOCUS_DTYPE)
-        init["first_off"] = np.uint64(0xFFFFFFFFFFFFFFFF)
-        self.d_table = torch.from_numpy(init.view(np.uint8).reshape(-1)).to(self.dev)
         self.d_cnt = torch.zeros(8, dtype=torch.int64, device=self.dev)
-        _lib.check(self.L.mc_diffs_aggregate_ex(self._p(self.d_text), self.n, self._p(self.d_posset), self.posset_size,
-                                                self._p(self.d_table), size, self._p(self.d_cnt), self._stream()))
+        self.table_size = 1024
+        self.d_table = _empty_table(torch, self.table_size, self.dev)
+        n_loci = 0
+        if keep_text:
+            self.data = open(meth_fi, "rb").read()
+            self.d_text = torch.from_numpy(np.frombuffer(self.data, dtype=np.uint8).copy()).to(self.dev)
+            self._ensure_room(n_loci, self.n)
+            _lib.check(self.L.mc_diffs_aggregate_ex(self._p(self.d_text), self.n, 0, self._p(self.d_posset), self.posset_size,
+                                                    self._p(self.d_table), self.table_size, self._p(self.d_cnt), self._stream()))
+        else:
+            with open(meth_fi, "rb") as fh:
+                base, carry = 0, b""
+                while True:
+                    piece = fh.read(STREAM_BYTES)
+                    buf = carry + piece
+                    if not buf:
+                        break
+                    if piece:
+                        cut = buf.rfind(b"\n") + 1
+                        if cut == 0:                              # no complete line yet
+                            carry = buf
+                            continue
+                    else:
+                        cut = len(buf)                            # last line without a newline
+                    self._ensure_room(n_loci, cut)
+                    d_piece = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8, count=cut).copy()).to(self.dev)
+                    _lib.check(self.L.mc_diffs_aggregate_ex(self._p(d_piece), cut, base, self._p(self.d_posset), self.posset_size,
+                                                            self._p(self.d_table), self.table_size, self._p(self.d_cnt), self._stream()))
+                    n_loci = int((self.d_table.view(torch.int64).view(-1, 3)[:, 0] != 0).sum().item())
+                    base += cut
+                    carry = buf[cut:]
+                    if not piece:
+                        break
         cnt = self.d_cnt.cpu().numpy()
         self.counters = cnt
         if cnt[1]:
@@ -132,11 +166,23 @@ class _Aggregation(object):
         used = np.nonzero(table["hash"] != 0)[0]
         order = np.argsort(table["first_off"][used], kind="stable")
         self.slots = used[order]                              # table slot of each locus, first-seen order
-        for e in table[self.slots]:
-            off = int(e["first_off"])
-            end = self.data.find(b"\n", off)
-            f = self.data[off:end if end >= 0 else self.n].split(b"\t")
-            self.loci.append((f[0].decode(), f[2].decode(), f[3].decode(), f[5].decode(), int(e["depth"]), int(e["meth"])))
+        with open(meth_fi, "rb") as fh:
+            for e in table[self.slots]:
+                fh.seek(int(e["first_off"]))
+                f = fh.readline().rstrip(b"\n").split(b"\t")
+                self.loci.append((f[0].decode(), f[2].decode(), f[3].decode(), f[5].decode(), int(e["depth"]), int(e["meth"])))
+
+    def _ensure_room(self, n_loci, piece_bytes):
+        """The table keeps a load factor <= 0.5 even if every row of the next piece were a new locus (a row is >= 48 bytes)."""
+        need = 2 * (n_loci + piece_bytes // 48 + 16)
+        if self.table_size >= need:
+            return
+        size = self.table_size
+        while size < need:
+            size *= 2
+        new = _empty_table(self.torch, size, self.dev)
+        self._lib.check(self.L.mc_diffs_rehash(self._p(self.d_table), self.table_size, self._p(new), size, self._p(self.d_cnt), self._stream()))
+        self.d_table, self.table_size = new, size
 
     def _p(self, t):
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
@@ -252,7 +298,7 @@ def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control
     if plot or plotsummary:
         raise NotImplementedError("make_bed --plot/--plotsummary are outside the accelerated path")
     pos_set = make_pos_set(pos_list) if pos_list else None
-    agg = _Aggregation(meth_fi, pos_set)
+    agg = _Aggregation(meth_fi, pos_set, keep_text=bool(verbose_results or pos_list))
     loci = agg.loci
     if verbose_results and agg.counters[5]:
         raise ValueError("--vo needs the 8-column format: %d rows of %s have no probability column" % (agg.counters[5], meth_fi))
@@ -261,6 +307,11 @@ def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control
         agg.index_rows()
     if pos_list:
         tests = agg.column_tests()
+    return _write_loci(loci, aggfi, depth_thresh, mod_thresh, pos_list, control, verbose_results, gff, ref, agg, tests)
+
+
+def _write_loci(loci, aggfi, depth_thresh, mod_thresh, pos_list, control, verbose_results, gff, ref, agg=None, tests=None):
+    """Thresholds (check_thresh, make_bed.py:21-28) and the BED / GFF rows (:132-159) for loci in first-seen order."""
     contexts = None
     if ref:
         from . import refmark
@@ -302,6 +353,46 @@ def aggregate_by_pos(meth_fi, aggfi, depth_thresh, mod_thresh, pos_list, control
         else:
             print(count, "unmethylated loci found with min depth", depth_thresh, "reads")
     return count
+
+
+def loci_from_histogram(refindex, depth, meth, first, odd_rows=None):
+    """The per-site histogram of the fused pipeline (mc_hist_accumulate; all-reduced over the ranks of a multi-GPU run)
+    -> list of (chrom, pos, context, strand, depth, meth) in first-seen order, i.e. what make_bed.py:75-98 builds from
+    the `.diffs` rows.  A site slot IS the reference's key (chrom, pos, pos+1, context, strand): the context is a function of
+    contig, position and strand.  `odd_rows` (Engine.odd_rows(), gathered over ranks) are the rows whose column 1 names
+    another contig than their window's (reference quirk, extract_contexts.py:216): they form loci of their own."""
+    depth = np.asarray(depth).astype(np.int64)
+    meth = np.asarray(meth).astype(np.int64)
+    first = np.asarray(first).astype(np.uint64)
+    used = np.flatnonzero(depth > 0)
+    entries = []                                  # (first-seen index, locus tuple)
+    for s_ in used.tolist():
+        ci, pos, rev = int(refindex.site_contig[s_]), int(refindex.site_pos[s_]), bool(refindex.site_rev[s_])
+        entries.append((int(first[s_]), (refindex.names[ci], str(pos), refindex.context(ci, pos, rev), "-" if rev else "+",
+                                         int(depth[s_]), int(meth[s_]))))
+    if odd_rows is not None and len(odd_rows):
+        extra = {}
+        for c in odd_rows:
+            rev = bool(c["rev"])
+            key = (refindex.names[int(c["chrom_contig"])], str(int(c["mpos"])), refindex.context(int(c["win_contig"]), int(c["mpos"]), rev),
+                   "-" if rev else "+")
+            idx = int(c["pad1"]) | (int(c["pad2"]) << 32)
+            e = extra.setdefault(key, [idx, 0, 0])
+            e[0] = min(e[0], idx)
+            e[1] += 1
+            e[2] += int(c["label"])
+        for key, (idx, d_, m_) in extra.items():
+            entries.append((idx, key + (d_, m_)))
+    entries.sort(key=lambda t: t[0])
+    return [e[1] for e in entries]
+
+
+def aggregate_from_histogram(refindex, depth, meth, first, aggfi, depth_thresh, mod_thresh, control=False, gff=False, ref=None,
+                             odd_rows=None):
+    """make_bed.py's default output (also --control / --gff / --ref) straight from the device histogram: no `.diffs` text is
+    parsed.  The modes that need per-read lists (-p, --vo) go through aggregate_by_pos on the `.diffs` file."""
+    loci = loci_from_histogram(refindex, depth, meth, first, odd_rows)
+    return _write_loci(loci, aggfi, depth_thresh, mod_thresh, None, control, False, gff, ref)
 
 
 def output_name(mCaller_file, positions=None, control=False, gff=False):

@@ -26,10 +26,13 @@ class ReferenceIndex(object):
         self.k = k
         self.base = base
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.names = sorted(seqs, key=lambda s: s.encode())
         if len(self.names) >= 65535:
             raise ValueError("too many contigs")
         self.marked = {}
+        self._marked_bytes = None
         bases_g, lens = [], []
         off = 0
         for nm in self.names:
@@ -97,6 +100,13 @@ class ReferenceIndex(object):
 
     def ref(self):
         return C.byref(self.struct)
+
+    def marked_bytes(self, strand):
+        """The 'M'-marked copy of every contig (strand 0 = forward, 1 = reverse) as bytes, in index order; encoded once and
+        shared by every writer (native and Python)."""
+        if self._marked_bytes is None:
+            self._marked_bytes = ([self.marked[nm][0].encode() for nm in self.names], [self.marked[nm][1].encode() for nm in self.names])
+        return self._marked_bytes[strand]
 
     def context(self, contig_index, mpos, rev):
         """revcomp(last_ref[mpos-k+1:mpos+k], last_rev) (extract_contexts.py:194)."""

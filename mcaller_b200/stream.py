@@ -29,34 +29,55 @@ def plan_chunks(read_offsets, total_bytes, chunk_bytes):
 class TextSink(object):
     """Renders the rows of a chunk as `.diffs.<k>` text with the native writer (mc_format_rows, host threads) straight from
     the pinned row buffer and the host copy of the TSV (read names are cut from it).  Used by HostStreamer one chunk behind
-    the GPU, so the formatting overlaps the next chunk's copy and kernels."""
+    the GPU, so the formatting overlaps the next chunk's copy and kernels.  A window still open at the end of a chunk comes
+    back completed as slot 0 of a later chunk (mc_carry_rows); its read name lies in the earlier chunk's text, so the sink
+    keeps those few bytes when it sees the open row."""
 
-    def __init__(self, refindex, k, base="A", with_prob=True, keep=False):
+    def __init__(self, refindex, k, base="A", with_prob=True, keep=False, max_threads=0):
         import ctypes as C
         names = refindex.names
         n = len(names)
-        self._keep = [nm.encode() for nm in names] + [refindex.marked[nm][0].encode() for nm in names] + \
-                     [refindex.marked[nm][1].encode() for nm in names]
+        self._keep = [nm.encode() for nm in names] + list(refindex.marked_bytes(0)) + list(refindex.marked_bytes(1))
         self.names, self.fwd, self.rev = (C.c_char_p * n)(*self._keep[:n]), (C.c_char_p * n)(*self._keep[n:2 * n]), (C.c_char_p * n)(*self._keep[2 * n:])
-        self.lens = (C.c_int64 * n)(*[len(refindex.marked[nm][0]) for nm in names])
+        self.lens = (C.c_int64 * n)(*[len(x) for x in self._keep[n:2 * n]])
         self.n, self.k, self.with_prob = n, int(k), 1 if with_prob else 0
         self.base, self.mod = base.encode(), (b"m6A" if base == "A" else b"m" + base.encode())
+        self.max_threads = int(max_threads)
         self.out = None
         self.text_bytes = 0
-        self.kept = [] if keep else None      # rendered text per chunk (tests); rows still open at a chunk end are not in it:
-        #                                       extract_features carries those to the next chunk (_RowFormatter.pending)
+        self.carry_name = None                # read name of the window currently open across a chunk edge
+        self.kept = [] if keep else None      # rendered text per chunk (tests)
+
+    def reset(self):
+        self.carry_name = None
+        self.text_bytes = 0
+        if self.kept is not None:
+            self.kept = []
 
     def render(self, h_calls, n_calls, host_text_ptr, max_read_len=256):
-        """h_calls: pinned uint8 tensor holding n_calls rows; host_text_ptr: address of the chunk's first byte in host memory."""
+        """h_calls: pinned uint8 tensor (or numpy uint8 array) holding n_calls rows; host_text_ptr: address of the chunk's
+        first byte in host memory (0 when the rows carry no read_off into a text, e.g. the row of Engine.close_carry)."""
         import ctypes as C
         from . import _lib
-        cap = n_calls * (96 + 26 * (self.k + 1) + max_read_len) + 4096
+        if n_calls <= 0:
+            return 0
+        raw = h_calls.numpy() if hasattr(h_calls, "numpy") and not isinstance(h_calls, np.ndarray) else h_calls
+        rows = raw[:n_calls * CALL_DTYPE.itemsize].view(CALL_DTYPE)
+        name = self.carry_name
+        nlen = len(name) if name is not None else 0
+        cap = n_calls * (96 + 26 * (self.k + 1) + max(max_read_len, nlen)) + 4096
         if self.out is None or len(self.out) < cap:
             self.out = C.create_string_buffer(int(cap * 1.25))
-        r = _lib.lib().mc_format_rows(C.c_void_p(h_calls.data_ptr()), n_calls, C.c_void_p(host_text_ptr), self.names, self.fwd, self.rev,
-                                      self.lens, self.n, self.k, self.base, self.mod, self.with_prob, self.out, len(self.out))
+        r = _lib.lib().mc_format_rows(C.c_void_p(rows.ctypes.data), n_calls, C.c_void_p(host_text_ptr), name, nlen, self.names, self.fwd,
+                                      self.rev, self.lens, self.n, self.k, self.base, self.mod, self.with_prob, self.max_threads,
+                                      self.out, len(self.out))
         if r < 0:
             _lib.check(int(r) if r > -100 else -1)
+        if rows[0]["kind"] != _lib.MC_NONE and rows[0]["read_off"] < 0:
+            self.carry_name = None            # the carried window has been written (or counted) with this chunk
+        last = rows[n_calls - 1]
+        if last["close_rec"] == _lib.PENDING and last["kind"] in (_lib.MC_CALL, _lib.MC_TOO_MANY_SKIPS) and last["read_off"] >= 0:
+            self.carry_name = C.string_at(host_text_ptr + int(last["read_off"]), int(last["read_len"]))
         self.text_bytes += int(r)
         if self.kept is not None:
             self.kept.append(self.out.raw[:r])
@@ -241,7 +262,9 @@ class HostStreamer(object):
     def run(self, host_buf, cuts, fetch_calls=True, sink=None):
         """host_buf: pinned uint8 CPU tensor; cuts: chunk end offsets from plan_chunks.  Returns dict of totals; rows of
         every chunk are copied to pinned host memory when fetch_calls (the D2H leg of the end-to-end path) and, with a
-        TextSink, rendered as `.diffs` text one chunk behind the GPU."""
+        TextSink, rendered as `.diffs` text one chunk behind the GPU.  Windows open at a chunk end are carried on the device
+        (Engine.d_carry) and appear, completed, as slot 0 of the next chunk with a kept line; the one still open after the
+        last chunk is left in the carry for the caller (Engine.close_carry: next rank / end of file)."""
         eng = self.eng
         fetch_calls = fetch_calls or sink is not None
         late = None                                   # (slot, n_calls, chunk start) of the chunk whose rows are not rendered yet
@@ -253,11 +276,11 @@ class HostStreamer(object):
         cur = torch.cuda.current_stream(self.dev)
         for e in self.free:
             e.record(cur)
-        tot = dict(calls=0, pending_resolved=0, too_many_skips=0, multi=0, errors=0, methylated=0, records=0, lines=0, rows=0)
+        tot = dict(calls=0, too_many_skips=0, multi=0, errors=0, methylated=0, records=0, lines=0, rows=0)
         bounds = [0] + list(cuts)
         if len(bounds) > 1:
             self._enqueue_copy(0, host_buf, bounds[0], bounds[1])
-        pending_prev = pending_tms_prev = 0
+        st = None
         for i in range(len(bounds) - 1):
             slot = i & 1
             if i + 2 < len(bounds):
@@ -265,7 +288,7 @@ class HostStreamer(object):
             cur.wait_event(self.ready[slot])
             n = bounds[i + 1] - bounds[i]
             res = eng.run_chunk(self.dbuf[slot], n)
-            st = eng.count_rows(res)
+            st = res.stats
             if fetch_calls and res.n_calls:
                 nb = res.n_calls * CALL_DTYPE.itemsize
                 sc = i & 1
@@ -279,13 +302,6 @@ class HostStreamer(object):
                         render(late)                  # the previous chunk's rows, while this chunk's copy-back is in flight
                     late = (sc, res.n_calls, bounds[i])
             self.free[slot].record(cur)
-            # a window left open by the previous chunk closes on this chunk's first kept line (any kept line does)
-            if (pending_prev or pending_tms_prev) and res.counters["kept"] > 0:
-                tot["pending_resolved"] += pending_prev
-                tot["too_many_skips"] += pending_tms_prev
-                pending_prev = pending_tms_prev = 0
-            pending_prev += st["pending"]
-            pending_tms_prev += st["pending_too_many_skips"]
             for kx in ("calls", "too_many_skips", "multi", "errors", "methylated"):
                 tot[kx] += st[kx]
             tot["records"] += res.n_records
@@ -294,6 +310,6 @@ class HostStreamer(object):
         cur.synchronize()
         if sink is not None and late is not None:
             render(late)
-        tot["calls"] += tot["pending_resolved"]
-        tot["dropped_at_eof"] = pending_prev
+        # the window (call or too-many-skips event) still open after the last chunk: Engine.close_carry decides its fate
+        tot["open_at_end"] = (st["pending"] + st["pending_too_many_skips"]) if st is not None else 0
         return tot

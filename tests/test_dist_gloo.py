@@ -14,18 +14,19 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         lo, hi = mdist.shard_range(101, rank, world)
-        depth = torch.zeros(16, dtype=torch.int32)
-        meth = torch.zeros(16, dtype=torch.int32)
+        counts = torch.zeros(32, dtype=torch.int32)               # depth | meth packed like Engine.d_counts
+        depth, meth = counts[:16], counts[16:]
         first = torch.full((16,), 2 ** 63 - 1, dtype=torch.int64)
         for i in range(lo, hi):
             s = i % 16
             depth[s] += 1
             meth[s] += i % 2
             first[s] = min(int(first[s]), mdist.rank_row_base(rank) + (i - lo))
-        mdist.allreduce_histogram(depth, meth, first)
-        # rank 0 leaves one window pending; rank 1's first kept line lies on contig 3 and it has nothing pending
-        res = mdist.exchange_boundaries(3 if rank == 1 else 0, 1 if rank == 0 else 0, torch.device("cpu"))
-        q.put((rank, lo, hi, depth.tolist(), meth.tolist(), first.tolist(), res))
+        mdist.allreduce_histogram(counts, first)
+        # rank 0's slice starts on contig 0, rank 1's first kept line lies on contig 3: rank 0's open window is closed by
+        # contig 3, nobody closes the last rank's (dropped like the last window of a file)
+        allk = mdist.gather_first_kept(torch.tensor([3 if rank == 1 else 0], dtype=torch.int64))
+        q.put((rank, lo, hi, depth.tolist(), meth.tolist(), first.tolist(), (allk.tolist(), mdist.closing_contig(allk, rank))))
     finally:
         dist.destroy_process_group()
 
@@ -48,8 +49,8 @@ def test_two_rank_histogram_and_boundary():
     want_m = [sum(i % 2 for i in range(101) if i % 16 == s) for s in range(16)]
     assert d0 == want_d and m0 == want_m
     assert f0 == list(range(16))                 # every slot is first seen by rank 0's rows 0..15
-    assert b0 == (1, 3)                          # rank 0's pending window is closed by rank 1's first kept line
-    assert b1 == (0, -1)                         # last rank: dropped, like the last window of a file
+    assert b0 == ([0, 3], 3)                     # rank 0's pending window is closed by rank 1's first kept line
+    assert b1 == ([0, 3], -1)                    # last rank: dropped, like the last window of a file
 
 
 def test_shard_range_covers_everything():
@@ -68,3 +69,22 @@ def test_plan_chunks_cuts_on_read_boundaries():
     assert cuts[-1] == 2000 and all(c in set(offs.tolist()) | {2000} for c in cuts)
     assert cuts == [250, 900, 1000, 1800, 2000]   # read [250,900) is larger than the chunk and goes alone
     assert plan_chunks(offs, 2000, 5000) == [2000]
+
+
+def test_reference_byte_ranges_and_merge(tmp_path):
+    """multigpu.byte_ranges is the reference's split (mCaller.py:63-68); merge_outputs concatenates the ranks' files in
+    offset order and removes them."""
+    import math
+    from mcaller_b200 import multigpu
+    for size in (0, 1, 10, 1001, 12345):
+        for w in (1, 2, 3, 8):
+            r = multigpu.byte_ranges(size, w)
+            chunk = int(math.ceil(size / float(w))) if size else 0
+            assert [a for a, _ in r] == [chunk * i for i in range(w)] and r[-1][1] == size
+    tsv = tmp_path / "x.eventalign.tsv"
+    tsv.write_bytes(b"y" * 1001)
+    for i, (a, _) in enumerate(multigpu.byte_ranges(1001, 3)):
+        open(multigpu.ec_tmp_name(str(tsv), 6, a), "w").write("rank%d\n" % i)
+    out = multigpu.merge_outputs(str(tsv), 6, 3)
+    assert open(out).read() == "rank0\nrank1\nrank2\n"
+    assert sorted(os.listdir(tmp_path)) == ["x.eventalign.diffs.6", "x.eventalign.tsv"]

@@ -155,3 +155,125 @@ def test_bed_deep_matches_reference(tmp_path, cuda_lib):
         mb.aggregate_by_pos(diffs, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]), pos_list, False, "--vo" in a, "--gff" in a,
                             None, False, "x", False)
         assert b["rc"] == 0 and open(out).read() == b["bed"], a
+
+
+def _cli_args(case, inp):
+    return gc.cli_args(case, inp)
+
+
+@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q", "pos_p"])
+@pytest.mark.parametrize("workers", [3, 7])
+def test_worker_ranges_equal_single_worker(name, workers, tmp_path, capsys, cuda_lib):
+    """`-t N` (mCaller.py:63-68 byte ranges, one extract_features call per range, worker i on GPU i mod n): each worker closes
+    its last open window by probing the text after its range, so the concatenated files equal the reference's -t 1 output."""
+    from mcaller_b200 import cli
+    case = gc.CASES[name]
+    gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    assert cli.mcaller_main(_cli_args(case, inp) + ["-t", str(workers)]) == 0
+    capsys.readouterr()
+    assert open(os.path.join(str(tmp_path), "syn.eventalign.diffs.6")).read() == gold["diffs"]
+
+
+def _default_mode_beds(gold):
+    return [b for b in gold["beds"] if "-p" not in b["args"] and "--vo" not in b["args"]]
+
+
+@pytest.mark.parametrize("name", ["gatc_s0", "gatc_s2"])
+@pytest.mark.parametrize("chunk", [None, 60000])
+def test_bed_from_device_histogram_matches_reference(name, chunk, tmp_path, capsys, cuda_lib):
+    """The fused path: per-site histogram on the device (mc_hist_accumulate, windows carried over chunk edges on the device)
+    -> make_bed.aggregate_from_histogram == the reference's make_bed.py output on its own `.diffs` file, byte for byte
+    (thresholds -d / -t, --control, --gff, --ref, first-seen row order), without parsing any `.diffs` text."""
+    from mcaller_b200 import extract_contexts as ec, make_bed as mb, read_qual
+    case = gc.CASES[name]
+    gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    old = ec.CHUNK_BYTES
+    if chunk:
+        ec.CHUNK_BYTES = chunk
+    try:
+        run = ec.RangeRun(inp["tsv"], inp["fasta"], read_qual.extract_read_quality(inp["fastq"]), 6, case.get("s", 0), 0.0, inp["model"], 0,
+                          endline=os.path.getsize(inp["tsv"]), base="A", motif=case["motif"], histogram=True)
+        run.stream()
+    finally:
+        ec.CHUNK_BYTES = old
+    row = run.eng.close_carry(-1)                               # end of the file: the last open window is dropped
+    assert int(row[0]["kind"]) == 3
+    assert open(run.tsv_output).read() == gold["diffs"]
+    depth, meth, first = run.eng.histogram_host()
+    beds = _default_mode_beds(gold)
+    assert len(beds) >= 2
+    for b in beds:
+        a = b["args"]
+        out = os.path.join(str(tmp_path), "h.bed")
+        mb.aggregate_from_histogram(run.ref, depth, meth, first, out, int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1]),
+                                    control="--control" in a, gff="--gff" in a, ref=inp["fasta"] if "--ref" in a else None,
+                                    odd_rows=run.eng.odd_rows())
+        assert open(out).read() == b["bed"], a
+    capsys.readouterr()
+
+
+def test_histogram_keeps_rows_closed_by_another_contig(tmp_path, capsys, cuda_lib):
+    """Reference quirk (extract_contexts.py:216): column 1 of a row is the CLOSING line's contig.  Such rows cannot be keyed
+    by site slot; the device hands them over (Engine.odd_rows) and the BED built from the histogram still equals make_bed's
+    on the `.diffs` text -- the A_s0 golden has truncated reads whose last window is closed by a read on the next contig."""
+    from mcaller_b200 import extract_contexts as ec, make_bed as mb, read_qual
+    case = gc.CASES["A_s0"]
+    gold = json.load(open(os.path.join(gc.GOLD, "A_s0.json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    run = ec.RangeRun(inp["tsv"], inp["fasta"], read_qual.extract_read_quality(inp["fastq"]), 6, 0, 0.0, inp["model"], 0,
+                      endline=os.path.getsize(inp["tsv"]), base="A", motif="A", histogram=True)
+    run.stream()
+    run.eng.close_carry(-1)
+    assert open(run.tsv_output).read() == gold["diffs"]
+    odd = run.eng.odd_rows()
+    depth, meth, first = run.eng.histogram_host()
+    out = os.path.join(str(tmp_path), "h.bed")
+    mb.aggregate_from_histogram(run.ref, depth, meth, first, out, 1, 0.5, odd_rows=odd)
+    want = [b for b in gold["beds"] if b["args"] == ["-d", "1", "-t", "0.5"]][0]["bed"]
+    assert open(out).read() == want
+    assert int(depth.sum()) + len(odd) == gold["counters"]["observations"]
+    capsys.readouterr()
+
+
+def _multi_rank_case(name, world, tmp_path, bed_args, backend=None):
+    """python -m mcaller_b200.cli mCaller ... --gpus <world> --bed in a subprocess (the ranks are spawned from it)."""
+    import subprocess
+    import sys
+    case = gc.CASES[name]
+    gold = json.load(open(os.path.join(gc.GOLD, name + ".json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__))) + os.pathsep + env.get("PYTHONPATH", "")
+    if backend:
+        env["MCALLER_B200_DIST_BACKEND"] = backend
+    env["MCALLER_B200_CHUNK_BYTES"] = "70000"                    # several chunks per rank: carries inside and across ranks
+    cmd = [sys.executable, "-m", "mcaller_b200.cli", "mCaller"] + gc.cli_args(case, inp) + ["--gpus", str(world), "--bed"] + bed_args
+    p = subprocess.run(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:]
+    return gold, p.stdout
+
+
+@pytest.mark.parametrize("name,world", [("gatc_s0", 2), ("gatc_s2", 2), ("gatc_s2", 3)])
+def test_multi_rank_product_path_on_one_gpu(name, world, tmp_path, cuda_lib):
+    """The multi-GPU product path (mcaller_b200.multigpu) with several ranks sharing this GPU (gloo carries the two
+    exchanges): concatenated `.diffs` == the reference's -t 1 output and the BED written from the all-reduced histogram ==
+    the reference's make_bed.py output, byte for byte."""
+    gold, _ = _multi_rank_case(name, world, tmp_path, ["--bed_min_read_depth", "2", "--bed_mod_threshold", "0.5"] if name == "gatc_s2"
+                               else ["--bed_min_read_depth", "3", "--bed_mod_threshold", "0.3"], backend="gloo")
+    assert open(os.path.join(str(tmp_path), "syn.eventalign.diffs.6")).read() == gold["diffs"]
+    want = [b for b in gold["beds"] if b["args"] == (["-d", "2", "-t", "0.5"] if name == "gatc_s2" else ["-d", "3", "-t", "0.3"])][0]["bed"]
+    assert open(os.path.join(str(tmp_path), "syn.methylation.summary.bed")).read() == want
+    assert not [f for f in os.listdir(str(tmp_path)) if ".tmp" in f]
+
+
+def test_multi_gpu_product_path_nccl(tmp_path, cuda_lib):
+    """Same over NCCL with one rank per GPU (needs >= 2 GPUs: `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    gold, _ = _multi_rank_case("gatc_s2", 2, tmp_path, ["--bed_min_read_depth", "2", "--bed_mod_threshold", "0.5"])
+    assert open(os.path.join(str(tmp_path), "syn.eventalign.diffs.6")).read() == gold["diffs"]
+    want = [b for b in gold["beds"] if b["args"] == ["-d", "2", "-t", "0.5"]][0]["bed"]
+    assert open(os.path.join(str(tmp_path), "syn.methylation.summary.bed")).read() == want

@@ -154,7 +154,7 @@ def test_c_abi_exports_match_header():
     for fn in declared:
         assert hasattr(lib, fn), fn
     assert declared == set(_lib.EXPORTS)
-    assert lib.mc_version() == 1
+    assert lib.mc_version() == _lib.MC_ABI_VERSION == 2
     assert lib.mc_num_tiles(1) == 1 and lib.mc_num_tiles(3840) == 1 and lib.mc_num_tiles(3841) == 2
     assert lib.mc_workspace_bytes(1000) > 8000
 
@@ -228,7 +228,7 @@ def test_native_row_writer_matches_python_repr():
     names = (C.c_char_p * 1)(b"c1")
     a_f, a_r, ln = (C.c_char_p * 1)(fwd), (C.c_char_p * 1)(rev), (C.c_int64 * 1)(26)
     out = C.create_string_buffer(400 * n)
-    r = lib.mc_format_rows(calls.ctypes.data_as(C.c_void_p), n, text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+    r = lib.mc_format_rows(calls.ctypes.data_as(C.c_void_p), n, text, None, 0, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, 0, out, len(out))
     assert r > 0, lib.mc_last_error()
     rows = out.raw[:r].decode().split("\n")[:-1]
     live = [i for i in range(n) if calls["kind"][i] == 0]
@@ -246,22 +246,36 @@ def test_native_row_writer_matches_python_repr():
     parts = []
     for a in range(0, n, 1000):
         sl = np.ascontiguousarray(calls[a:a + 1000])
-        r2 = lib.mc_format_rows(sl.ctypes.data_as(C.c_void_p), len(sl), text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+        r2 = lib.mc_format_rows(sl.ctypes.data_as(C.c_void_p), len(sl), text, None, 0, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, 0, out, len(out))
         assert r2 >= 0
         parts.append(out.raw[:r2])
     assert b"".join(parts) == whole
     # an error flag on a row is reported with the row, whichever thread meets it
     bad = calls.copy()
     bad["err"][4321] = 4
-    r3 = lib.mc_format_rows(bad.ctypes.data_as(C.c_void_p), n, text, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, out, len(out))
+    r3 = lib.mc_format_rows(bad.ctypes.data_as(C.c_void_p), n, text, None, 0, names, a_f, a_r, ln, 1, 1, b"A", b"m6A", 1, 0, out, len(out))
     assert r3 == -104 and b"4321" in lib.mc_last_error()
     # k = 3: context is cut from the strand's marked copy and reverse-complemented for '-' rows
     calls2 = np.zeros(2, dtype=_lib.CALL_DTYPE)
     calls2["mpos"], calls2["read_len"], calls2["rev"] = 10, 2, [0, 1]
-    r = lib.mc_format_rows(calls2.ctypes.data_as(C.c_void_p), 2, text, names, a_f, a_r, ln, 1, 3, b"A", b"m6A", 0, out, len(out))
+    r = lib.mc_format_rows(calls2.ctypes.data_as(C.c_void_p), 2, text, None, 0, names, a_f, a_r, ln, 1, 3, b"A", b"m6A", 0, 0, out, len(out))
     rows = out.raw[:r].decode().split("\n")[:-1]
     assert rows[0].split("\t")[3] == fwd[8:13].decode() and rows[1].split("\t")[3] == refmark.revcomp(rev[8:13].decode())
     assert len(rows[0].split("\t")) == 6
+    # a row carried over a chunk edge (read_off < 0) takes its read name from the caller; MC_NONE slots are skipped; the
+    # thread cap does not change the bytes
+    calls3 = np.zeros(3, dtype=_lib.CALL_DTYPE)
+    calls3["mpos"], calls3["read_len"], calls3["rev"] = 10, 2, [0, 1, 0]
+    calls3["read_off"][0] = -1
+    calls3["kind"][2] = _lib.MC_NONE
+    r = lib.mc_format_rows(calls3.ctypes.data_as(C.c_void_p), 3, text, b"carried-read", 12, names, a_f, a_r, ln, 1, 3, b"A", b"m6A", 0, 1, out, len(out))
+    rows = out.raw[:r].decode().split("\n")[:-1]
+    assert len(rows) == 2 and rows[0].split("\t")[1] == "carried-read" and rows[1].split("\t")[1] == "rd"
+    assert lib.mc_format_rows(calls3.ctypes.data_as(C.c_void_p), 3, text, None, 0, names, a_f, a_r, ln, 1, 3, b"A", b"m6A", 0, 0, out, len(out)) == -1
+    # a context over a reference letter outside ACGTNM: the reference raises KeyError in revcomp; here an error, not a NUL byte
+    a_bad = (C.c_char_p * 1)(b"TTGTACGTRCMCGGACGTACGTAAAA")
+    r = lib.mc_format_rows(calls2.ctypes.data_as(C.c_void_p), 2, text, None, 0, names, a_f, a_bad, ln, 1, 3, b"A", b"m6A", 0, 0, out, len(out))
+    assert r == -1 and b"ACGTNM" in lib.mc_last_error()
 
 
 def test_tail_search_of_last_read_boundary_equals_full_search():
