@@ -99,6 +99,7 @@ enum {
     MC_C_LONGLINE,         /* lines whose first 12 columns outran the look-ahead and took the byte-wise slow path (informational) */
     MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
     MC_C_RUN_CURSOR,       /* internal: next unclaimed run of chunks (dynamic work distribution of mc_scan) */
+    MC_C_RAW,              /* records left in raw form (MC_RF_RAW) for mc_order_records to finish (informational) */
     MC_C_COUNT = 16
 };
 
@@ -220,8 +221,10 @@ int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab
  * previous record's (extract_contexts.py:161, `read_name != last_read`).  Writes the first record index of
  * each segment to d_seg_start (capacity rec_cap+1, terminated by the record count) and the segment count to
  * d_nseg[0].  d_n_records[0] (device) is the record count written by mc_order_records; rec_cap >= it sizes the launch.
+ * Records whose flags do not yet say whether a new read starts there (MC_RF_SEGKNOWN clear) are compared with their
+ * predecessor in the text and get MC_RF_SEGKNOWN / MC_RF_NEWREAD written back.
  */
-int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
+int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
                      uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream);
 
 /*

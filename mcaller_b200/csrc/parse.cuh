@@ -112,3 +112,56 @@ __device__ __forceinline__ void parse_values(const B &t, int f2, int f5, int f6,
     else diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
     if (tokens_equal(t, f2, f9)) flags |= MC_RF_EQ;
 }
+
+// ---- 8-byte register fast paths for the values of a record (any other shape falls back to the byte loops of parse.cuh) ----
+// 0x80 per byte of v that is not an ASCII digit
+__device__ __forceinline__ unsigned long long nondigit8(unsigned long long v) {
+    const unsigned long long x = v ^ 0x3030303030303030ull;
+    return (((x & 0x7f7f7f7f7f7f7f7full) + 0x7676767676767676ull) | v) & 0x8080808080808080ull;
+}
+// n (1..7) digit bytes at the low end of v -> value
+__device__ __forceinline__ uint32_t digits_value(unsigned long long v, int n) {
+    const unsigned long long x = (v ^ 0x3030303030303030ull) << (64 - 8 * n);      // right-aligned digit values, zeros below
+    const uint32_t L = (uint32_t)x, H = (uint32_t)(x >> 32);
+    auto conv4 = [](uint32_t h) {                                 // 4 digit values, most significant in byte 0 -> 0..9999
+        const uint32_t t = ((h * 2561u) >> 8) & 0x00ff00ffu;
+        return (t * 6553601u) >> 16;
+    };
+    return conv4(L) * 10000u + conv4(H);
+}
+// "<1..7 digits><ws>" -> value; false for any other shape
+__device__ __forceinline__ bool fast_uint8(unsigned long long v, int &out) {
+    const unsigned long long nd = nondigit8(v);
+    if (nd == 0ull) return false;
+    const int n = (__ffsll((long long)nd) - 1) >> 3;
+    if (n == 0 || ((v >> (8 * n)) & 0xFFull) > 0x20ull) return false;
+    out = (int)digits_value(v, n);
+    return true;
+}
+// "<digits>.<digits><ws>" with at most 7 bytes before the whitespace -> mantissa and number of fraction digits
+__device__ __forceinline__ bool fast_decimal8(unsigned long long v, uint32_t &mant, int &nfrac) {
+    const unsigned long long nd = nondigit8(v);
+    if (nd == 0ull) return false;
+    const int p1 = (__ffsll((long long)nd) - 1) >> 3;             // first non-digit: must be the point
+    if (p1 == 0 || p1 > 6 || ((v >> (8 * p1)) & 0xFFull) != 0x2eull) return false;
+    const unsigned long long low = (1ull << (8 * p1)) - 1ull;
+    const unsigned long long w = (v & low) | ((v >> 8) & ~low);    // the point removed: 7 bytes
+    const unsigned long long nd2 = ((nd & low) | ((nd >> 8) & ~low)) & 0x0080808080808080ull;
+    if (nd2 == 0ull) return false;
+    const int p2 = (__ffsll((long long)nd2) - 1) >> 3;            // first non-digit after it: must be whitespace
+    if (((w >> (8 * p2)) & 0xFFull) > 0x20ull) return false;
+    mant = digits_value(w, p2);
+    nfrac = p2 - p1;
+    return true;
+}
+// token at pa == token at pb for tokens of up to 7 bytes: 1 / 0, or -1 when one of them is longer (byte loop decides)
+__device__ __forceinline__ int fast_tokens_equal8(unsigned long long a, unsigned long long b) {
+    auto ws8 = [](unsigned long long v) {                          // 0x80 per byte <= 0x20
+        return ~((((v & 0x7f7f7f7f7f7f7f7full) + 0x5f5f5f5f5f5f5f5full) | v)) & 0x8080808080808080ull;
+    };
+    const unsigned long long wa = ws8(a), wb = ws8(b);
+    if (wa == 0ull || wb == 0ull) return -1;
+    const int la = (__ffsll((long long)wa) - 1) >> 3, lb = (__ffsll((long long)wb) - 1) >> 3;
+    if (la != lb) return 0;
+    return (((a ^ b) & ((1ull << (8 * la)) - 1ull)) == 0ull) ? 1 : 0;
+}

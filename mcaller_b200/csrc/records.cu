@@ -229,59 +229,6 @@ __device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) 
     return (lo >> sh) | (hi << (64 - sh));
 }
 
-// ---- 8-byte register fast paths for the values of a record (any other shape falls back to the byte loops of parse.cuh) ----
-// 0x80 per byte of v that is not an ASCII digit
-__device__ __forceinline__ unsigned long long nondigit8(unsigned long long v) {
-    const unsigned long long x = v ^ 0x3030303030303030ull;
-    return (((x & 0x7f7f7f7f7f7f7f7full) + 0x7676767676767676ull) | v) & 0x8080808080808080ull;
-}
-// n (1..7) digit bytes at the low end of v -> value
-__device__ __forceinline__ uint32_t digits_value(unsigned long long v, int n) {
-    const unsigned long long x = (v ^ 0x3030303030303030ull) << (64 - 8 * n);      // right-aligned digit values, zeros below
-    const uint32_t L = (uint32_t)x, H = (uint32_t)(x >> 32);
-    auto conv4 = [](uint32_t h) {                                 // 4 digit values, most significant in byte 0 -> 0..9999
-        const uint32_t t = ((h * 2561u) >> 8) & 0x00ff00ffu;
-        return (t * 6553601u) >> 16;
-    };
-    return conv4(L) * 10000u + conv4(H);
-}
-// "<1..7 digits><ws>" -> value; false for any other shape
-__device__ __forceinline__ bool fast_uint8(unsigned long long v, int &out) {
-    const unsigned long long nd = nondigit8(v);
-    if (nd == 0ull) return false;
-    const int n = (__ffsll((long long)nd) - 1) >> 3;
-    if (n == 0 || ((v >> (8 * n)) & 0xFFull) > 0x20ull) return false;
-    out = (int)digits_value(v, n);
-    return true;
-}
-// "<digits>.<digits><ws>" with at most 7 bytes before the whitespace -> mantissa and number of fraction digits
-__device__ __forceinline__ bool fast_decimal8(unsigned long long v, uint32_t &mant, int &nfrac) {
-    const unsigned long long nd = nondigit8(v);
-    if (nd == 0ull) return false;
-    const int p1 = (__ffsll((long long)nd) - 1) >> 3;             // first non-digit: must be the point
-    if (p1 == 0 || p1 > 6 || ((v >> (8 * p1)) & 0xFFull) != 0x2eull) return false;
-    const unsigned long long low = (1ull << (8 * p1)) - 1ull;
-    const unsigned long long w = (v & low) | ((v >> 8) & ~low);    // the point removed: 7 bytes
-    const unsigned long long nd2 = ((nd & low) | ((nd >> 8) & ~low)) & 0x0080808080808080ull;
-    if (nd2 == 0ull) return false;
-    const int p2 = (__ffsll((long long)nd2) - 1) >> 3;            // first non-digit after it: must be whitespace
-    if (((w >> (8 * p2)) & 0xFFull) > 0x20ull) return false;
-    mant = digits_value(w, p2);
-    nfrac = p2 - p1;
-    return true;
-}
-// token at pa == token at pb for tokens of up to 7 bytes: 1 / 0, or -1 when one of them is longer (byte loop decides)
-__device__ __forceinline__ int fast_tokens_equal8(unsigned long long a, unsigned long long b) {
-    auto ws8 = [](unsigned long long v) {                          // 0x80 per byte <= 0x20
-        return ~((((v & 0x7f7f7f7f7f7f7f7full) + 0x5f5f5f5f5f5f5f5full) | v)) & 0x8080808080808080ull;
-    };
-    const unsigned long long wa = ws8(a), wb = ws8(b);
-    if (wa == 0ull || wb == 0ull) return -1;
-    const int la = (__ffsll((long long)wa) - 1) >> 3, lb = (__ffsll((long long)wb) - 1) >> 3;
-    if (la != lb) return 0;
-    return (((a ^ b) & ((1ull << (8 * la)) - 1ull)) == 0ull) ? 1 : 0;
-}
-
 // do the L bytes at pa and pb differ (the '\n' padding after the text keeps the 8-byte loads legal).  Both sides are
 // streamed as aligned 8-byte words and realigned in registers: 1 + ceil(L / 8) loads per side, all independent.
 __device__ __forceinline__ bool bytes_differ(const uint8_t *pa, const uint8_t *pb, int L) {
@@ -305,21 +252,17 @@ __device__ __forceinline__ bool bytes_differ(const uint8_t *pa, const uint8_t *p
 }
 
 __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
-                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap) {
-    // A warp finishes 31 records; lane 0 re-walks the record before them (the previous warp's last) only to know its
-    // read-name span, so that every lane can compare its read name with its predecessor's, handed over by one shuffle
-    // while both lines are still in L1.  That comparison is the read segmentation flag (MC_RF_NEWREAD).
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long i = warp * 31 + lane - 1;
-    const bool active = i >= 0 && i < dev_count(d_n, rec_cap);
-    alignas(16) mc_record r;
-    if (active) r = rec[i];
-    else { r.line_lo = 0u; r.line_hi = 0; r.name_off = 0; r.name_len = 0; r.flags = 0; r.pos = 0; r.contig = 0; r.event_idx = 0; r.diff = 0.0; }
-    // lane 0 always walks: the record's owner (previous warp) may be rewriting it right now, only its line offset is stable
-    const bool raw = active && (lane == 0 || (r.flags & MC_RF_RAW));
+                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap,
+                                                       const unsigned long long *__restrict__ scan_counters) {
+    // Stage 1 finishes its records itself while the line is staged in shared memory; what arrives here in raw form are the
+    // unusual shapes (signs, numbers of more than 7 digits, long tokens, lines beyond the look-ahead): one thread per
+    // record, the others leave at once -- and the whole grid does when stage 1 reports no raw record at all.
+    if (scan_counters && scan_counters[MC_C_RAW] == 0ull) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dev_count(d_n, rec_cap)) return;
+    alignas(16) mc_record r = rec[i];
+    if (!(r.flags & MC_RF_RAW)) return;
     const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
-    if (raw) {
     // 16-byte steps from the aligned address at or below the line start; the '\n' padding after the text makes every
     // line end inside readable memory
     const int64_t a0 = line & ~15ll;
@@ -370,59 +313,38 @@ __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restric
     int ev_idx = 0;
     double diff = 0.0;
     if (nf < 11 || name_end < 0 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;   // cannot happen for a kept line
-    else if (lane > 0) {
-        // usual shapes ("1234", "87.41", 6-mers) from 8-byte register loads; anything else takes the byte loops
-        const uint8_t *lp = text + line;
-        uint32_t m_ev = 0u, m_md = 0u;
-        int n_ev = 0, n_md = 0;
-        const int teq = fast_tokens_equal8(load8_unaligned(lp + f2), load8_unaligned(lp + f9));
-        if (line + f10 + 16 < limit && teq >= 0 && fast_uint8(load8_unaligned(lp + f5), ev_idx) &&
-            fast_decimal8(load8_unaligned(lp + f6), m_ev, n_ev) && fast_decimal8(load8_unaligned(lp + f10), m_md, n_md)) {
-            const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
-            diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
-            if (teq) fl |= MC_RF_EQ;
-        } else {
-            ev_idx = 0;
-            parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
-        }
-    }
+    else parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
     r.name_off = (uint16_t)f3;
     r.name_len = (uint16_t)(name_end < 0 ? 0 : name_end - f3);
     r.event_idx = ev_idx;
     r.diff = diff;
     r.flags = (uint8_t)fl;
-    }
-    // read segmentation: same read as the previous record <=> equal name length and bytes (extract_contexts.py:161, :179)
-    const unsigned long long prev_line = __shfl_up_sync(0xffffffffu, (unsigned long long)line, 1);
-    const uint32_t prev_span = __shfl_up_sync(0xffffffffu, (uint32_t)r.name_off | ((uint32_t)r.name_len << 16), 1);
-    if (!active || lane == 0) return;
-    uint32_t fl = r.flags | MC_RF_SEGKNOWN;
-    if (i == 0 || (prev_span >> 16) != r.name_len ||
-        bytes_differ(text + (int64_t)prev_line + (prev_span & 0xFFFFu), text + line + r.name_off, r.name_len))
-        fl |= MC_RF_NEWREAD;
-    r.flags = (uint8_t)fl;
     uint4 *dst = reinterpret_cast<uint4 *>(rec + i);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    if (raw) dst[0] = src[0];
+    dst[0] = src[0];
     dst[1] = src[1];
 }
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, const mc_record *__restrict__ rec, int64_t n_cap,
+__global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, mc_record *__restrict__ rec, int64_t n_cap,
                                                   const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ flags) {
     const int64_t n = dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t f = 1u;
-    if (i > 0) {
-        const mc_record b = rec[i];
-        if (b.flags & MC_RF_SEGKNOWN) {
-            f = (b.flags & MC_RF_NEWREAD) ? 1u : 0u;              // compared while the record was finished
-        } else {
+    const mc_record b = rec[i];
+    if (b.flags & MC_RF_SEGKNOWN) {
+        f = (b.flags & MC_RF_NEWREAD) ? 1u : 0u;                  // stage 1 compared the names while both lines were staged
+    } else {
+        // first record of a scan pass, neighbour of a raw record, or records that did not come through stage 1: compare the
+        // read names in the text, and leave the answer in the record (the window builder reads it there).  Only the flag
+        // byte of the own record is written; neighbours read this record's name span and line offset, never its flags.
+        if (i > 0) {
             const mc_record a = rec[i - 1];
             if (a.name_len == b.name_len)
                 f = bytes_differ(text + rec_line(a) + a.name_off, text + rec_line(b) + b.name_off, a.name_len) ? 1u : 0u;
         }
+        rec[i].flags = (uint8_t)(b.flags | MC_RF_SEGKNOWN | (f ? MC_RF_NEWREAD : 0u));
     }
     flags[i] = f;
 }
@@ -493,13 +415,14 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t 
     MC_LAUNCH_CHECK();
     // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
     // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
-    k_finish_records<<<(unsigned)((rec_out_cap + 247) / 248), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
-                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap);
+    k_finish_records<<<(unsigned)((rec_out_cap + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
+                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap,
+                                                                            reinterpret_cast<const unsigned long long *>(d_scan_counters));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
-extern "C" int mc_segment_reads(const uint8_t *d_text, const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
+extern "C" int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
                                 uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream) {
     MC_REQUIRE(d_text && d_rec && d_n_records && d_seg_start && d_nseg && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;

@@ -24,8 +24,11 @@
 //      finds columns 1, 2, 10 and 12 without touching the bytes in between (the ~58 B read name is never walked); 12-column
 //      check, contig lookup, NNNNNN test, position, candidate bit;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the run, or
-//      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags}.  Their
-//      values (event index, currents, k-mer equality, read-name span) are parsed in stage 2 at full lane occupancy.
+//      every kept line in dense mode); those get a 32-byte record, FINISHED here while the line is still staged in shared
+//      memory: columns 3, 4, 6, 7, 10 and 11 are located in the same 160-bit window, event index / currents / k-mers are
+//      decoded from 8-byte register loads (np.round(event_mean - model_mean, 4) in float64, k-mer equality, read-name span),
+//      and the read name is compared with the previous recorded line of the pass (MC_RF_NEWREAD).  Only unusual shapes
+//      (signs, > 7 digit numbers, long tokens, lines beyond the look-ahead) are left raw (MC_RF_RAW) for stage 2.
 //      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
 // Algorithmic HBM traffic: the text itself (once) + 32 B per record (~1 B per line in sparse mode).
@@ -57,10 +60,10 @@ static_assert(MC_TEXT_PAD >= LOOKA + 64, "text padding must cover the look-ahead
 
 struct WarpSmem {
     alignas(16) uint8_t text[2][WB];     // double-buffered staged bytes (TMA destination, 16-byte aligned)
-    alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
+    alignas(16) uint32_t nw[NW + 8];     // non-whitespace bits (byte > 0x20; zero padded): field starts / ends are derived from it
     alignas(16) uint32_t nl[NW + 4];     // newline bits
     uint16_t lstart[LCAP + 4];
-    uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
+    uint32_t cnt[8];                     // per-warp event counters (flushed once at the end); [6] = records left raw
     unsigned long long key[4];           // the hint contig's name in 8-byte pieces (quiet test; names of up to 31 bytes)
     alignas(8) unsigned long long bar[2];
 };
@@ -111,14 +114,19 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
 
 // ---- generic field walk (rare: lines whose first 12 columns do not fit the 160-bit window) ------------------------------
 // position of the n-th (0-based) field start at or after smem offset s; NW*32 when it lies beyond the staged bytes
-__device__ __noinline__ int select_fs_walk(const uint32_t *fs, int s, int n) {
+// field-start bits of mask word w: non-whitespace bytes whose predecessor is whitespace
+__device__ __forceinline__ uint32_t fs_word(const uint32_t *nw, int w) {
+    const uint32_t v = nw[w];
+    return v & ~((v << 1) | (w > 0 ? nw[w - 1] >> 31 : 0u));
+}
+__device__ __noinline__ int select_fs_walk(const uint32_t *nw, int s, int n) {
     int w = s >> 5;
-    uint32_t m = fs[w] & (0xFFFFFFFFu << (s & 31));
+    uint32_t m = fs_word(nw, w) & (0xFFFFFFFFu << (s & 31));
     int c = __popc(m);
     while (c <= n) {
         n -= c;
         if (++w >= NW) return NW * 32;
-        m = fs[w];
+        m = fs_word(nw, w);
         c = __popc(m);
     }
     for (; n > 0; --n) m &= m - 1u;
@@ -142,11 +150,30 @@ __device__ __forceinline__ int nth_bit(uint32_t m, int j) {     // position of t
     for (int t = 6; t < j; ++t) m &= m - 1u;                     // words with more than 7 field starts: rare
     return __ffs(m) - 1;
 }
-__device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11) {
+// 160-bit window aligned at the line start s: N = non-whitespace bits, F = field-start bits (the byte before a line start
+// is a newline, so bit 0 of the window has a whitespace predecessor)
+struct LineWindow {
+    uint32_t N0, N1, N2, N3, N4, F0, F1, F2, F3, F4;
+};
+__device__ __forceinline__ LineWindow line_window(const WarpSmem &S, int s) {
     const int w0 = s >> 5, sh = s & 31;
-    const uint32_t a0 = S.fs[w0], a1 = S.fs[w0 + 1], a2 = S.fs[w0 + 2], a3 = S.fs[w0 + 3], a4 = S.fs[w0 + 4], a5 = S.fs[w0 + 5];
-    const uint32_t W0 = __funnelshift_r(a0, a1, sh), W1 = __funnelshift_r(a1, a2, sh), W2 = __funnelshift_r(a2, a3, sh),
-                   W3 = __funnelshift_r(a3, a4, sh), W4 = __funnelshift_r(a4, a5, sh);
+    const uint32_t a0 = S.nw[w0], a1 = S.nw[w0 + 1], a2 = S.nw[w0 + 2], a3 = S.nw[w0 + 3], a4 = S.nw[w0 + 4], a5 = S.nw[w0 + 5];
+    LineWindow L;
+    L.N0 = __funnelshift_r(a0, a1, sh);
+    L.N1 = __funnelshift_r(a1, a2, sh);
+    L.N2 = __funnelshift_r(a2, a3, sh);
+    L.N3 = __funnelshift_r(a3, a4, sh);
+    L.N4 = __funnelshift_r(a4, a5, sh);
+    L.F0 = L.N0 & ~(L.N0 << 1);
+    L.F1 = L.N1 & ~((L.N1 << 1) | (L.N0 >> 31));
+    L.F2 = L.N2 & ~((L.N2 << 1) | (L.N1 >> 31));
+    L.F3 = L.N3 & ~((L.N3 << 1) | (L.N2 >> 31));
+    L.F4 = L.N4 & ~((L.N4 << 1) | (L.N3 >> 31));
+    return L;
+}
+__device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11) {
+    const LineWindow L = line_window(S, s);
+    const uint32_t W0 = L.F0, W1 = L.F1, W2 = L.F2, W3 = L.F3, W4 = L.F4;
     const int c0 = __popc(W0), c1 = c0 + __popc(W1), c2 = c1 + __popc(W2), c3 = c2 + __popc(W3), c4 = c3 + __popc(W4);
     if (c4 >= 12) {
         auto sel = [&](int k) {
@@ -180,10 +207,10 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
         }
     } else {
         // fewer than 12 field starts within 160 bytes: short line or unusually wide columns -> generic walk
-        f0 = select_fs_walk(S.fs, s, 0);
-        f1 = select_fs_walk(S.fs, s, 1);
-        f9 = select_fs_walk(S.fs, s, 9);
-        f11 = select_fs_walk(S.fs, s, 11);
+        f0 = select_fs_walk(S.nw, s, 0);
+        f1 = select_fs_walk(S.nw, s, 1);
+        f9 = select_fs_walk(S.nw, s, 9);
+        f11 = select_fs_walk(S.nw, s, 11);
     }
 }
 
@@ -258,6 +285,56 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
     }
     if (nf < 12) return ST_SHORT;
     return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, -1, cid, pos);
+}
+
+// ---- record finishing from the staged bytes (what stage 2 did from global memory in round 1) ---------------------------------
+// Columns 3, 4, 6, 7, 10, 11 of the line starting at staged offset s, located by rank/select on the 160-bit field-start window;
+// event index, np.round(event_mean - model_mean, 4) (extract_contexts.py:286), k-mer equality (:169) and the read-name span
+// (:161).  Returns false for anything but the usual shapes -- the record then stays MC_RF_RAW and stage 2 finishes it from
+// global memory with the byte loops of parse.cuh (same float64 either way).
+__device__ __forceinline__ bool finish_line(const WarpSmem &S, const uint8_t *text, int s, int &ev_idx, double &diff, uint32_t &eq,
+                                            int &name_off, int &name_len) {
+    const LineWindow L = line_window(S, s);
+    const int c0 = __popc(L.F0), c1 = c0 + __popc(L.F1), c2 = c1 + __popc(L.F2), c3 = c2 + __popc(L.F3), c4 = c3 + __popc(L.F4);
+    if (c4 < 11) return false;                                     // column 11 starts beyond the window
+    auto sel = [&](int k) {                                        // window-relative start of column k + 1
+        const int wi = (k >= c0) + (k >= c1) + (k >= c2) + (k >= c3);
+        const uint32_t m = wi == 0 ? L.F0 : wi == 1 ? L.F1 : wi == 2 ? L.F2 : wi == 3 ? L.F3 : L.F4;
+        const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : wi == 3 ? c2 : c3;
+        return 32 * wi + nth_bit(m, k - base);
+    };
+    const int r2 = sel(2), r3 = sel(3), r5 = sel(5), r6 = sel(6), r9 = sel(9), r10 = sel(10);
+    if (s + r10 + 12 > WB) return false;                           // the 8-byte loads below must stay inside the staged bytes
+    // end of the read name: first whitespace at or after r3
+    int wi = r3 >> 5;
+    uint32_t z = ~(wi == 0 ? L.N0 : wi == 1 ? L.N1 : wi == 2 ? L.N2 : wi == 3 ? L.N3 : L.N4) & (0xFFFFFFFFu << (r3 & 31));
+    while (z == 0u) {
+        if (++wi > 4) return false;
+        z = ~(wi == 1 ? L.N1 : wi == 2 ? L.N2 : wi == 3 ? L.N3 : L.N4);
+    }
+    const int rend = 32 * wi + __ffs(z) - 1;
+    const int teq = fast_tokens_equal8(load8(text, s + r2), load8(text, s + r9));
+    uint32_t m_ev = 0u, m_md = 0u;
+    int n_ev = 0, n_md = 0;
+    if (teq < 0 || !fast_uint8(load8(text, s + r5), ev_idx) || !fast_decimal8(load8(text, s + r6), m_ev, n_ev) ||
+        !fast_decimal8(load8(text, s + r10), m_md, n_md))
+        return false;
+    const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
+    diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
+    eq = teq ? MC_RF_EQ : 0u;
+    name_off = r3;
+    name_len = rend - r3;
+    return true;
+}
+// do the L staged bytes at offsets a and b differ (8 bytes at a time, any alignment)
+__device__ __forceinline__ bool staged_differ(const uint8_t *text, int a, int b, int L) {
+    unsigned long long d = 0ull;
+    for (int j = 0; j < L; j += 8) {
+        unsigned long long x = load8(text, a + j) ^ load8(text, b + j);
+        if (L - j < 8) x &= (1ull << (8 * (L - j))) - 1ull;
+        d |= x;
+    }
+    return d != 0ull;
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
@@ -532,7 +609,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // ---- 3. full parse: field-start map of the chunk (once), then one lane per line -------------------------------
             if (!full_ready) {
                 full_ready = true;
-                uint32_t prev_top = 0u;                               // was the last byte of word 32r-1 non-whitespace
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int w = 32 * r + lane;
@@ -540,14 +616,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
                     const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x),
                                                   gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w));
-                    // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
-                    const uint32_t top = nonws >> 31;
-                    uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
-                    if (lane == 0) pt = prev_top;
-                    prev_top = __shfl_sync(0xffffffffu, top, 31);
-                    S.fs[w] = nonws & ~((nonws << 1) | pt);
+                    S.nw[w] = nonws;
                 }
-                if (lane < 8) S.fs[NW + lane] = 0u;
+                if (lane < 8) S.nw[NW + lane] = 0u;
                 // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold
                 // the look-ahead words instead of a single lane walking the bit map
                 if (!tail) {
@@ -565,6 +636,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
             uint32_t status = 0u;
             int cid = -1, pos = 0, s = 0;
+            bool staged = false;       // first 12 columns inside the staged bytes (else: classified from global memory)
             if (lane < n_pass) {
                 s = S.lstart[lane];
                 const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : (e_last >= 0 ? e_last : next_bit(S.nl, s));
@@ -572,6 +644,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 int f0, f1, f9, f11;
                 line_fields(S, s, f0, f1, f9, f11);
                 if (f11 < e) {
+                    staged = true;
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
                     const unsigned long long k8 = load8(text, f0);
                     // names of up to 7 bytes compare in registers: the name bytes and the whitespace right after them
@@ -617,20 +690,43 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 const int new_hint = __shfl_sync(0xffffffffu, cid, top);       // contig hint follows the last kept line
                 if (new_hint != hint) set_hint(new_hint);
             }
-            // ---- 5. raw records ------------------------------------------------------------------------------------------
+            // ---- 5. records: finished from the staged bytes, raw only for unusual shapes -------------------------------------
+            int ev_idx = 0, name_off = 0, name_len = 0;
+            double diff = 0.0;
+            uint32_t fl = 0u;
+            bool fin = false;
+            if (emit) {
+                fl = (status & ST_CAND) ? MC_RF_CAND : 0u;
+                uint32_t eq = 0u;
+                fin = staged && finish_line(S, text, s, ev_idx, diff, eq, name_off, name_len);
+                if (fin) fl |= eq;
+                else { fl |= MC_RF_RAW; ev_idx = 0; diff = 0.0; name_off = 0; name_len = 0; atomicAdd(&S.cnt[6], 1u); }
+            }
+            // read name of the previous recorded line of this pass (same read <=> equal bytes, extract_contexts.py:161);
+            // the first record of a pass and neighbours of raw records are compared in stage 3 instead
+            {
+                const uint32_t my_span = fin ? ((uint32_t)(s + name_off) | ((uint32_t)name_len << 16)) : 0xFFFFFFFFu;
+                const uint32_t below_e = emit_m & lt_mask;
+                const uint32_t prev_span = __shfl_sync(0xffffffffu, my_span, below_e ? 31 - __clz(below_e) : lane);
+                if (fin && below_e && prev_span != 0xFFFFFFFFu) {
+                    fl |= MC_RF_SEGKNOWN;
+                    if ((int)(prev_span >> 16) != name_len || staged_differ(text, (int)(prev_span & 0xFFFFu), s + name_off, name_len))
+                        fl |= MC_RF_NEWREAD;
+                }
+            }
             if (emit) {
                 const unsigned long long slot = slot_cur + __popc(emit_m & lt_mask);
                 if (slot < rec_cap) {
                     const int64_t goff = G0 + s;
-                    const uint32_t fl = ((status & ST_CAND) ? MC_RF_CAND : 0u) | MC_RF_RAW;
                     uint4 a, b;
-                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                   // line_lo
-                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                  // line_hi | name_off (0)
-                    a.z = (uint32_t)pos;                                     // pos
-                    a.w = 0u;                                                // event_idx
-                    b.x = 0u; b.y = 0u;                                      // diff
-                    b.z = (uint32_t)cid << 16;                               // name_len (0) | contig
-                    b.w = fl;                                                // flags | pad
+                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                              // line_lo
+                    a.y = ((uint32_t)(goff >> 32) & 0xFFFFu) | ((uint32_t)name_off << 16);   // line_hi | name_off
+                    a.z = (uint32_t)pos;                                                // pos
+                    a.w = (uint32_t)ev_idx;                                             // event_idx
+                    const unsigned long long db = (unsigned long long)__double_as_longlong(diff);
+                    b.x = (uint32_t)db; b.y = (uint32_t)(db >> 32);                     // diff
+                    b.z = (uint32_t)name_len | ((uint32_t)cid << 16);                   // name_len | contig
+                    b.w = fl;                                                           // flags | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
                     dst[0] = a;
                     dst[1] = b;
@@ -666,9 +762,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         if (c_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)c_lines);
         if (c_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)c_kept);
     }
-    if (lane < 6) {
+    if (lane < 7) {
         const int which = lane == 0 ? MC_C_SHORT : lane == 1 ? MC_C_UNKNOWN_CONTIG : lane == 2 ? MC_C_NNN : lane == 3 ? MC_C_BADPOS
-                        : lane == 4 ? MC_C_LONGLINE : MC_C_OVERFLOW;
+                        : lane == 4 ? MC_C_LONGLINE : lane == 5 ? MC_C_OVERFLOW : MC_C_RAW;
         const unsigned v = S.cnt[lane];
         if (v) atomicAdd(&d_counters[which], (unsigned long long)v);
     }
