@@ -75,7 +75,9 @@ typedef struct mc_record {
     uint16_t name_len;
     uint16_t contig;       /* contig index */
     uint8_t flags;         /* MC_RF_* */
-    uint8_t pad[3];
+    uint8_t kbits_fwd;     /* bit c: the forward-strand marked copy holds 'M' at pos + c, c < k (meth_fwd[pos:pos+k], :176) */
+    uint8_t kbits_rev;     /* same for the reverse-strand copy */
+    uint8_t pad;
 } mc_record;               /* 32 bytes */
 
 #define MC_RF_EQ 1u        /* reference_kmer (col 3) == model_kmer (col 10) */
@@ -131,7 +133,7 @@ enum { MC_CALL = 0, MC_TOO_MANY_SKIPS = 1, MC_MULTI_M = 2, MC_NONE = 3 /* empty 
 #define MC_CE_CONTEXT 1u   /* window within k of a contig end (reference: IndexError / sys.exit, :195, :224) */
 #define MC_CE_MODELKEY 2u  /* base after the target not in ACGTM (reference: KeyError -> sys.exit, :218-223) */
 #define MC_CE_BADNUM 4u    /* a fed line had an unsupported numeric field */
-#define MC_CE_COLUMN 8u    /* more than 128 events in one column (pairwise-sum block limit) */
+#define MC_CE_COLUMN 8u    /* columns with more than 128 events outgrew the spill arena of mc_build_windows */
 #define MC_CE_SPACING 16u  /* multi-M shift of 0 (reference: 'n diffs off' -> sys.exit, :257-266) */
 
 /* ---- classifier (host struct holding device pointers; layout mirrors sklearn's fitted attributes) ---- */
@@ -244,12 +246,14 @@ int mc_segment_quality(const uint8_t *d_text, const mc_record *d_rec, const uint
  * write) so rows come out in file order.  d_rec must come from mc_order_records (MC_RF_SEGKNOWN / MC_RF_NEWREAD set)
  * and d_seg_start from mc_segment_reads on the same records.  d_seg_count is scratch of seg_cap uint32.  d_ncalls[0]
  * receives the number of rows (all kinds); rows beyond call_cap are dropped and d_ncalls[1] is set.  Segments whose
- * quality is below qual_thresh are skipped entirely (:167).  d_ws: mc_workspace_bytes(rec_cap).
+ * quality is below qual_thresh are skipped entirely (:167).  d_ws: mc_workspace_bytes(rec_cap).  d_spill (spill_cap doubles)
+ * holds the values of columns with more than 128 events while numpy's recursive halving is replayed on them (a stalled
+ * read); a chunk that needs more than spill_cap flags the row with MC_CE_COLUMN.
  */
 int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap, const uint32_t *d_seg_start,
                      const uint64_t *d_nseg, int64_t seg_cap, const double *d_seg_qual, const mc_refindex *ref, int skip_thresh,
                      double qual_thresh, int two_models, mc_call *d_calls, int64_t call_cap, uint32_t *d_seg_count,
-                     uint64_t *d_ncalls, void *d_ws, void *stream);
+                     uint64_t *d_ncalls, void *d_ws, double *d_spill, int64_t spill_cap, void *stream);
 
 /*
  * Chunk / rank edges.  The reference closes a window when it reads the NEXT kept line (extract_contexts.py:179), so the

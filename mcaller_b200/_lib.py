@@ -48,7 +48,7 @@ class SynthSpec(C.Structure):
 
 
 RECORD_DTYPE = np.dtype([("line_lo", "<u4"), ("line_hi", "<u2"), ("name_off", "<u2"), ("pos", "<i4"), ("event_idx", "<i4"),
-                         ("diff", "<f8"), ("name_len", "<u2"), ("contig", "<u2"), ("flags", "u1"), ("pad", "u1", (3,))])
+                         ("diff", "<f8"), ("name_len", "<u2"), ("contig", "<u2"), ("flags", "u1"), ("kbits_fwd", "u1"), ("kbits_rev", "u1"), ("pad", "u1")])
 assert RECORD_DTYPE.itemsize == 32
 
 CALL_DTYPE = np.dtype([("read_off", "<i8"), ("prob", "<f8"), ("feat", "<f8", (MC_MAXK + 1,)), ("read_len", "<i4"),
@@ -94,9 +94,10 @@ _PROTOS = {
     "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     # d_rec, d_n_records, rec_cap, d_seg_start, d_nseg, seg_cap, d_seg_qual, ref, skip, qual, two_models, d_calls, call_cap,
-    # d_seg_count, d_ncalls, d_ws, stream
+    # d_seg_count, d_ncalls, d_ws, d_spill, spill_cap, stream
     "mc_build_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RefIndex),
-                                   C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p]),
     "mc_carry_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     # d_rows, d_ncalls, d_rec, d_n_records, d_seg_start, d_nseg, d_seg_qual, qual_thresh, d_carry, d_nrows_out, d_abort, stream
     "mc_carry_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,

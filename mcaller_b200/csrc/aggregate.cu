@@ -284,33 +284,6 @@ k_diffs_values(const uint8_t *__restrict__ text, const mc_diffs_row *__restrict_
     ncol[i] = (uint32_t)nc;
 }
 
-// numpy's pairwise summation (np.add.reduce over a contiguous float64 vector) of f(x_i), i in [0, n)
-template <class F>
-__device__ double pairwise_sum(F f, int64_t i0, int64_t n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
-        return res;
-    }
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = f(i0 + j);
-        int64_t i = 8;
-        for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i0 + i + j));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
-        return res;
-    }
-    int64_t n2 = n / 2;
-    n2 -= n2 % 8;
-    const double left = pairwise_sum(f, i0, n2);
-    return __dadd_rn(left, pairwise_sum(f, i0 + n2, n - n2));
-}
-
 // per locus (CSR over the sorted rows) and column: n, np.mean(x), np.add.reduce((x - mean)**2)
 __global__ void __launch_bounds__(128)
 k_diffs_colstats(const double *__restrict__ vals, const uint32_t *__restrict__ ncol, const uint32_t *__restrict__ locus_off, int64_t n_loci,
@@ -322,9 +295,9 @@ k_diffs_colstats(const double *__restrict__ vals, const uint32_t *__restrict__ n
     const int64_t r0 = locus_off[l], n = (int64_t)locus_off[l + 1] - r0;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     auto x = [&](int64_t i) { return c < (int)ncol[i] ? vals[i * (MC_MAXK + 1) + c] : nan; };   // ragged rows: pandas fills NaN
-    const double mean = __ddiv_rn(pairwise_sum(x, r0, n), (double)n);
+    const double mean = __ddiv_rn(mc_pairwise_sum(x, r0, n), (double)n);
     auto sq = [&](int64_t i) { const double d = __dsub_rn(x(i), mean); return __dmul_rn(d, d); };
-    const double ss = pairwise_sum(sq, r0, n);
+    const double ss = mc_pairwise_sum(sq, r0, n);
     stats[2 * t] = mean;
     stats[2 * t + 1] = ss;
 }

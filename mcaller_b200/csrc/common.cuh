@@ -77,3 +77,30 @@ __device__ __forceinline__ int64_t mc_dev_count(const unsigned long long *d_n, i
     const unsigned long long v = *d_n;
     return v < (unsigned long long)cap ? (int64_t)v : cap;
 }
+
+// numpy's pairwise summation (np.add.reduce over a contiguous float64 vector) of f(x_i), i in [0, n)
+template <class F>
+__device__ double mc_pairwise_sum(F f, int64_t i0, int64_t n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = f(i0 + j);
+        int64_t i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i0 + i + j));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    const double left = mc_pairwise_sum(f, i0, n2);
+    return __dadd_rn(left, mc_pairwise_sum(f, i0 + n2, n - n2));
+}

@@ -137,11 +137,13 @@ int mc_exscan_u32_dev(const uint32_t *d_in, uint32_t *d_out, int64_t n_cap, cons
 }
 
 // workspace layout used by the stages: [A: uint32 n][B: uint32 n][scan sums]
+extern "C" int64_t mc_windows_workspace_bytes(int64_t rec_cap);
 extern "C" int64_t mc_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
     const int64_t a = ((n * 4 + 255) / 256) * 256;
-    // + the per-block row totals / offsets of the window builder (2 uint32 per block of records; sized for blocks of 1024)
-    return 2 * a + ((8 * ((n + 1023) / 1024) + 255) / 256) * 256 + mc_exscan_ws_bytes(n) + 512;
+    const int64_t mine = 2 * a + mc_exscan_ws_bytes(n) + 512;
+    const int64_t win = mc_windows_workspace_bytes(n);             // unit counts, first-'M' indices, block totals, tags (windows.cu)
+    return mine > win ? mine : win;
 }
 static inline uint32_t *ws_a(void *ws) { return reinterpret_cast<uint32_t *>(ws); }
 static inline uint32_t *ws_b(void *ws, int64_t n) { return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ws) + ((n * 4 + 255) / 256) * 256); }

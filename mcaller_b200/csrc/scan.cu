@@ -696,7 +696,12 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             uint32_t fl = 0u;
             bool fin = false;
             if (emit) {
-                fl = (status & ST_CAND) ? MC_RF_CAND : 0u;
+                fl = 0u;
+                if (status & ST_CAND) {
+                    // the targets inside this line's k-mer on either strand (meth_ref[pos:pos+k], :176) travel with the record
+                    const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
+                    fl = MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
+                }
                 uint32_t eq = 0u;
                 fin = staged && finish_line(S, text, s, ev_idx, diff, eq, name_off, name_len);
                 if (fin) fl |= eq;
@@ -726,7 +731,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     const unsigned long long db = (unsigned long long)__double_as_longlong(diff);
                     b.x = (uint32_t)db; b.y = (uint32_t)(db >> 32);                     // diff
                     b.z = (uint32_t)name_len | ((uint32_t)cid << 16);                   // name_len | contig
-                    b.w = fl;                                                           // flags | pad
+                    b.w = fl;                                                           // flags | kbits_fwd | kbits_rev | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
                     dst[0] = a;
                     dst[1] = b;

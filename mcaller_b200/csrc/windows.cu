@@ -14,72 +14,46 @@
 // only read-level state they need is `last_read` / `first_read_ind` (:161-174), i.e. the read's first line with an 'M',
 // which k_first_m finds per read beforehand.  Reads whose first record lies within k of the contig start stay one unit:
 // a window at position 0 never closes (`if mpos and`, :179) and keeps its columns across non-candidate lines.
-// A block of 256 threads owns 3072 consecutive records, compacts the unit starts among them into shared memory and
-// runs one thread per unit; two passes (count rows / write rows) so rows land in file order.  Column sums are
-// accumulated in numpy's pairwise order (8 running lanes + sequential tail) so np.mean is reproduced bit for bit.
+//
+// A block of 256 threads owns WIN_RECS consecutive records.  It STAGES them in shared memory with coalesced loads (the
+// fields the state machine reads: position, event index, flags, the k-mer's target bits on both strands that stage 1
+// left in the record, contig; the write pass also the float64 deviation), compacts the unit starts among them and runs
+// one thread per unit through the literal state machine -- every per-record step is then a shared-memory read instead of
+// a dependent global load.  Two passes (count rows / write rows) so rows land in file order.
+//
+// Column values are not accumulated while the lines go by: the state machine only tags every fed record with the column
+// slot it went to and remembers where each slot's current contents begin.  When a window closes, the values of a column
+// are read back from the staged records in file order and summed exactly like numpy does (np.mean -> add.reduce:
+// sequential below 8 values, 8 running lanes + tail up to 128, recursive halving above), so the float64 column means are
+// reproduced bit for bit for ANY number of events per column; nothing lives in local memory.
 #include "common.cuh"
 
 namespace {
 
-// Column values live in local memory; the column counts (8 x 8 bits, saturating at 255 -- more than 128 events in a column is
-// reported as MC_CE_COLUMN anyway) and the column map (8 x 4 bits) are packed in registers, so the count pass and the
-// control flow of the write pass touch no memory.
-#ifndef MC_WIN_SMEM_ROWS
-#define MC_WIN_SMEM_ROWS 2
+#ifndef MC_WIN_ITEMS
+#define MC_WIN_ITEMS 10
 #endif
-constexpr int SROWS = MC_WIN_SMEM_ROWS;           // first values of every column kept in shared memory (0: all in local memory)
-struct ColState {
-    double lane[MC_MAXK][8];
-    double pend[MC_MAXK][8];
-    double *sm;                                   // this thread's [SROWS][MC_MAXK] slice of shared memory, thread-interleaved
-    __device__ __forceinline__ double get(int c, int j) const {
-        if (SROWS > 0 && j < SROWS) return sm[(j * MC_MAXK + c) * SM_STRIDE];
-        return pend[c][j];
-    }
-    __device__ __forceinline__ void put(int c, int j, double v) {
-        if (SROWS > 0 && j < SROWS) sm[(j * MC_MAXK + c) * SM_STRIDE] = v;
-        else pend[c][j] = v;
-    }
-    static constexpr int SM_STRIDE = 256;         // = WIN_THREADS (asserted below): element e of thread t sits at [e][t]
-};
+constexpr int WIN_THREADS = 256, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 2560 records per block
+constexpr int WIN_UNITS = WIN_RECS / 2 + 2;       // a unit holds a candidate and is followed by a non-candidate: <= ceil(n/2) units
+static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
+constexpr uint32_t TAG_NONE = 0xFu;               // record fed no column
+
+// ---- staged record: {pos, event_idx, flags | kbits_fwd << 8 | kbits_rev << 16 | tag << 24, contig} -----------------------
+__device__ __forceinline__ uint4 stage_word(const mc_record *p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return make_uint4(a.z, a.w, (b.w & 0x00FFFFFFu) | (TAG_NONE << 24), b.z >> 16);
+}
+__device__ __forceinline__ double stage_diff(const mc_record *p) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
+}
+
 __device__ __forceinline__ int cnt_get(unsigned long long cnts, int c) { return (int)((cnts >> (8 * c)) & 0xFFull); }
 __device__ __forceinline__ void cnt_inc(unsigned long long &cnts, int c) {
-    if (cnt_get(cnts, c) < 255) cnts += 1ull << (8 * c);
+    if (cnt_get(cnts, c) < 255) cnts += 1ull << (8 * c);           // saturates: 255 means "255 or more", recounted when it matters
 }
 __device__ __forceinline__ void cnt_clear(unsigned long long &cnts, int c) { cnts &= ~(0xFFull << (8 * c)); }
 __device__ __forceinline__ int map_get(uint32_t mp, int c) { return (int)((mp >> (4 * c)) & 0xFu); }
-
-__device__ __forceinline__ void col_push(ColState &C, unsigned long long &cnts, int c, double v) {
-    const int n = cnt_get(cnts, c);
-    const int j = n & 7;
-    C.put(c, j, v);
-    cnt_inc(cnts, c);
-    if (j == 7) {
-        if (n == 7) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) C.lane[c][i] = C.get(c, i);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) C.lane[c][i] = __dadd_rn(C.lane[c][i], C.get(c, i));
-        }
-    }
-}
-
-// numpy add.reduce pairwise order for n <= 128 (see oracle/mcaller_oracle.c np_pairwise), then / n
-__device__ __forceinline__ double col_mean(const ColState &C, unsigned long long cnts, int c) {
-    const int n = cnt_get(cnts, c);
-    double res;
-    if (n < 8) {
-        res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, C.get(c, i));
-    } else {
-        const double *r = C.lane[c];
-        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (int i = 0; i < (n & 7); ++i) res = __dadd_rn(res, C.get(c, i));
-    }
-    return __ddiv_rn(res, (double)n);
-}
 
 __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
 
@@ -104,17 +78,10 @@ __device__ __forceinline__ uint8_t comp_base(uint8_t c) {
     }
 }
 
-#ifndef MC_WIN_ITEMS
-#define MC_WIN_ITEMS 12
-#endif
-constexpr int WIN_THREADS = 256, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 3072 records per block: ~230 units, one per thread
-static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
-static_assert(ColState::SM_STRIDE == WIN_THREADS, "shared-memory column slices are interleaved by thread");
-
 // first line of each read with an 'M' under the per-line strand guess (:169-176): record index and event index
 __global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ rec, const uint32_t *__restrict__ seg_start, int64_t seg_cap,
-                                                const unsigned long long *__restrict__ d_nseg, mc_refindex R,
-                                                uint32_t *__restrict__ first_idx, int32_t *__restrict__ first_ind) {
+                                                const unsigned long long *__restrict__ d_nseg, uint32_t *__restrict__ first_idx,
+                                                int32_t *__restrict__ first_ind) {
     const int64_t n_seg = mc_dev_count(d_nseg, seg_cap);
     const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= n_seg) return;
@@ -122,67 +89,163 @@ __global__ void __launch_bounds__(128) k_first_m(const mc_record *__restrict__ r
     uint32_t fi = 0xFFFFFFFFu;
     int32_t ev = 0;
     for (uint32_t i = b; i < e; ++i) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rec + i)), c = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1);
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1);
         const uint32_t fl = c.w & 0xFFu;
         if (!(fl & MC_RF_CAND)) continue;
-        const int pos = (int)a.z, cid = (int)(c.z >> 16);
         const int rev = !(fl & MC_RF_EQ);
-        uint32_t bits = 0u;
-        if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, R.k);
-        if (bits) { fi = i; ev = (int32_t)a.w; break; }
+        const uint32_t bits = rev ? ((c.w >> 16) & 0xFFu) : ((c.w >> 8) & 0xFFu);      // 'M's of the k-mer on that strand (stage 1)
+        if (bits) { fi = i; ev = (int32_t)__ldg(reinterpret_cast<const uint4 *>(rec + i)).w; break; }
     }
     first_idx[seg] = fi;
     first_ind[seg] = ev;
 }
 
+// spill arena for columns with more than 128 events (numpy's recursive halving needs random access to the values)
+struct Spill {
+    double *buf;
+    unsigned long long cap;
+    unsigned long long *cursor;
+};
+
+// where a unit finds the staged fields of record i: this block's shared memory, or global memory past the block's range
+struct ColSrc {
+    const uint4 *s_rec;
+    const double *s_diff;
+    const mc_record *rec;
+    const uint8_t *g_tag;
+    int64_t base;
+};
+__device__ __forceinline__ uint32_t cs_tag(const ColSrc &S, uint32_t i) {
+    const int64_t j = (int64_t)i - S.base;
+    return (j >= 0 && j < WIN_RECS) ? (S.s_rec[j].z >> 24) : (uint32_t)S.g_tag[i];
+}
+__device__ __forceinline__ double cs_diff(const ColSrc &S, uint32_t i) {
+    const int64_t j = (int64_t)i - S.base;
+    return (j >= 0 && j < WIN_RECS) ? S.s_diff[j] : stage_diff(S.rec + i);
+}
+// np.add.reduce of a column with 8 or more values (rare: P(8+ events on one position) < 1 %), kept out of line so the
+// common path stays small: 8 running lanes + sequential tail up to 128 values, recursive halving above
+__device__ __noinline__ double col_sum_big(const ColSrc S, uint32_t src, uint32_t f0, uint32_t upto, int n, Spill spill, uint32_t *err,
+                                           int *n_out) {
+    double res = 0.0;
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = 0.0;
+        const int full = n - (n % 8);
+        int t = 0;
+        uint32_t j = f0;
+        for (; j < upto && t < full; ++j) {
+            if (cs_tag(S, j) != src) continue;
+            const double v = cs_diff(S, j);
+            // element t of the column goes to running lane t % 8 (the first eight start the lanes)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((t & 7) == q) r[q] = t < 8 ? v : __dadd_rn(r[q], v);
+            ++t;
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; j < upto; ++j)
+            if (cs_tag(S, j) == src) res = __dadd_rn(res, cs_diff(S, j));
+        *n_out = n;
+        return res;
+    }
+    // more than 128 events in one column (a stalled read): the 8-bit counter saturates at 255, so recount; numpy halves
+    // recursively, which needs the values side by side -> gather them into the spill arena
+    n = 0;
+    for (uint32_t j = f0; j < upto; ++j) n += (cs_tag(S, j) == src);
+    *n_out = n;
+    const unsigned long long at = atomicAdd(spill.cursor, (unsigned long long)n);
+    if (at + (unsigned long long)n > spill.cap) { *err |= MC_CE_COLUMN; return 0.0; }
+    double *a = spill.buf + at;
+    int t = 0;
+    for (uint32_t j = f0; j < upto; ++j)
+        if (cs_tag(S, j) == src) a[t++] = cs_diff(S, j);
+    return mc_pairwise_sum([a](int64_t q) { return a[q]; }, 0, n);
+}
+
 template <bool WRITE>
-__global__ void __launch_bounds__(WIN_THREADS)
+__global__ void __launch_bounds__(WIN_THREADS, 3)
 k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned long long *__restrict__ d_n_records,
           const uint32_t *__restrict__ seg_start, int64_t seg_cap, const unsigned long long *__restrict__ d_nseg,
           const double *__restrict__ seg_qual, const uint32_t *__restrict__ first_idx, const int32_t *__restrict__ first_ind_arr,
           mc_refindex R, int skip_thresh, double qual_thresh, int two_models, mc_call *__restrict__ calls,
           unsigned long long call_cap, uint32_t *__restrict__ unit_cnt /* [n_records], written at unit starts */,
-          uint32_t *__restrict__ blk_tot, const uint32_t *__restrict__ blk_off) {
-    __shared__ uint32_t s_unit[WIN_RECS];         // record index of each unit start of the block, in record order
-    __shared__ uint32_t s_off[WIN_RECS];          // write pass: row offset of each unit
-    __shared__ uint16_t s_seg[WIN_RECS];          // read segment of each unit, relative to the block's first record's
+          uint32_t *__restrict__ blk_tot, const uint32_t *__restrict__ blk_off, uint8_t *__restrict__ g_tag /* [n_records] */, Spill spill) {
+    __shared__ uint32_t s_unit[WIN_UNITS];        // record index of each unit start of the block, in record order
+    __shared__ uint32_t s_off[WIN_UNITS];         // write pass: row offset of each unit
+    __shared__ uint16_t s_seg[WIN_UNITS];         // read segment of each unit, relative to the block's first record's
     __shared__ int s_warp[WIN_THREADS / 32 + 1];
     __shared__ int64_t s_seg0;
-    extern __shared__ __align__(16) double s_cols[];              // write pass: [SROWS][MC_MAXK][WIN_THREADS] first values of each column
+    extern __shared__ __align__(16) uint4 s_dyn[];                // [WIN_RECS] staged records, then (write pass) [WIN_RECS] float64 deviations
+    uint4 *s_rec = s_dyn;
+    double *s_diff = reinterpret_cast<double *>(s_dyn + WIN_RECS);
     const int k = R.k;
     // the record / segment counts live on the device; the grid was sized for rec_cap records
     const int64_t n_records = mc_dev_count(d_n_records, rec_cap), n_seg = mc_dev_count(d_nseg, seg_cap);
-    if ((int64_t)blockIdx.x * WIN_RECS >= n_records || n_seg <= 0) {       // block-uniform
+    const int64_t base = (int64_t)blockIdx.x * WIN_RECS;
+    if (base >= n_records || n_seg <= 0) {                        // block-uniform
         if (!WRITE && threadIdx.x == 0) blk_tot[blockIdx.x] = 0u;
         return;
     }
+    // ---- stage the block's records (coalesced: a warp reads 32 consecutive records) ------------------------------------------
+    for (int j = threadIdx.x; j < WIN_RECS; j += WIN_THREADS) {
+        const int64_t i = base + j;
+        if (i < n_records) {
+            s_rec[j] = stage_word(rec + i);
+            if (WRITE) s_diff[j] = stage_diff(rec + i);
+        } else {
+            s_rec[j] = make_uint4(0u, 0u, TAG_NONE << 24, 0u);
+        }
+    }
+    if (threadIdx.x == 0) {                       // segment of the block's first record: last segment starting at or before it
+        int64_t lo = 0, hi = n_seg - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if ((int64_t)__ldg(seg_start + mid) <= base) lo = mid; else hi = mid - 1;
+        }
+        s_seg0 = lo;
+    }
+    __syncthreads();
+    // staged view of record i (this block's range) or a global read (a unit that runs past the block's last record)
+    auto rec_word = [&](uint32_t i) -> uint4 {
+        const int64_t j = (int64_t)i - base;
+        return (j >= 0 && j < WIN_RECS) ? s_rec[j] : stage_word(rec + i);
+    };
+    auto rec_diff = [&](uint32_t i) -> double {
+        const int64_t j = (int64_t)i - base;
+        return (WRITE && j >= 0 && j < WIN_RECS) ? s_diff[j] : stage_diff(rec + i);
+    };
+    auto tag_set = [&](uint32_t i, uint32_t t) {
+        const int64_t j = (int64_t)i - base;
+        if (j >= 0 && j < WIN_RECS) s_rec[j].z = (s_rec[j].z & 0x00FFFFFFu) | (t << 24);
+        else g_tag[i] = (uint8_t)t;
+    };
+    auto tag_get = [&](uint32_t i) -> uint32_t {
+        const int64_t j = (int64_t)i - base;
+        return (j >= 0 && j < WIN_RECS) ? (s_rec[j].z >> 24) : (uint32_t)g_tag[i];
+    };
     // ---- unit starts among this block's records, compacted in record order ------------------------------------------------
     int nu;
     {
-        const int64_t base = (int64_t)blockIdx.x * WIN_RECS;
-        if (threadIdx.x == 0) {                   // segment of the block's first record: last segment starting at or before it
-            int64_t lo = 0, hi = n_seg - 1;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi + 1) >> 1;
-                if ((int64_t)__ldg(seg_start + mid) <= base) lo = mid; else hi = mid - 1;
-            }
-            s_seg0 = lo;
-        }
-        const int64_t i0 = base + (int64_t)threadIdx.x * WIN_ITEMS;
+        const int j0 = threadIdx.x * WIN_ITEMS;
+        const int64_t i0 = base + j0;
         uint32_t prev_cand = 0u;
-        if (i0 > 0 && i0 <= n_records) prev_cand = __ldg(reinterpret_cast<const uint4 *>(rec + i0 - 1) + 1).w & MC_RF_CAND;
+        if (i0 > 0 && i0 <= n_records)
+            prev_cand = (j0 > 0 ? s_rec[j0 - 1].z : __ldg(reinterpret_cast<const uint4 *>(rec + i0 - 1) + 1).w) & MC_RF_CAND;
         uint32_t umask = 0u, nmask = 0u;          // unit starts / read starts among this thread's records
 #pragma unroll
         for (int j = 0; j < WIN_ITEMS; ++j) {
             const int64_t i = i0 + j;
             if (i < n_records) {
-                const uint32_t fl = __ldg(reinterpret_cast<const uint4 *>(rec + i) + 1).w & 0xFFu;
+                const uint4 w = s_rec[j0 + j];
+                const uint32_t fl = w.z & 0xFFu;
                 const uint32_t cand = fl & MC_RF_CAND;
                 bool u;
                 if (i == 0 || (fl & MC_RF_NEWREAD)) {
                     if (i != base) nmask |= 1u << j;
                     u = cand != 0u;
-                    if (!u) u = (int)__ldg(reinterpret_cast<const uint4 *>(rec + i)).z < k;      // whole-read unit (see above)
+                    if (!u) u = (int)w.x < k;                     // whole-read unit (see above)
                 } else {
                     u = cand != 0u && prev_cand == 0u;
                 }
@@ -196,25 +259,35 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
         const int on = off >> 16;
         for (uint32_t m = umask; m; m &= m - 1u) {
             const int j = __ffs(m) - 1;
-            s_unit[ou] = (uint32_t)(i0 + j);
-            s_seg[ou] = (uint16_t)(on + __popc(nmask & ((2u << j) - 1u)));
+            if (ou < WIN_UNITS) {
+                s_unit[ou] = (uint32_t)(i0 + j);
+                s_seg[ou] = (uint16_t)(on + __popc(nmask & ((2u << j) - 1u)));
+            }
             ++ou;
         }
         nu = total & 0xFFFF;
+        if (nu > WIN_UNITS) nu = WIN_UNITS;       // cannot happen (see WIN_UNITS)
         __syncthreads();
     }
     if (WRITE) {
         // row offsets of the block's units: counts of the first pass -> exclusive prefix in shared memory
-        for (int u = threadIdx.x; u < WIN_RECS; u += WIN_THREADS) s_off[u] = u < nu ? unit_cnt[s_unit[u]] : 0u;
-        __syncthreads();
-        uint32_t v[WIN_ITEMS];
+        constexpr int UPT = (WIN_UNITS + WIN_THREADS - 1) / WIN_THREADS;          // units per thread in the prefix
+        uint32_t v[UPT];
         int sum = 0;
 #pragma unroll
-        for (int j = 0; j < WIN_ITEMS; ++j) { v[j] = s_off[threadIdx.x * WIN_ITEMS + j]; sum += (int)v[j]; }
+        for (int j = 0; j < UPT; ++j) {
+            const int u = threadIdx.x * UPT + j;
+            v[j] = u < nu ? unit_cnt[s_unit[u]] : 0u;
+            sum += (int)v[j];
+        }
         int total;
         uint32_t run = blk_off[blockIdx.x] + (uint32_t)mc_block_exscan<WIN_THREADS>(sum, s_warp, total);
 #pragma unroll
-        for (int j = 0; j < WIN_ITEMS; ++j) { s_off[threadIdx.x * WIN_ITEMS + j] = run; run += v[j]; }
+        for (int j = 0; j < UPT; ++j) {
+            const int u = threadIdx.x * UPT + j;
+            if (u < WIN_UNITS) s_off[u] = run;
+            run += v[j];
+        }
         __syncthreads();
     }
     int my_rows = 0;
@@ -222,7 +295,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     const uint32_t b = s_unit[un];
     const int64_t seg = s_seg0 + s_seg[un];
     const uint32_t seg_b = __ldg(seg_start + seg), e_read = __ldg(seg_start + seg + 1);
-    const bool whole = (int)__ldg(reinterpret_cast<const uint4 *>(rec + seg_b)).z < k;     // the read is one unit
+    const bool whole = (int)rec_word(seg_b).x < k;             // the read is one unit
     uint32_t n_out = 0;
     const double myq = seg_qual[seg];
     if (myq < qual_thresh || (whole && b != seg_b)) {          // whole read dropped (:167) / unit covered by the whole-read unit
@@ -233,10 +306,11 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     uint32_t out_pos = WRITE ? s_off[un] : 0u;
     const uint32_t fidx = __ldg(first_idx + seg);
 
-    alignas(16) ColState C;
-    C.sm = WRITE ? s_cols + threadIdx.x : nullptr;
     unsigned long long cnts = 0ull;                // events per column slot
     uint32_t mp = 0x76543210u;                     // window column -> column slot (the multi-M carry permutes it)
+    uint32_t fst[MC_MAXK];                         // record at which the current contents of each column slot begin
+#pragma unroll
+    for (int c = 0; c < MC_MAXK; ++c) fst[c] = b;
     bool started = b > fidx;     // read_name == last_read  (this read already had a line with 'M')
     bool has_mpos = false;
     int mpos = 0, first_ind = started ? __ldg(first_ind_arr + seg) : 0, last_rev = 0, last_cid = 0;
@@ -245,8 +319,28 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
 
 #define MPOS_TRUTHY (has_mpos && mpos != 0)
 
-    // emits the row(s) for the open window; `close_idx` = ordered index of the closing record (or ~0u)
-    auto emit_window = [&](uint32_t close_idx, int chrom_cid) {
+    // np.mean of the values that column slot `src` holds when the window closes at record `upto` (exclusive): the records
+    // tagged with the slot since fst[src], in file order, summed like numpy's add.reduce
+    auto col_mean = [&](int src, uint32_t upto, uint32_t &err) -> double {
+        int n = cnt_get(cnts, src);
+        uint32_t f0 = b;
+#pragma unroll
+        for (int c = 0; c < MC_MAXK; ++c)
+            if (c == src) f0 = fst[c];
+        double res = 0.0;
+        if (n < 8) {
+            for (uint32_t j = f0; j < upto; ++j)
+                if (tag_get(j) == (uint32_t)src) res = __dadd_rn(res, rec_diff(j));
+        } else {
+            const ColSrc S{s_rec, s_diff, rec, g_tag, base};
+            res = col_sum_big(S, (uint32_t)src, f0, upto, n, spill, &err, &n);
+        }
+        return __ddiv_rn(res, (double)n);
+    };
+
+    // emits the row(s) for the open window; `close_idx` = ordered index of the closing record (or ~0u); the window holds the
+    // records before `upto`
+    auto emit_window = [&](uint32_t close_idx, int chrom_cid, uint32_t upto) {
         int n_empty = 0;
         for (int c = 0; c < k; ++c) n_empty += (cnt_get(cnts, map_get(mp, c)) == 0);
         if (WRITE) {
@@ -266,6 +360,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
                 o.pad0 = 0;
                 o.seg = (uint32_t)seg;
                 o.pad1 = 0;
+                o.pad2 = 0;
                 uint32_t err = sticky_err;
                 uint32_t empty_mask = 0u;
                 const int64_t g = __ldg(R.d_base + last_cid) + mpos;
@@ -281,10 +376,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
                     for (int c = 0; c < k; ++c) {                 // :186-188 (forward reads are flipped)
                         const int src = map_get(mp, last_rev ? c : (k - 1 - c));
                         if (cnt_get(cnts, src) == 0) { o.feat[c] = 0.0; empty_mask |= 1u << c; }
-                        else {
-                            if (cnt_get(cnts, src) > 128) err |= MC_CE_COLUMN;
-                            o.feat[c] = col_mean(C, cnts, src);
-                        }
+                        else o.feat[c] = col_mean(src, upto, err);
                     }
                     o.feat[k] = myq;                              // :189-193
                     for (int c = k + 1; c <= MC_MAXK; ++c) o.feat[c] = 0.0;
@@ -334,6 +426,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
                 o.n_empty = 0; o.empty_mask = 0; o.model_sel = 0; o.label = 0; o.err = 0; o.pad0 = 0;
                 o.seg = (uint32_t)seg;
                 o.pad1 = 0;
+                o.pad2 = 0;
             }
             ++out_pos;
         }
@@ -344,16 +437,16 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     // The row-producing code (column means, divisions, context look-ups) is by far the heaviest path and a lane needs it
     // only once per ~20 records.  Run in rounds so the warp executes it together: each lane advances through its records
     // until it reaches a window close (or its end-of-read hand-off), then all lanes that have one emit, then the next round.
+    // a record the unit steps over beyond the block's staged range has its tag in global memory: start it as 'fed no column'
+    auto tag_init = [&](uint32_t q) {
+        if (WRITE && (int64_t)q - base >= WIN_RECS) g_tag[q] = (uint8_t)TAG_NONE;
+    };
     uint32_t i = b;
-    mc_record r = (b < e) ? load_rec(rec + b) : mc_record();
-    mc_record r_next = (b + 1 < e) ? load_rec(rec + b + 1) : mc_record();
+    uint4 r = (b < e) ? rec_word(b) : make_uint4(0u, 0u, 0u, 0u);
+    if (b < e) tag_init(b);
     auto advance = [&]() {
         ++i;
-        r = r_next;
-        if (i + 1 < e) r_next = load_rec(rec + i + 1);              // overlap the next record's latency with this one's work
-        // a lane streams its own 32-byte records: pull the 128-byte line 16 records ahead into L2 (L1 is left to the
-        // column state, which lives in local memory).  Count pass only: in the write pass the prefetch was measured slower.
-        if (!WRITE && (i & 3u) == 0u && (int64_t)i + 16 < n_records) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + i + 16));
+        if (i < e) { r = rec_word(i); tag_init(i); }
     };
     int rev = 0, first_m = -1, cid = 0, pos = 0;
     bool pending_close = false, handoff_done = false;
@@ -366,9 +459,17 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
             last_rev = rev;
             last_cid = cid;
             name_rec = i;
-            if (r.flags & MC_RF_BADNUM) sticky_err |= MC_CE_BADNUM;
-            if (WRITE) col_push(C, cnts, map_get(mp, first_m), r.diff);
-            else cnt_inc(cnts, map_get(mp, first_m));
+            if (r.z & MC_RF_BADNUM) sticky_err |= MC_CE_BADNUM;
+            const int slot = map_get(mp, first_m);
+            if (WRITE) {
+                if (cnt_get(cnts, slot) == 0) {
+#pragma unroll
+                    for (int c = 0; c < MC_MAXK; ++c)
+                        if (c == slot) fst[c] = i;
+                }
+                tag_set(i, (uint32_t)slot);
+            }
+            cnt_inc(cnts, slot);
         } else if (MPOS_TRUTHY) {                                  // :289-291
             has_mpos = false;
             reset_cols();
@@ -377,21 +478,21 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     for (;;) {
         // ---- phase 1: advance to the next emission point ---------------------------------------------------------------
         while (!pending_close && i < e) {
-            if (!whole && !(r.flags & MC_RF_CAND)) e = i + 1;      // the closer ends the unit
+            const uint32_t fl = r.z & 0xFFu;
+            if (!whole && !(fl & MC_RF_CAND)) e = i + 1;           // the closer ends the unit
             const bool same_read = started;
             if (!same_read) {                                      // :161-162
-                first_ind = r.event_idx;
-                if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+                first_ind = (int)r.y;
+                if (fl & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
             }
-            if (!same_read) rev = !(r.flags & MC_RF_EQ);           // :169-174
+            if (!same_read) rev = !(fl & MC_RF_EQ);                // :169-174
             else {
-                if (r.flags & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
-                rev = !(r.event_idx > first_ind);
+                if (fl & MC_RF_BADIDX) sticky_err |= MC_CE_BADNUM;
+                rev = !((int)r.y > first_ind);
             }
-            cid = r.contig;
-            pos = r.pos;
-            uint32_t bits = 0u;                                    // 'M's of meth_ref[pos:pos+k] (:176)
-            if (pos < __ldg(R.d_len + cid)) bits = mc_kmer_bits(rev ? R.d_site_rev : R.d_site_fwd, __ldg(R.d_base + cid) + pos, k);
+            cid = (int)r.w;
+            pos = (int)r.x;
+            const uint32_t bits = rev ? ((r.z >> 16) & 0xFFu) : ((r.z >> 8) & 0xFFu);   // 'M's of meth_ref[pos:pos+k] (:176), from stage 1
             first_m = bits ? (__ffs(bits) - 1) : -1;
             if (MPOS_TRUTHY && pos >= mpos + 1 && same_read) {     // :179 (the other-read case is the segment hand-off below)
                 pending_close = true;
@@ -418,7 +519,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
                 chrom = -1;
             }
         }
-        emit_window(close_idx, chrom);
+        emit_window(close_idx, chrom, i);
         if (pending_handoff) {
             handoff_done = true;
             continue;
@@ -464,14 +565,24 @@ __global__ void k_check_cap(const unsigned long long *d_ncalls, unsigned long lo
 
 }  // namespace
 
+extern "C" int64_t mc_windows_workspace_bytes(int64_t rec_cap) {
+    if (rec_cap < 1) rec_cap = 1;
+    auto up = [](int64_t bytes) { return ((bytes + 255) / 256) * 256; };
+    const int64_t nb = (rec_cap + WIN_RECS - 1) / WIN_RECS;
+    // [unit_cnt: u32 rec_cap][first_ind: i32 rec_cap][blk_tot, blk_off: u32 nb each][tags: u8 rec_cap][spill cursor][scan sums]
+    return up(rec_cap * 4) + up(rec_cap * 4) + up(2 * nb * 4) + up(rec_cap) + 256 + mc_exscan_ws_bytes(nb) + 512;
+}
+
 extern "C" int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap, const uint32_t *d_seg_start,
                                 const uint64_t *d_nseg, int64_t seg_cap, const double *d_seg_qual, const mc_refindex *ref,
                                 int skip_thresh, double qual_thresh, int two_models, mc_call *d_calls, int64_t call_cap,
-                                uint32_t *d_seg_count, uint64_t *d_ncalls, void *d_ws, void *stream) {
+                                uint32_t *d_seg_count, uint64_t *d_ncalls, void *d_ws, double *d_spill, int64_t spill_cap,
+                                void *stream) {
     MC_REQUIRE(d_rec && d_n_records && d_seg_start && d_nseg && d_seg_qual && ref && d_calls && d_seg_count && d_ncalls && d_ws,
                "null pointer");
     MC_REQUIRE(ref->k >= 1 && ref->k <= MC_MAXK, "k out of range");
     MC_REQUIRE(skip_thresh >= 0, "skip_thresh must be >= 0");
+    MC_REQUIRE(spill_cap == 0 || d_spill, "spill arena missing");
     cudaStream_t st = (cudaStream_t)stream;
     MC_CUDA_CHECK(cudaMemsetAsync(d_ncalls, 0, 16, st));
     if (seg_cap <= 0 || rec_cap <= 0) return MC_OK;
@@ -479,29 +590,33 @@ extern "C" int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_reco
     if (seg_cap > rec_cap) seg_cap = rec_cap;                       // a segment holds at least one record
     const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n_records);
     const unsigned long long *ds = reinterpret_cast<const unsigned long long *>(d_nseg);
-    // workspace: [unit_cnt: u32 rec_cap][first_ind: i32 seg_cap][blk_tot, blk_off: u32 nb each][scan sums]
     const int64_t nb = (rec_cap + WIN_RECS - 1) / WIN_RECS;
     auto up = [](int64_t bytes) { return ((bytes + 255) / 256) * 256; };
     uint8_t *w = reinterpret_cast<uint8_t *>(d_ws);
     uint32_t *unit_cnt = reinterpret_cast<uint32_t *>(w);
     int32_t *first_ind = reinterpret_cast<int32_t *>(w + up(rec_cap * 4));
-    uint32_t *blk_tot = reinterpret_cast<uint32_t *>(w + up(rec_cap * 4) + up(seg_cap * 4));
+    uint32_t *blk_tot = reinterpret_cast<uint32_t *>(w + 2 * up(rec_cap * 4));
     uint32_t *blk_off = blk_tot + nb;
-    void *scan_ws = w + up(rec_cap * 4) + up(seg_cap * 4) + up(2 * nb * 4);
+    uint8_t *tags = w + 2 * up(rec_cap * 4) + up(2 * nb * 4);
+    unsigned long long *spill_cursor = reinterpret_cast<unsigned long long *>(tags + up(rec_cap));
+    void *scan_ws = reinterpret_cast<uint8_t *>(spill_cursor) + 256;
+    MC_CUDA_CHECK(cudaMemsetAsync(spill_cursor, 0, 8, st));
+    const Spill spill{d_spill, (unsigned long long)spill_cap, spill_cursor};
     uint32_t *first_idx = d_seg_count;                             // caller's seg_cap-sized scratch
-    k_first_m<<<(unsigned)((seg_cap + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, seg_cap, ds, *ref, first_idx, first_ind);
+    k_first_m<<<(unsigned)((seg_cap + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, seg_cap, ds, first_idx, first_ind);
     MC_LAUNCH_CHECK();
-    k_windows<false><<<(unsigned)nb, WIN_THREADS, 0, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx, first_ind,
+    constexpr size_t rec_bytes = sizeof(uint4) * WIN_RECS, diff_bytes = sizeof(double) * WIN_RECS;
+    MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes));
+    MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rec_bytes + diff_bytes)));
+    k_windows<false><<<(unsigned)nb, WIN_THREADS, rec_bytes, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx, first_ind,
                                                           *ref, skip_thresh, qual_thresh, two_models, d_calls,
-                                                          (unsigned long long)call_cap, unit_cnt, blk_tot, nullptr);
+                                                          (unsigned long long)call_cap, unit_cnt, blk_tot, nullptr, tags, spill);
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(blk_tot, blk_off, nb, d_ncalls, scan_ws, st);
     if (rc) return rc;
-    constexpr size_t cols_bytes = sizeof(double) * SROWS * MC_MAXK * WIN_THREADS;
-    MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_bytes));
-    k_windows<true><<<(unsigned)nb, WIN_THREADS, cols_bytes, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx,
+    k_windows<true><<<(unsigned)nb, WIN_THREADS, rec_bytes + diff_bytes, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx,
                                                                   first_ind, *ref, skip_thresh, qual_thresh, two_models, d_calls,
-                                                                  (unsigned long long)call_cap, unit_cnt, nullptr, blk_off);
+                                                                  (unsigned long long)call_cap, unit_cnt, nullptr, blk_off, tags, spill);
     MC_LAUNCH_CHECK();
     k_check_cap<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
                                  reinterpret_cast<unsigned long long *>(d_ncalls) + 1);

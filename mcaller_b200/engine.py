@@ -25,6 +25,7 @@ S_STATS = 24                # 7 row statistics of mc_count_calls
 S_WORDS = 32
 # persistent device state (uint64 slots): global row index of the next chunk's slot 0, rows in the odd-row list
 P_ROW_BASE, P_N_ODD = 0, 1
+SPILL_CAP = 1 << 22         # doubles: values of columns with more than 128 events (a stalled read) while numpy's halving is replayed
 ODD_CAP = 1 << 16           # rows whose closing contig differs from their window's (reference quirk Q4); merged on the host
 
 
@@ -86,6 +87,7 @@ class Engine(object):
             self.d_carry = torch.zeros(CARRY_BYTES, dtype=torch.uint8, device=self.device)
             self.d_carry_out = torch.zeros(CALL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
             self.d_odd = torch.zeros(ODD_CAP * CALL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+            self.d_spill = torch.zeros(SPILL_CAP, dtype=torch.float64, device=self.device)
             self.h_small = np.zeros(S_WORDS, dtype=np.uint64)
             self.rec_cap_learned = 0          # largest demand seen so far (records reserved / rows written)
             self.call_cap_learned = 0
@@ -252,7 +254,8 @@ class Engine(object):
         rows1 = V(calls.data_ptr() + CALL_DTYPE.itemsize)
         check(L.mc_build_windows(V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()), self._status_ptr(S_NSEG),
                                  rec_cap, V(seg_qual.data_ptr()), self.ref.ref(), self.skip_thresh, self.qual_thresh, self.two_models,
-                                 rows1, call_cap, V(seg_count.data_ptr()), self._status_ptr(S_NCALLS), V(ws.data_ptr()), st))
+                                 rows1, call_cap, V(seg_count.data_ptr()), self._status_ptr(S_NCALLS), V(ws.data_ptr()),
+                                 V(self.d_spill.data_ptr()), SPILL_CAP, st))
         check(L.mc_chunk_guard(V(self.d_small.data_ptr()), rec_cap, self._status_ptr(S_NREC), rec_cap, self._status_ptr(S_NCALLS), call_cap,
                                self._status_ptr(S_ABORT), st))
         check(L.mc_carry_rows(V(calls.data_ptr()), self._status_ptr(S_NCALLS), V(rec_b.data_ptr()), self._status_ptr(S_NREC),
