@@ -184,16 +184,24 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * strand), that follows a candidate, or that is the first kept line of a run of chunks; with dense != 0 for
  * every kept line (needed with -q).  Records of one chunk are contiguous and in line order; warps reserve slots in
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
- * holes); d_tile_tab[chunk] = {first record slot, count | flags} (flags are consumed by mc_order_records, which also
- * drops the run-first records whose predecessor line turns out not to be a candidate).
+ * holes); d_tile_tab[chunk] = {first record slot, count | flags} and d_run_tab[run] = {records of the run, flags} are consumed
+ * by mc_order_records, which also drops the run-first records whose predecessor line turns out not to be a candidate.
+ * Records are finished here while the line is staged in shared memory (event index, np.round(event_mean - model_mean, 4),
+ * k-mer equality, read-name span, target bits of the k-mer, read-change flag against the previous record of the pass); only
+ * unusual shapes are left raw (MC_RF_RAW, counted in MC_C_RAW).
  * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
  * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
  * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
  * d_counters (MC_C_COUNT uint64) must be zeroed by the caller; d_text must be 16-byte and d_tile_tab 8-byte aligned.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,
-            mc_record *d_rec, int64_t rec_cap, uint32_t *d_tile_tab /* [2*n_tiles] */,
+            mc_record *d_rec, int64_t rec_cap, uint32_t *d_tile_tab /* [2*n_tiles] */, uint32_t *d_run_tab /* [2*n_runs] */,
             uint64_t *d_counters, void *stream);
+
+/* Chunks per run mc_scan uses for nbytes of text on the current device (consecutive chunks parsed by one warp); the run
+ * table holds ceil(mc_num_tiles(nbytes) / run length) entries of two uint32: {records of the run, flags}.  mc_order_records
+ * must be given the same run length. */
+int mc_scan_run_len(int64_t nbytes);
 
 /* Test / tuning hook: chunks per run of mc_scan (consecutive chunks parsed by one warp, which carries the
  * "last kept line" state between them).  0 = automatic (32, shortened for small inputs so every warp gets runs to
@@ -206,7 +214,7 @@ int64_t mc_num_tiles(int64_t nbytes);
 /* bytes of scratch needed by the scan-based stages below for up to n items */
 int64_t mc_workspace_bytes(int64_t n);
 
-/* Stage 2 -- put the records into file order (exclusive scan of the chunk table + gather).  d_rec_in is the stage-1
+/* Stage 2 -- put the records into file order (exclusive scan of the run table, then one warp per run gathers its chunks).  d_rec_in is the stage-1
  * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
  * records, which land densely in d_rec_out (rec_out_cap slots; rec_in_cap is always enough).  Records that stage 1 left
  * in raw form (MC_RF_RAW) are finished here, one thread per record: event index, the float64 np.round(event_mean -
@@ -214,9 +222,9 @@ int64_t mc_workspace_bytes(int64_t n);
  * changes between neighbouring records are flagged (MC_RF_NEWREAD).  d_scan_counters: the counter block mc_scan wrote
  * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
  * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
-int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles, const mc_record *d_rec_in,
-                     int64_t rec_in_cap, const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap,
-                     uint64_t *d_n_out, void *d_ws, void *stream);
+int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uint32_t *d_tile_tab, int64_t n_tiles, uint32_t *d_run_tab,
+                     int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
+                     mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the

@@ -100,6 +100,7 @@ int64_t format_range(const FormatArgs &A, int64_t lo, int64_t hi, std::string &d
         // the read name: bytes of this chunk's text, or (a window carried over a chunk edge) the name the caller kept
         const char *read = reinterpret_cast<const char *>(A.h_text) + c.read_off;
         size_t read_len = (size_t)c.read_len;
+        if (c.read_off >= 0 && !A.h_text) { err_row = i; err_flags = -6; return MC_EINVAL; }
         if (c.read_off < 0) {
             if (!A.carry_name) { err_row = i; err_flags = -4; return MC_EINVAL; }
             read = reinterpret_cast<const char *>(A.carry_name);
@@ -152,7 +153,7 @@ extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const
                                   const char *const *marked_rev, const int64_t *contig_len, int32_t n_contigs, int32_t k,
                                   const char *base_label, const char *mod_label, int32_t with_prob, int32_t max_threads, char *out,
                                   int64_t out_cap) {
-    if (!h_calls || !h_text || !contig_names || !marked_fwd || !marked_rev || !contig_len || !out || k < 1 || k > MC_MAXK ||
+    if (!h_calls || !contig_names || !marked_fwd || !marked_rev || !contig_len || !out || k < 1 || k > MC_MAXK ||
         !base_label || !mod_label || strlen(base_label) > 256 || strlen(mod_label) > 256) {
         mc_set_error("mc_format_rows: bad argument");
         return MC_EINVAL;
@@ -189,6 +190,7 @@ extern "C" int64_t mc_format_rows(const mc_call *h_calls, int64_t n_calls, const
         else if (eflags[(size_t)t] == -1) mc_set_error("mc_format_rows: contig index out of range");
         else if (eflags[(size_t)t] == -2) mc_set_error("mc_format_rows: context out of range");
         else if (eflags[(size_t)t] == -4) mc_set_error("mc_format_rows: row %lld was carried over a chunk edge but no read name was given", (long long)erow[(size_t)t]);
+        else if (eflags[(size_t)t] == -6) mc_set_error("mc_format_rows: row %lld names its read by offset but no text was given", (long long)erow[(size_t)t]);
         else if (eflags[(size_t)t] == -5)
             mc_set_error("mc_format_rows: the context of row %lld (position %d) covers a reference letter outside ACGTNM", (long long)erow[(size_t)t],
                          h_calls[erow[(size_t)t]].mpos);

@@ -152,57 +152,82 @@ static inline void *ws_s(void *ws, int64_t n) { return reinterpret_cast<uint8_t 
 namespace {
 
 // ---- stage 2: gather records into file order ----------------------------------------------------------------
-// Stage 1 records the first kept line of a run of chunks blindly because the line before it belongs to another warp.
-// With all chunks done the predecessor is known (every chunk reports the state of the last kept line seen so far in its
-// run): the record is dropped unless the previous kept line was a candidate (or there is none, so the first kept line of
-// the text stays: it may close a window handed over by the caller).
-__global__ void __launch_bounds__(256) k_resolve_fillers(uint32_t *__restrict__ tile_tab, int64_t n_tiles, uint32_t *__restrict__ cnt_clean,
-                                                        const unsigned long long *__restrict__ scan_counters, unsigned long long rec_in_cap) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_tiles) return;
+// Stage 1 hands over two tables: per chunk {first record slot, count | filler flag << 16 | state << 17} and per RUN of
+// consecutive chunks (one warp parsed them in order) {records of the run, filler flag | state of the run's last kept
+// line << 1}.  The order of the records is fixed run by run: only the ~n_chunks / 32 run entries are prefix-summed, a
+// warp then walks its run's chunk entries (most are empty in sparse mode) and copies the records.
+//
+// Stage 1 records the first kept line of a run blindly because the line before it belongs to another warp.  With all
+// runs done the predecessor is known (every run reports the state of its last kept line): the record is dropped unless
+// the previous kept line was a candidate (or there is none, so the first kept line of the text stays: it may close a
+// window handed over by the caller).
+__global__ void __launch_bounds__(256) k_run_resolve(uint32_t *__restrict__ run_tab, int64_t n_runs, uint32_t *__restrict__ cnt_clean,
+                                                    const unsigned long long *__restrict__ scan_counters, unsigned long long rec_in_cap) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
     // stage 1 ran out of record slots: its buffer has unwritten records.  Nothing is ordered (zero records come out), the
     // caller sees the overflow in the counters and runs the chunk again with a larger buffer.
     if (scan_counters && (scan_counters[MC_C_OVERFLOW] != 0ull || scan_counters[MC_C_RECORDS] > rec_in_cap)) {
-        cnt_clean[c] = 0u;
+        cnt_clean[r] = 0u;
         return;
     }
-    const uint32_t v = tile_tab[2 * c + 1];
-    uint32_t count = v & 0xFFFFu;
-    if ((v >> 16) & 1u) {
-        int64_t p = c - 1;
+    uint32_t count = run_tab[2 * r];
+    const uint32_t v = run_tab[2 * r + 1];
+    if (v & 1u) {
+        int64_t p = r - 1;
         uint32_t st = 0u;
-        while (p >= 0 && (st = (tile_tab[2 * p + 1] >> 17) & 3u) == 0u) --p;
+        while (p >= 0 && (st = (run_tab[2 * p + 1] >> 1) & 3u) == 0u) --p;
         if (p >= 0 && st == 1u && count > 0u) {
-            tile_tab[2 * c] += 1u;           // skip the filler (it is the chunk's first record)
+            run_tab[2 * r + 1] = v | 0x80000000u;           // the gather skips the filler (first record of its chunk)
             --count;
         }
     }
-    cnt_clean[c] = count;
+    cnt_clean[r] = count;
 }
 
-__global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ tile_cnt,
-                                               const uint32_t *__restrict__ tile_dst, int64_t n_tiles, const mc_record *__restrict__ in,
-                                               unsigned long long in_cap, mc_record *__restrict__ out, unsigned long long out_cap) {
-    // a warp owns 32 chunks; most hold no record (sparse mode), so the warp walks the non-empty ones and copies each
-    // chunk's records with one lane per 16-byte half record (coalesced 32-byte records, no per-thread copy loops)
+__global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ run_tab,
+                                                    const uint32_t *__restrict__ run_dst, int64_t n_tiles, int64_t n_runs, int run_len,
+                                                    const mc_record *__restrict__ in, unsigned long long in_cap, mc_record *__restrict__ out,
+                                                    unsigned long long out_cap) {
+    // a warp owns a run; lane j looks at the run's j-th chunk (32 at a time), the warp then copies each non-empty chunk's
+    // records with one lane per 16-byte half record (coalesced 32-byte records, no per-thread copy loops)
     const int lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long src = 0ull, dst = 0ull;
-    uint32_t cnt = 0u;
-    if (tile < n_tiles) {
-        cnt = tile_cnt[tile];
-        if (cnt) { src = tile_tab[2 * tile]; dst = tile_dst[tile]; }
-    }
-    uint32_t busy = __ballot_sync(0xffffffffu, cnt != 0u);
-    while (busy) {
-        const int l = __ffs(busy) - 1;
-        busy &= busy - 1u;
-        const unsigned long long s0 = __shfl_sync(0xffffffffu, src, l), d0 = __shfl_sync(0xffffffffu, dst, l);
-        const uint32_t c = __shfl_sync(0xffffffffu, cnt, l);
-        for (uint32_t h = lane; h < 2u * c; h += 32u) {              // half records
-            const unsigned long long j = h >> 1;
-            if (s0 + j >= in_cap || d0 + j >= out_cap) continue;     // records dropped by a capacity overflow
-            reinterpret_cast<uint4 *>(out + d0 + j)[h & 1u] = __ldg(reinterpret_cast<const uint4 *>(in + s0 + j) + (h & 1u));
+    const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (run >= n_runs) return;
+    const uint32_t rv = __ldg(run_tab + 2 * run + 1);
+    if (__ldg(run_tab + 2 * run) == 0u) return;                  // nothing recorded in this run
+    const bool drop = (rv >> 31) != 0u;
+    unsigned long long d_run = __ldg(run_dst + run);
+    const int64_t c0 = run * run_len, c1 = min(c0 + (int64_t)run_len, n_tiles);
+    for (int64_t cb = c0; cb < c1; cb += 32) {
+        const int64_t c = cb + lane;
+        unsigned long long src = 0ull;
+        uint32_t cnt = 0u;
+        if (c < c1) {
+            const uint2 e = __ldg(reinterpret_cast<const uint2 *>(tile_tab) + c);
+            src = e.x;
+            cnt = e.y & 0xFFFFu;
+            if (drop && ((e.y >> 16) & 1u) && cnt > 0u) { src += 1ull; --cnt; }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned long long dst = d_run + (incl - cnt);
+        d_run += __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t busy = __ballot_sync(0xffffffffu, cnt != 0u);
+        while (busy) {
+            const int l = __ffs(busy) - 1;
+            busy &= busy - 1u;
+            const unsigned long long s0 = __shfl_sync(0xffffffffu, src, l), d0 = __shfl_sync(0xffffffffu, dst, l);
+            const uint32_t n = __shfl_sync(0xffffffffu, cnt, l);
+            for (uint32_t h = lane; h < 2u * n; h += 32u) {              // half records
+                const unsigned long long j = h >> 1;
+                if (s0 + j >= in_cap || d0 + j >= out_cap) continue;     // records dropped by a capacity overflow
+                reinterpret_cast<uint4 *>(out + d0 + j)[h & 1u] = __ldg(reinterpret_cast<const uint4 *>(in + s0 + j) + (h & 1u));
+            }
         }
     }
 }
@@ -396,27 +421,27 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 
 }  // namespace
 
-extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, uint32_t *d_tile_tab, int64_t n_tiles,
-                                const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters, mc_record *d_rec_out,
-                                int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
-    MC_REQUIRE(d_text && d_tile_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
+extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uint32_t *d_tile_tab, int64_t n_tiles, uint32_t *d_run_tab,
+                                int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
+                                mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
+    MC_REQUIRE(d_text && d_tile_tab && d_run_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
+    MC_REQUIRE(run_len >= 1, "run length must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles <= 0) {
         MC_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, 8, st));
         return MC_OK;
     }
-    uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_tiles);
-    const unsigned nb = (unsigned)((n_tiles + 255) / 256);
-    k_resolve_fillers<<<nb, 256, 0, st>>>(d_tile_tab, n_tiles, cnt, reinterpret_cast<const unsigned long long *>(d_scan_counters),
-                                          (unsigned long long)rec_in_cap);
+    const int64_t n_runs = (n_tiles + run_len - 1) / run_len;
+    uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_runs);
+    k_run_resolve<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(d_run_tab, n_runs, cnt, reinterpret_cast<const unsigned long long *>(d_scan_counters),
+                                                                   (unsigned long long)rec_in_cap);
     MC_LAUNCH_CHECK();
-    int rc = mc_exscan_u32(cnt, dst, n_tiles, d_n_out, ws_s(d_ws, n_tiles), st);
+    int rc = mc_exscan_u32(cnt, dst, n_runs, d_n_out, ws_s(d_ws, n_runs), st);
     if (rc) return rc;
-    k_gather<<<nb, 256, 0, st>>>(d_tile_tab, cnt, dst, n_tiles, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
-                                 (unsigned long long)rec_out_cap);
+    k_gather_runs<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_tile_tab, d_run_tab, dst, n_tiles, n_runs, run_len, d_rec_in,
+                                                                        (unsigned long long)rec_in_cap, d_rec_out, (unsigned long long)rec_out_cap);
     MC_LAUNCH_CHECK();
     // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
-    // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
     k_finish_records<<<(unsigned)((rec_out_cap + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
                                                                             reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap,
                                                                             reinterpret_cast<const unsigned long long *>(d_scan_counters));

@@ -340,7 +340,7 @@ __device__ __forceinline__ bool staged_differ(const uint8_t *text, int a, int b,
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
 k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, int run_len, mc_refindex R,
        int dense, mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
-       unsigned long long *__restrict__ d_counters) {
+       uint32_t *__restrict__ d_run_tab, unsigned long long *__restrict__ d_counters) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[wib];
@@ -425,6 +425,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     int run_end = min(chunk + run_len, n_chunks);
     if (chunk < n_chunks) cur_async = stage(chunk, 0);
     int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
+    unsigned run_total = 0u, run_filler = 0u;                     // records / filler flag of the run so far
 
     while (chunk < n_chunks) {
         const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
@@ -753,7 +754,16 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             reinterpret_cast<uint2 *>(d_tile_tab)[chunk] =
                 make_uint2((uint32_t)(slot_cur - n_emitted), n_emitted | (filler << 16) | ((uint32_t)(prev_state + 1) << 17));
         }
-        if (last_of_run) prev_state = -1;
+        run_total += n_emitted;
+        run_filler |= filler;
+        if (last_of_run) {
+            // per-run entry for stage 2 (which orders the records run by run): {records of the run, first record is a filler |
+            // state of the run's last kept line (0 none, 1 not a candidate, 2 candidate) << 1}
+            if (lane == 0) reinterpret_cast<uint2 *>(d_run_tab)[chunk / run_len] = make_uint2(run_total, run_filler | ((uint32_t)(prev_state + 1) << 1));
+            run_total = 0u;
+            run_filler = 0u;
+            prev_state = -1;
+        }
         chunk = next;
         run_end = next_end;
         buf ^= 1;
@@ -786,9 +796,34 @@ extern "C" int mc_scan_set_run_len(int run_len) {
 
 extern "C" int64_t mc_num_tiles(int64_t nbytes) { return nbytes <= 0 ? 0 : (nbytes + CHUNK - 1) / CHUNK; }
 
+// persistent grid of mc_scan and the run length it uses for nbytes of text (stage 2 walks the same runs)
+static int scan_geometry(int64_t n_chunks, int64_t *blocks_out, int *run_len_out) {
+    int dev = 0, sms = 0;
+    MC_CUDA_CHECK(cudaGetDevice(&dev));
+    MC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t blocks = (n_chunks + WARPS - 1) / WARPS;
+    const int64_t resident = (int64_t)sms * MC_SCAN_MIN_CTAS;     // persistent: MC_SCAN_MIN_CTAS CTAs per SM
+    if (blocks > resident) blocks = resident;
+    // run length: as long as possible (fewer run-first "filler" passes) while every warp still gets >= 8 runs to balance on
+    int run_len = MC_SCAN_RUN;
+    while (run_len > 1 && n_chunks < blocks * WARPS * 8 * (int64_t)run_len) run_len >>= 1;
+    if (g_run_len_override > 0) run_len = g_run_len_override;
+    *blocks_out = blocks;
+    *run_len_out = run_len;
+    return MC_OK;
+}
+extern "C" int mc_scan_run_len(int64_t nbytes) {
+    const int64_t n_chunks = mc_num_tiles(nbytes);
+    if (n_chunks == 0) return 1;
+    int64_t blocks = 0;
+    int run_len = 1;
+    if (scan_geometry(n_chunks, &blocks, &run_len)) return -1;
+    return run_len;
+}
+
 extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense, mc_record *d_rec,
-                       int64_t rec_cap, uint32_t *d_tile_tab, uint64_t *d_counters, void *stream) {
-    MC_REQUIRE(d_text && ref && d_rec && d_tile_tab && d_counters, "null pointer");
+                       int64_t rec_cap, uint32_t *d_tile_tab, uint32_t *d_run_tab, uint64_t *d_counters, void *stream) {
+    MC_REQUIRE(d_text && ref && d_rec && d_tile_tab && d_run_tab && d_counters, "null pointer");
     MC_REQUIRE(nbytes >= 0 && rec_cap >= 0, "negative size");
     MC_REQUIRE((reinterpret_cast<uintptr_t>(d_text) & 15) == 0, "d_text must be 16-byte aligned");
     MC_REQUIRE((reinterpret_cast<uintptr_t>(d_tile_tab) & 7) == 0, "d_tile_tab must be 8-byte aligned");
@@ -799,24 +834,20 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     const int64_t n_chunks = mc_num_tiles(nbytes);
     if (n_chunks == 0) return MC_OK;
     MC_REQUIRE(n_chunks < (1ll << 30), "too many chunks (chunk of text larger than 4 TB)");
-    int dev = 0, sms = 0;
-    MC_CUDA_CHECK(cudaGetDevice(&dev));
-    MC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sizeof(WarpSmem) * WARPS;
     MC_CUDA_CHECK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (n_chunks + WARPS - 1) / WARPS;
-    const int64_t resident = (int64_t)sms * MC_SCAN_MIN_CTAS;     // persistent: MC_SCAN_MIN_CTAS CTAs per SM
-    if (blocks > resident) blocks = resident;
+    int64_t blocks = 0;
+    int run_len = 1;
+    {
+        const int rc = scan_geometry(n_chunks, &blocks, &run_len);
+        if (rc) return rc;
+    }
     // 16-byte loads / bulk copies are allowed up to the end of the caller's '\n' padding
     const int64_t text_limit16 = ((nbytes + MC_TEXT_PAD) / 16) * 16;
-    // run length: as long as possible (fewer run-first "filler" passes) while every warp still gets >= 8 runs to balance on
-    int run_len = MC_SCAN_RUN;
-    while (run_len > 1 && n_chunks < blocks * WARPS * 8 * (int64_t)run_len) run_len >>= 1;
-    if (g_run_len_override > 0) run_len = g_run_len_override;
     // the run cursor must start at zero whatever the caller did with the counter block
     MC_CUDA_CHECK(cudaMemsetAsync(d_counters + MC_C_RUN_CURSOR, 0, sizeof(uint64_t), (cudaStream_t)stream));
     k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense, d_rec,
-                                                                     (unsigned long long)rec_cap, d_tile_tab,
+                                                                     (unsigned long long)rec_cap, d_tile_tab, d_run_tab,
                                                                      reinterpret_cast<unsigned long long *>(d_counters));
     MC_LAUNCH_CHECK();
     return MC_OK;

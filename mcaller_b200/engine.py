@@ -229,6 +229,8 @@ class Engine(object):
         L, st = self.L, self._sptr()
         V = C.c_void_p
         tile_tab = self._buf("tile_tab", 8 * max(n_tiles, 1))
+        run_len = max(int(L.mc_scan_run_len(nbytes)), 1)
+        run_tab = self._buf("run_tab", 8 * max((n_tiles + run_len - 1) // run_len, 1))
         rec_a = self._buf("rec_a", 32 * rec_cap)
         rec_b = self._buf("rec_b", 32 * rec_cap)
         ws = self._buf("ws", L.mc_workspace_bytes(max(rec_cap, n_tiles)))
@@ -241,11 +243,11 @@ class Engine(object):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         check(L.mc_scan(V(d_text.data_ptr()), nbytes, self.ref.ref(), 1 if self.dense else 0, V(rec_a.data_ptr()), rec_cap,
-                        V(tile_tab.data_ptr()), V(self.d_small.data_ptr()), st))
+                        V(tile_tab.data_ptr()), V(run_tab.data_ptr()), V(self.d_small.data_ptr()), st))
         if self.scan_events is not None:
             e1.record()
             self.scan_events.append((e0, e1))
-        check(L.mc_order_records(V(d_text.data_ptr()), nbytes, V(tile_tab.data_ptr()), n_tiles, V(rec_a.data_ptr()), rec_cap,
+        check(L.mc_order_records(V(d_text.data_ptr()), nbytes, V(tile_tab.data_ptr()), n_tiles, V(run_tab.data_ptr()), run_len, V(rec_a.data_ptr()), rec_cap,
                                  V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(ws.data_ptr()), st))
         check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()),
                                  self._status_ptr(S_NSEG), V(ws.data_ptr()), st))
@@ -261,7 +263,7 @@ class Engine(object):
         check(L.mc_carry_rows(V(calls.data_ptr()), self._status_ptr(S_NCALLS), V(rec_b.data_ptr()), self._status_ptr(S_NREC),
                               V(seg_start.data_ptr()), self._status_ptr(S_NSEG), V(seg_qual.data_ptr()), self.qual_thresh,
                               V(self.d_carry.data_ptr()), self._status_ptr(S_NROWS), self._status_ptr(S_ABORT), st))
-        # 1 scan + 7 order (cursor memset aside: fillers, 3 scan kernels, gather, finish) + 5 segmentation + 1 quality
+        # 1 scan + 6 order (run resolution, 3 scan kernels, gather, finish) + 5 segmentation + 1 quality
         # + 7 windows (first-'M', 2 passes, 3 scan kernels, capacity check) + guard + carry
         self.launches += 1 + 6 + 5 + 1 + 7 + 2
         if self.models is not None:
