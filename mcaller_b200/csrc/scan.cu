@@ -711,7 +711,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // read name of the previous recorded line of this pass (same read <=> equal bytes, extract_contexts.py:161);
             // the first record of a pass and neighbours of raw records are compared in stage 3 instead
             {
-                const uint32_t my_span = fin ? ((uint32_t)(s + name_off) | ((uint32_t)name_len << 16)) : 0xFFFFFFFFu;
+                // (a run-first "filler" record may still be dropped by stage 2, so it is nobody's known predecessor)
+                const uint32_t my_span = (fin && !filler_lane) ? ((uint32_t)(s + name_off) | ((uint32_t)name_len << 16)) : 0xFFFFFFFFu;
                 const uint32_t below_e = emit_m & lt_mask;
                 const uint32_t prev_span = __shfl_sync(0xffffffffu, my_span, below_e ? 31 - __clz(below_e) : lane);
                 if (fin && below_e && prev_span != 0xFFFFFFFFu) {

@@ -102,7 +102,7 @@ class _Aggregation(object):
     locus table that grows with the loci seen (the reference streams line by line, make_bed.py:75); the modes that need
     per-read lists (-p, --vo) keep the whole file on the device for their second pass."""
 
-    def __init__(self, meth_fi, pos_set=None, keep_text=False):
+    def __init__(self, meth_fi, pos_set=None, keep_text=None):
         import torch
         from . import _lib, engine
         engine.require_cuda()
@@ -114,6 +114,8 @@ class _Aggregation(object):
         self.slots = np.zeros(0, dtype=np.int64)
         self.counters = np.zeros(8, dtype=np.int64)
         self.data = None
+        if keep_text is None:
+            keep_text = pos_set is not None       # the per-read passes (index_rows / column_tests) need the text on the device
         if self.n == 0:
             return
         self.d_posset = None
