@@ -78,29 +78,66 @@ __device__ __forceinline__ int64_t mc_dev_count(const unsigned long long *d_n, i
     return v < (unsigned long long)cap ? (int64_t)v : cap;
 }
 
-// numpy's pairwise summation (np.add.reduce over a contiguous float64 vector) of f(x_i), i in [0, n)
+// numpy's pairwise summation (np.add.reduce over a contiguous float64 vector) of f(x_i), i in [i0, i0 + n):
+// sequential below 8 values, 8 running lanes + sequential tail up to 128, and above that numpy splits at n/2 rounded down
+// to a multiple of 8 and adds the two halves.  The halving is walked with an explicit stack (depth <= log2(n / 64)) instead
+// of device-side recursion, whose frames would need more than the default 1 KB of stack for a few thousand values.
 template <class F>
-__device__ double mc_pairwise_sum(F f, int64_t i0, int64_t n) {
+__device__ __forceinline__ double mc_pairwise_block(F f, int64_t i0, int64_t n) {
     if (n < 8) {
         double res = 0.0;
         for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = f(i0 + j);
-        int64_t i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = f(i0 + j);
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i0 + i + j));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i0 + i + j));
     }
-    int64_t n2 = n / 2;
-    n2 -= n2 % 8;
-    const double left = mc_pairwise_sum(f, i0, n2);
-    return __dadd_rn(left, mc_pairwise_sum(f, i0 + n2, n - n2));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, f(i0 + i));
+    return res;
+}
+template <class F>
+__device__ double mc_pairwise_sum(F f, int64_t i0, int64_t n) {
+    if (n <= 128) return mc_pairwise_block(f, i0, n);
+    constexpr int DEPTH = 40;
+    int64_t st_i0[DEPTH], st_n[DEPTH];
+    double st_left[DEPTH];
+    int st_phase[DEPTH];                      // 0: nothing done, 1: left half running, 2: right half running
+    int sp = 0;
+    st_i0[0] = i0; st_n[0] = n; st_phase[0] = 0; st_left[0] = 0.0;
+    double ret = 0.0;
+    for (;;) {
+        if (st_phase[sp] == 0) {
+            if (st_n[sp] <= 128 || sp + 1 >= DEPTH) {          // leaf (the depth bound cannot bind for n < 2^40)
+                ret = mc_pairwise_block(f, st_i0[sp], st_n[sp]);
+            } else {
+                int64_t n2 = st_n[sp] / 2;
+                n2 -= n2 % 8;
+                st_phase[sp] = 1;
+                st_i0[sp + 1] = st_i0[sp]; st_n[sp + 1] = n2; st_phase[sp + 1] = 0;
+                ++sp;
+                continue;
+            }
+        }
+        // `ret` holds the sum of the frame at sp: hand it to the parent
+        for (;;) {
+            if (sp == 0) return ret;
+            --sp;
+            if (st_phase[sp] == 1) {                             // left half done: run the right half
+                int64_t n2 = st_n[sp] / 2;
+                n2 -= n2 % 8;
+                st_left[sp] = ret;
+                st_phase[sp] = 2;
+                st_i0[sp + 1] = st_i0[sp] + n2; st_n[sp + 1] = st_n[sp] - n2; st_phase[sp + 1] = 0;
+                ++sp;
+                break;
+            }
+            ret = __dadd_rn(st_left[sp], ret);                   // both halves done
+        }
+    }
 }
