@@ -297,11 +297,12 @@ int mc_carry_rows(mc_call *d_rows, const uint64_t *d_ncalls, const mc_record *d_
                   const uint32_t *d_seg_start, const uint64_t *d_nseg, const double *d_seg_qual, double qual_thresh,
                   mc_carry *d_carry, uint64_t *d_nrows_out, const uint64_t *d_abort, void *stream);
 /* Overflow guard of a chunk: d_abort[0] = 1 when a buffer of the stages so far was too small (mc_scan's overflow counter, reserved
- * record slots > rec_cap, ordered records > rec_out_cap, rows > call_cap), else 0.  The stages that change state across chunks
+ * record slots > rec_cap, ordered records > rec_out_cap, read segments > seg_cap, rows > call_cap), else 0.  The stages that change state across chunks
  * (mc_carry_rows, mc_hist_accumulate) take d_abort and do nothing when it is set, so the host can grow its buffers and run the
  * chunk again without having synchronised in between. */
 int mc_chunk_guard(const uint64_t *d_counters, int64_t rec_cap, const uint64_t *d_n_records, int64_t rec_out_cap,
-                   const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort, void *stream);
+                   const uint64_t *d_nseg, int64_t seg_cap, const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort,
+                   void *stream);
 int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64_t *d_next_contigs, int from, int count, mc_call *d_row_out,
                    uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first, int64_t n_sites, uint64_t *d_row_base, void *stream);
 

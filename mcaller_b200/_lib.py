@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcaller_b200.so")
+LIB_PATH = os.environ.get("MCALLER_B200_LIB") or os.path.join(HERE, "libmcaller_b200.so")      # the env var selects a tuning build
 
 MC_TILE_BYTES = 3840
 MC_TEXT_PAD = 4096
@@ -105,8 +105,9 @@ _PROTOS = {
     # d_rows, d_ncalls, d_rec, d_n_records, d_seg_start, d_nseg, d_seg_qual, qual_thresh, d_carry, d_nrows_out, d_abort, stream
     "mc_carry_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
-    # d_counters, rec_cap, d_n_records, rec_out_cap, d_ncalls, call_cap, d_abort, stream
-    "mc_chunk_guard": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    # d_counters, rec_cap, d_n_records, rec_out_cap, d_nseg, seg_cap, d_ncalls, call_cap, d_abort, stream
+    "mc_chunk_guard": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_void_p]),
     # d_carry, closing_contig, d_next_contigs, from, count, d_row_out, d_depth, d_meth, d_first, n_sites, d_row_base, stream
     "mc_carry_close": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_void_p, C.c_void_p]),

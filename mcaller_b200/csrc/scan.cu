@@ -50,6 +50,9 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_RUN
 #define MC_SCAN_RUN 32
 #endif
+#ifndef MC_SCAN_FINISH
+#define MC_SCAN_FINISH 1                      // 0 (tuning builds): leave every record raw for stage 2, as in round 1
+#endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int LCAP = 32;                      // lines per pass (one per lane)
@@ -288,47 +291,62 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
 }
 
 // ---- record finishing from the staged bytes (what stage 2 did from global memory in round 1) ---------------------------------
-// Columns 3, 4, 6, 7, 10, 11 of the line starting at staged offset s, located by rank/select on the 160-bit field-start window;
-// event index, np.round(event_mean - model_mean, 4) (extract_contexts.py:286), k-mer equality (:169) and the read-name span
-// (:161).  Returns false for anything but the usual shapes -- the record then stays MC_RF_RAW and stage 2 finishes it from
-// global memory with the byte loops of parse.cuh (same float64 either way).
-__device__ __forceinline__ bool finish_line(const WarpSmem &S, const uint8_t *text, int s, int &ev_idx, double &diff, uint32_t &eq,
-                                            int &name_off, int &name_len) {
-    const LineWindow L = line_window(S, s);
-    const int c0 = __popc(L.F0), c1 = c0 + __popc(L.F1), c2 = c1 + __popc(L.F2), c3 = c2 + __popc(L.F3), c4 = c3 + __popc(L.F4);
-    if (c4 < 11) return false;                                     // column 11 starts beyond the window
-    auto sel = [&](int k) {                                        // window-relative start of column k + 1
-        const int wi = (k >= c0) + (k >= c1) + (k >= c2) + (k >= c3);
-        const uint32_t m = wi == 0 ? L.F0 : wi == 1 ? L.F1 : wi == 2 ? L.F2 : wi == 3 ? L.F3 : L.F4;
-        const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : wi == 3 ? c2 : c3;
-        return 32 * wi + nth_bit(m, k - base);
-    };
-    const int r2 = sel(2), r3 = sel(3), r5 = sel(5), r6 = sel(6), r9 = sel(9), r10 = sel(10);
-    if (s + r10 + 12 > WB) return false;                           // the 8-byte loads below must stay inside the staged bytes
-    // end of the read name: first whitespace at or after r3
-    int wi = r3 >> 5;
-    uint32_t z = ~(wi == 0 ? L.N0 : wi == 1 ? L.N1 : wi == 2 ? L.N2 : wi == 3 ? L.N3 : L.N4) & (0xFFFFFFFFu << (r3 & 31));
-    while (z == 0u) {
-        if (++wi > 4) return false;
-        z = ~(wi == 1 ? L.N1 : wi == 2 ? L.N2 : wi == 3 ? L.N3 : L.N4);
+// Columns 3, 4, 6, 7, 10, 11 of the line starting at staged offset s, found by walking the field-start bits of the
+// non-whitespace map; event index, np.round(event_mean - model_mean, 4) (extract_contexts.py:286), k-mer equality (:169) and
+// the read-name span (:161).  Returns false for anything but the usual shapes -- the record then stays MC_RF_RAW and stage 2
+// finishes it from global memory with the byte loops of parse.cuh (same float64 either way).
+// Deliberately out of line and written with loops: it runs once per pass of the ~9 % of chunks that record anything, and
+// what matters is that its instructions stay out of the way of the scan loop (the kernel is instruction-cache sensitive).
+struct Finished {
+    double diff;
+    int ev_idx, name_off, name_len;
+    uint32_t eq;
+};
+__device__ __noinline__ bool finish_line(const uint32_t *nw, const uint8_t *text, int s, Finished *out) {
+    int w = s >> 5;
+    uint32_t cur = nw[w];
+    uint32_t m = cur & ~(cur << 1) & (0xFFFFFFFFu << (s & 31));    // the byte before a line start is a newline: bit s starts a field if set
+    int p[11];
+#pragma unroll 1
+    for (int nf = 0; nf < 11; ++nf) {
+        while (m == 0u) {
+            if (++w >= NW) return false;
+            const uint32_t nx = nw[w];
+            m = nx & ~((nx << 1) | (cur >> 31));
+            cur = nx;
+        }
+        p[nf] = 32 * w + __ffs(m) - 1;
+        m &= m - 1u;
     }
-    const int rend = 32 * wi + __ffs(z) - 1;
-    const int teq = fast_tokens_equal8(load8(text, s + r2), load8(text, s + r9));
-    uint32_t m_ev = 0u, m_md = 0u;
-    int n_ev = 0, n_md = 0;
-    if (teq < 0 || !fast_uint8(load8(text, s + r5), ev_idx) || !fast_decimal8(load8(text, s + r6), m_ev, n_ev) ||
-        !fast_decimal8(load8(text, s + r10), m_md, n_md))
-        return false;
-    const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
-    diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
-    eq = teq ? MC_RF_EQ : 0u;
-    name_off = r3;
-    name_len = rend - r3;
+    if (p[10] + 12 > WB) return false;                             // the 8-byte loads below must stay inside the staged bytes
+    // end of the read name: first whitespace at or after its start
+    int w3 = p[3] >> 5;
+    uint32_t z = ~nw[w3] & (0xFFFFFFFFu << (p[3] & 31));
+    while (z == 0u) {
+        if (++w3 >= NW) return false;
+        z = ~nw[w3];
+    }
+    const int pend = 32 * w3 + __ffs(z) - 1;
+    const int teq = fast_tokens_equal8(load8(text, p[2]), load8(text, p[9]));
+    if (teq < 0 || !fast_uint8(load8(text, p[5]), out->ev_idx)) return false;
+    double val[2];
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        uint32_t mant = 0u;
+        int nfrac = 0;
+        if (!fast_decimal8(load8(text, p[j ? 10 : 6]), mant, nfrac)) return false;
+        val[j] = __ddiv_rn((double)mant, c_pow10[nfrac]);
+    }
+    out->diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(val[0], val[1]), 1e4)), 1e4);
+    out->eq = teq ? MC_RF_EQ : 0u;
+    out->name_off = p[3] - s;
+    out->name_len = pend - p[3];
     return true;
 }
 // do the L staged bytes at offsets a and b differ (8 bytes at a time, any alignment)
-__device__ __forceinline__ bool staged_differ(const uint8_t *text, int a, int b, int L) {
+__device__ __noinline__ bool staged_differ(const uint8_t *text, int a, int b, int L) {
     unsigned long long d = 0ull;
+#pragma unroll 1
     for (int j = 0; j < L; j += 8) {
         unsigned long long x = load8(text, a + j) ^ load8(text, b + j);
         if (L - j < 8) x &= (1ull << (8 * (L - j))) - 1ull;
@@ -703,10 +721,12 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
                     fl = MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
                 }
-                uint32_t eq = 0u;
-                fin = staged && finish_line(S, text, s, ev_idx, diff, eq, name_off, name_len);
-                if (fin) fl |= eq;
-                else { fl |= MC_RF_RAW; ev_idx = 0; diff = 0.0; name_off = 0; name_len = 0; atomicAdd(&S.cnt[6], 1u); }
+                Finished F;
+#if MC_SCAN_FINISH
+                fin = staged && finish_line(S.nw, text, s, &F);
+#endif
+                if (fin) { fl |= F.eq; ev_idx = F.ev_idx; diff = F.diff; name_off = F.name_off; name_len = F.name_len; }
+                else { fl |= MC_RF_RAW; atomicAdd(&S.cnt[6], 1u); }
             }
             // read name of the previous recorded line of this pass (same read <=> equal bytes, extract_contexts.py:161);
             // the first record of a pass and neighbours of raw records are compared in stage 3 instead

@@ -89,8 +89,7 @@ class Engine(object):
             self.d_odd = torch.zeros(ODD_CAP * CALL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
             self.d_spill = torch.zeros(SPILL_CAP, dtype=torch.float64, device=self.device)
             self.h_small = np.zeros(S_WORDS, dtype=np.uint64)
-            self.rec_cap_learned = 0          # largest demand seen so far (records reserved / rows written)
-            self.call_cap_learned = 0
+            self.rec_per_byte = self.call_per_byte = self.seg_per_byte = 0.0     # largest demand per text byte seen so far
             self.launches = 0
             self.redone = 0                   # chunks run a second time because a buffer was too small
             self.scan_events = None           # set to [] to collect (start, end) CUDA events around the scan kernel
@@ -188,18 +187,24 @@ class Engine(object):
         res.nbytes = nbytes
         n_tiles = int(L.mc_num_tiles(nbytes))
         slack = 256 * min(n_tiles, 8192) + 4096
+        # capacities only size launches and buffers: heuristics for the first chunk, afterwards what the chunks so far needed
+        # per byte of text (+25 %); a chunk that outgrows them is run again (mc_chunk_guard)
         if rec_cap is None:
-            rec_cap = max(self._default_rec_cap(nbytes, n_tiles), int(self.rec_cap_learned * 1.25) + slack if self.rec_cap_learned else 0)
+            rec_cap = (int(self.rec_per_byte * nbytes * 1.25) + slack) if self.rec_per_byte else self._default_rec_cap(nbytes, n_tiles)
         if call_cap is None:
-            call_cap = max(rec_cap // 8 + 1024, int(self.call_cap_learned * 1.25) + 1024 if self.call_cap_learned else 0)
+            call_cap = (int(self.call_per_byte * nbytes * 1.25) + 1024) if self.rec_per_byte else rec_cap // 8 + 1024
+        seg_cap = (int(self.seg_per_byte * nbytes * 1.5) + 1024) if self.rec_per_byte else rec_cap
         rec_cap = int(min(max(rec_cap, 1), 2 ** 32 - 2))
         call_cap = int(max(call_cap, 1))
+        seg_cap = int(min(max(seg_cap, 1), rec_cap))
         attempts = 0
         while True:
-            cnt = self._launch_chunk(d_text, nbytes, n_tiles, rec_cap, call_cap)
-            reserved, n_rec, n_calls = int(cnt[C_RECORDS]), int(cnt[S_NREC]), int(cnt[S_NCALLS])
-            self.rec_cap_learned = max(self.rec_cap_learned, reserved)
-            self.call_cap_learned = max(self.call_cap_learned, n_calls)
+            cnt = self._launch_chunk(d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap)
+            reserved, n_rec, n_calls, n_seg = int(cnt[C_RECORDS]), int(cnt[S_NREC]), int(cnt[S_NCALLS]), int(cnt[S_NSEG])
+            if nbytes > 0:
+                self.rec_per_byte = max(self.rec_per_byte, reserved / nbytes)
+                self.call_per_byte = max(self.call_per_byte, n_calls / nbytes)
+                self.seg_per_byte = max(self.seg_per_byte, n_seg / nbytes)
             if not cnt[S_ABORT]:
                 break
             self.redone += 1
@@ -211,6 +216,8 @@ class Engine(object):
                     raise _lib.McallerCudaError("chunk produces more than 2^32 records; use smaller chunks")
                 rec_cap = int(min(max(reserved, rec_cap * 2 if cnt[C_OVERFLOW] and reserved <= rec_cap else 0) + slack, 2 ** 32 - 2))
                 call_cap = max(call_cap, rec_cap // 8 + 1024)
+            elif n_seg > seg_cap:
+                seg_cap = min(n_seg + 1024, rec_cap)
             else:
                 call_cap = n_calls + 1024
         res.counters = {nm: int(cnt[i]) for i, nm in enumerate(_lib.COUNTER_NAMES)}
@@ -224,7 +231,7 @@ class Engine(object):
                          pending_too_many_skips=int(v[6]))
         return res
 
-    def _launch_chunk(self, d_text, nbytes, n_tiles, rec_cap, call_cap):
+    def _launch_chunk(self, d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap):
         """All stages of one chunk, back to back on the current stream; one status read at the end."""
         L, st = self.L, self._sptr()
         V = C.c_void_p
@@ -235,8 +242,8 @@ class Engine(object):
         rec_b = self._buf("rec_b", 32 * rec_cap)
         ws = self._buf("ws", L.mc_workspace_bytes(max(rec_cap, n_tiles)))
         seg_start = self._buf("seg_start", 4 * (rec_cap + 2))
-        seg_qual = self._buf("seg_qual", 8 * rec_cap)
-        seg_count = self._buf("seg_count", 4 * rec_cap)
+        seg_qual = self._buf("seg_qual", 8 * seg_cap)
+        seg_count = self._buf("seg_count", 4 * seg_cap)
         calls = self._buf("calls", CALL_DTYPE.itemsize * (call_cap + 1))          # slot 0 + the chunk's rows
         self.d_small.zero_()
         if self.scan_events is not None:
@@ -251,15 +258,15 @@ class Engine(object):
                                  V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(ws.data_ptr()), st))
         check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()),
                                  self._status_ptr(S_NSEG), V(ws.data_ptr()), st))
-        check(L.mc_segment_quality(V(d_text.data_ptr()), V(rec_b.data_ptr()), V(seg_start.data_ptr()), self._status_ptr(S_NSEG), rec_cap,
+        check(L.mc_segment_quality(V(d_text.data_ptr()), V(rec_b.data_ptr()), V(seg_start.data_ptr()), self._status_ptr(S_NSEG), seg_cap,
                                    V(self.d_qual.data_ptr()), self.qual_table_size, V(seg_qual.data_ptr()), self._status_ptr(S_MISSING_QUAL), st))
         rows1 = V(calls.data_ptr() + CALL_DTYPE.itemsize)
         check(L.mc_build_windows(V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()), self._status_ptr(S_NSEG),
-                                 rec_cap, V(seg_qual.data_ptr()), self.ref.ref(), self.skip_thresh, self.qual_thresh, self.two_models,
+                                 seg_cap, V(seg_qual.data_ptr()), self.ref.ref(), self.skip_thresh, self.qual_thresh, self.two_models,
                                  rows1, call_cap, V(seg_count.data_ptr()), self._status_ptr(S_NCALLS), V(ws.data_ptr()),
                                  V(self.d_spill.data_ptr()), SPILL_CAP, st))
-        check(L.mc_chunk_guard(V(self.d_small.data_ptr()), rec_cap, self._status_ptr(S_NREC), rec_cap, self._status_ptr(S_NCALLS), call_cap,
-                               self._status_ptr(S_ABORT), st))
+        check(L.mc_chunk_guard(V(self.d_small.data_ptr()), rec_cap, self._status_ptr(S_NREC), rec_cap, self._status_ptr(S_NSEG), seg_cap,
+                               self._status_ptr(S_NCALLS), call_cap, self._status_ptr(S_ABORT), st))
         check(L.mc_carry_rows(V(calls.data_ptr()), self._status_ptr(S_NCALLS), V(rec_b.data_ptr()), self._status_ptr(S_NREC),
                               V(seg_start.data_ptr()), self._status_ptr(S_NSEG), V(seg_qual.data_ptr()), self.qual_thresh,
                               V(self.d_carry.data_ptr()), self._status_ptr(S_NROWS), self._status_ptr(S_ABORT), st))
