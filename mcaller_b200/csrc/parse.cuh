@@ -165,3 +165,121 @@ __device__ __forceinline__ int fast_tokens_equal8(unsigned long long a, unsigned
     if (la != lb) return 0;
     return (((a ^ b) & ((1ull << (8 * la)) - 1ull)) == 0ull) ? 1 : 0;
 }
+
+// ---- finishing a raw record from the text in global memory (shared by stage 1's batched flush and stage 2) ------------------
+__device__ __forceinline__ uint32_t fin_gt20(uint32_t w) { return (((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u; }
+__device__ __forceinline__ uint32_t fin_pack16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    const uint32_t lo = 0x08040201u, hi = 0x80402010u;
+    const uint32_t a = __dp4a(m1, hi, __dp4a(m0, lo, 0u)), b = __dp4a(m3, hi, __dp4a(m2, lo, 0u));
+    return (a >> 7) | (b << 1);
+}
+// 8 bytes at any alignment from two aligned 8-byte loads
+__device__ __forceinline__ unsigned long long load8_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+    const int sh = 8 * (int)(a & 7);
+    const unsigned long long lo = __ldg(q);
+    if (sh == 0) return lo;
+    const unsigned long long hi = __ldg(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+// do the L bytes at pa and pb differ (the '\n' padding after the text keeps the 8-byte loads legal).  Both sides are
+// streamed as aligned 8-byte words and realigned in registers: 1 + ceil(L / 8) loads per side, all independent.
+__device__ __forceinline__ bool bytes_differ(const uint8_t *pa, const uint8_t *pb, int L) {
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(pa), ub = reinterpret_cast<uintptr_t>(pb);
+    const unsigned long long *qa = reinterpret_cast<const unsigned long long *>(ua & ~(uintptr_t)7);
+    const unsigned long long *qb = reinterpret_cast<const unsigned long long *>(ub & ~(uintptr_t)7);
+    const int sa = 8 * (int)(ua & 7), sb = 8 * (int)(ub & 7);
+    unsigned long long a_lo = __ldg(qa), b_lo = __ldg(qb), diff = 0ull;
+#pragma unroll 5
+    for (int j = 0; j < L; j += 8) {
+        const unsigned long long a_hi = __ldg(++qa), b_hi = __ldg(++qb);
+        const unsigned long long va = sa ? ((a_lo >> sa) | (a_hi << (64 - sa))) : a_lo;
+        const unsigned long long vb = sb ? ((b_lo >> sb) | (b_hi << (64 - sb))) : b_lo;
+        unsigned long long d = va ^ vb;
+        if (L - j < 8) d &= (1ull << (8 * (L - j))) - 1ull;               // 1..7 tail bytes
+        diff |= d;
+        a_lo = a_hi;
+        b_lo = b_hi;
+    }
+    return diff != 0ull;
+}
+
+// Walks the columns of the record's line in the text (16-byte SWAR steps over the non-whitespace map; columns split on
+// runs of bytes <= 0x20 like str.split(), extract_contexts.py:150) and parses what the window builder needs: read-name span
+// (column 4), event index (6), np.round(event_mean - model_mean, 4) (7, 11) and the k-mer equality flag (3 vs 10).  The usual
+// shapes ("1234", "87.41", 6-mers) are decoded from 8-byte register loads, anything else by the byte loops above -- both
+// give the same float64.  Clears MC_RF_RAW.
+__device__ __forceinline__ void mc_finish_record(const uint8_t *__restrict__ text, int64_t limit, mc_record &r) {
+    const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
+    // 16-byte steps from the aligned address at or below the line start; the '\n' padding after the text makes every
+    // line end inside readable memory
+    const int64_t a0 = line & ~15ll;
+    const int skip = (int)(line - a0);
+    int nf = 0, f2 = 0, f3 = 0, name_end = -1, f5 = 0, f6 = 0, f9 = 0, f10 = 0;
+    uint32_t prev_nonws = 0u;          // was the byte before this step non-whitespace (the byte before the line is '\n')
+    bool done = false;
+    constexpr int MAX_STEPS = 256;     // 4 KB: twice the documented limit for the first 12 columns of a line
+    for (int step = 0; step < MAX_STEPS && !done; ++step) {
+        const int64_t g = a0 + 16ll * step;
+        if (g >= limit) break;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + g));
+        uint32_t nonws = fin_pack16(fin_gt20(v.x), fin_gt20(v.y), fin_gt20(v.z), fin_gt20(v.w));
+        if (step == 0) nonws &= 0xFFFFu << skip;                 // ignore the bytes before the line start
+        // no newline test: a recorded line is a kept line, its first 12 columns start before its end (stage 1 checked), so
+        // the walk stops at the 11th column; MAX_STEPS bounds it for records that did not come from stage 1
+        const int base = 16 * step - skip;                       // line-relative offset of byte 0 of this step
+        uint32_t fs = nonws & ~((nonws << 1) | prev_nonws);
+        if (name_end < 0 && nf >= 4) {                           // first whitespace (or the newline) after the read name
+            const uint32_t z = ~nonws & 0xFFFFu & ((step == 0) ? (0xFFFFu << skip) : 0xFFFFu);
+            const uint32_t zz = z & ~((1u << max(f3 - base, 0)) - 1u);
+            if (zz) name_end = base + __ffs(zz) - 1;
+        }
+        while (fs) {
+            const int b = __ffs(fs) - 1;
+            fs &= fs - 1u;
+            const int pos = base + b;
+            switch (nf) {
+                case 2: f2 = pos; break;
+                case 3: f3 = pos; break;
+                case 5: f5 = pos; break;
+                case 6: f6 = pos; break;
+                case 9: f9 = pos; break;
+                case 10: f10 = pos; break;
+                default: break;
+            }
+            ++nf;
+            if (nf == 4 && name_end < 0) {                       // the name may end inside this same step
+                const uint32_t z = ~nonws & 0xFFFFu & ~((1u << b) - 1u);
+                if (z) name_end = base + __ffs(z) - 1;
+            }
+            if (nf == 11) { done = true; break; }
+        }
+        prev_nonws = (nonws >> 15) & 1u;
+    }
+    uint32_t fl = r.flags & ~MC_RF_RAW;
+    int ev_idx = 0;
+    double diff = 0.0;
+    if (nf < 11 || name_end < 0 || f3 > 65535 || name_end - f3 > 65535) fl |= MC_RF_BADNUM | MC_RF_BADIDX;   // cannot happen for a kept line
+    else {
+        const uint8_t *lp = text + line;
+        uint32_t m_ev = 0u, m_md = 0u;
+        int n_ev = 0, n_md = 0;
+        const int teq = fast_tokens_equal8(load8_unaligned(lp + f2), load8_unaligned(lp + f9));
+        if (line + f10 + 16 < limit && teq >= 0 && fast_uint8(load8_unaligned(lp + f5), ev_idx) &&
+            fast_decimal8(load8_unaligned(lp + f6), m_ev, n_ev) && fast_decimal8(load8_unaligned(lp + f10), m_md, n_md)) {
+            const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
+            diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
+            if (teq) fl |= MC_RF_EQ;
+        } else {
+            const GlobalBytes t{text + line, limit - line};
+            ev_idx = 0;
+            parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+        }
+    }
+    r.name_off = (uint16_t)f3;
+    r.name_len = (uint16_t)(name_end < 0 ? 0 : name_end - f3);
+    r.event_idx = ev_idx;
+    r.diff = diff;
+    r.flags = (uint8_t)fl;
+}

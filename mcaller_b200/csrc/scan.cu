@@ -24,11 +24,12 @@
 //      finds columns 1, 2, 10 and 12 without touching the bytes in between (the ~58 B read name is never walked); 12-column
 //      check, contig lookup, NNNNNN test, position, candidate bit;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the run, or
-//      every kept line in dense mode); those get a 32-byte record, FINISHED here while the line is still staged in shared
-//      memory: columns 3, 4, 6, 7, 10 and 11 are located in the same 160-bit window, event index / currents / k-mers are
-//      decoded from 8-byte register loads (np.round(event_mean - model_mean, 4) in float64, k-mer equality, read-name span),
-//      and the read name is compared with the previous recorded line of the pass (MC_RF_NEWREAD).  Only unusual shapes
-//      (signs, > 7 digit numbers, long tokens, lines beyond the look-ahead) are left raw (MC_RF_RAW) for stage 2.
+//      every kept line in dense mode); those get a 32-byte record {line offset, position, contig, flags, the k-mer's target
+//      bits on both strands} and their slot goes into a 64-entry queue of the warp.  Whenever 32 are queued (and at the end
+//      of a run) the warp FINISHES them together, one lane per record, from the text that is still in L2: column walk,
+//      event index, np.round(event_mean - model_mean, 4) in float64, k-mer equality, read-name span, and the read-change
+//      flag against the previous record (mc_finish_record, parse.cuh) -- the value parse runs at full lane occupancy
+//      although only ~3 % of the lines are recorded.
 //      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
 // Algorithmic HBM traffic: the text itself (once) + 32 B per record (~1 B per line in sparse mode).
@@ -67,6 +68,7 @@ struct WarpSmem {
     alignas(16) uint32_t nl[NW + 4];     // newline bits
     uint16_t lstart[LCAP + 4];
     uint32_t cnt[8];                     // per-warp event counters (flushed once at the end); [6] = records left raw
+    uint32_t q[64];                      // slots of recorded lines waiting to be finished (32 at a time)
     unsigned long long key[4];           // the hint contig's name in 8-byte pieces (quiet test; names of up to 31 bytes)
     alignas(8) unsigned long long bar[2];
 };
@@ -290,69 +292,55 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
     return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, -1, cid, pos);
 }
 
-// ---- record finishing from the staged bytes (what stage 2 did from global memory in round 1) ---------------------------------
-// Columns 3, 4, 6, 7, 10, 11 of the line starting at staged offset s, found by walking the field-start bits of the
-// non-whitespace map; event index, np.round(event_mean - model_mean, 4) (extract_contexts.py:286), k-mer equality (:169) and
-// the read-name span (:161).  Returns false for anything but the usual shapes -- the record then stays MC_RF_RAW and stage 2
-// finishes it from global memory with the byte loops of parse.cuh (same float64 either way).
-// Deliberately out of line and written with loops: it runs once per pass of the ~9 % of chunks that record anything, and
-// what matters is that its instructions stay out of the way of the scan loop (the kernel is instruction-cache sensitive).
-struct Finished {
-    double diff;
-    int ev_idx, name_off, name_len;
-    uint32_t eq;
-};
-__device__ __noinline__ bool finish_line(const uint32_t *nw, const uint8_t *text, int s, Finished *out) {
-    int w = s >> 5;
-    uint32_t cur = nw[w];
-    uint32_t m = cur & ~(cur << 1) & (0xFFFFFFFFu << (s & 31));    // the byte before a line start is a newline: bit s starts a field if set
-    int p[11];
-#pragma unroll 1
-    for (int nf = 0; nf < 11; ++nf) {
-        while (m == 0u) {
-            if (++w >= NW) return false;
-            const uint32_t nx = nw[w];
-            m = nx & ~((nx << 1) | (cur >> 31));
-            cur = nx;
+// ---- batched finishing of queued records: the first n (<= 32) slots of the warp's queue, one lane each ------------------------
+// Out of line: it runs once per 32 recorded lines and must not sit in the scan loop's instruction stream.
+__device__ __noinline__ void scan_flush(WarpSmem &S, mc_record *d_rec, const uint8_t *__restrict__ d_text, int64_t text_limit, int n,
+                                        int &q_n, long long &prev_line, uint32_t &prev_span) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const bool act = lane < n;
+    alignas(16) mc_record r;
+    uint32_t slot = 0u, internal = 0u;
+    if (act) {
+        slot = S.q[lane];
+        const uint4 *src = reinterpret_cast<const uint4 *>(d_rec + slot);
+        uint4 *dr = reinterpret_cast<uint4 *>(&r);
+        dr[0] = __ldcg(src);                                      // written by this warp a few chunks ago (L2)
+        dr[1] = __ldcg(src + 1);
+        internal = r.pad;                                         // bit 0: run-first filler
+        r.pad = 0;
+        mc_finish_record(d_text, text_limit, r);
+    }
+    const long long line = act ? (((long long)r.line_hi << 32) | (long long)r.line_lo) : -1;
+    const uint32_t span = act ? ((uint32_t)r.name_off | ((uint32_t)r.name_len << 16)) : 0u;
+    // a filler is nobody's known predecessor (stage 2 may drop it), nor is a record whose walk failed
+    const bool walk_failed = act && (r.flags & MC_RF_BADIDX) && r.name_len == 0;
+    const long long line_pub = (act && !(internal & 1u) && !walk_failed) ? line : -1;
+    long long pl = __shfl_up_sync(0xffffffffu, line_pub, 1);
+    uint32_t ps = __shfl_up_sync(0xffffffffu, span, 1);
+    if (lane == 0) { pl = prev_line; ps = prev_span; }
+    if (act) {
+        if (pl >= 0 && !walk_failed) {
+            uint32_t fl = r.flags | MC_RF_SEGKNOWN;
+            if ((ps >> 16) != r.name_len || bytes_differ(d_text + pl + (ps & 0xFFFFu), d_text + line + r.name_off, r.name_len))
+                fl |= MC_RF_NEWREAD;
+            r.flags = (uint8_t)fl;
         }
-        p[nf] = 32 * w + __ffs(m) - 1;
-        m &= m - 1u;
+        uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
+        const uint4 *sr = reinterpret_cast<const uint4 *>(&r);
+        dst[0] = sr[0];
+        dst[1] = sr[1];
     }
-    if (p[10] + 12 > WB) return false;                             // the 8-byte loads below must stay inside the staged bytes
-    // end of the read name: first whitespace at or after its start
-    int w3 = p[3] >> 5;
-    uint32_t z = ~nw[w3] & (0xFFFFFFFFu << (p[3] & 31));
-    while (z == 0u) {
-        if (++w3 >= NW) return false;
-        z = ~nw[w3];
-    }
-    const int pend = 32 * w3 + __ffs(z) - 1;
-    const int teq = fast_tokens_equal8(load8(text, p[2]), load8(text, p[9]));
-    if (teq < 0 || !fast_uint8(load8(text, p[5]), out->ev_idx)) return false;
-    double val[2];
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-        uint32_t mant = 0u;
-        int nfrac = 0;
-        if (!fast_decimal8(load8(text, p[j ? 10 : 6]), mant, nfrac)) return false;
-        val[j] = __ddiv_rn((double)mant, c_pow10[nfrac]);
-    }
-    out->diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(val[0], val[1]), 1e4)), 1e4);
-    out->eq = teq ? MC_RF_EQ : 0u;
-    out->name_off = p[3] - s;
-    out->name_len = pend - p[3];
-    return true;
-}
-// do the L staged bytes at offsets a and b differ (8 bytes at a time, any alignment)
-__device__ __noinline__ bool staged_differ(const uint8_t *text, int a, int b, int L) {
-    unsigned long long d = 0ull;
-#pragma unroll 1
-    for (int j = 0; j < L; j += 8) {
-        unsigned long long x = load8(text, a + j) ^ load8(text, b + j);
-        if (L - j < 8) x &= (1ull << (8 * (L - j))) - 1ull;
-        d |= x;
-    }
-    return d != 0ull;
+    prev_line = __shfl_sync(0xffffffffu, line_pub, n - 1);
+    prev_span = __shfl_sync(0xffffffffu, span, n - 1);
+    // move the rest of the queue down
+    const int rest = q_n - n;
+    uint32_t tmp = 0u;
+    if (lane < rest) tmp = S.q[n + lane];
+    __syncwarp();
+    if (lane < rest) S.q[lane] = tmp;
+    q_n = rest;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
@@ -444,6 +432,12 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     if (chunk < n_chunks) cur_async = stage(chunk, 0);
     int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
     unsigned run_total = 0u, run_filler = 0u;                     // records / filler flag of the run so far
+    // ---- batched finishing of the queued records (see 4. above) ---------------------------------------------------------------
+    int q_n = 0;                                                  // queued slots (warp-uniform)
+    long long prev_line = -1;                                     // line / name span of the last finished record of this run, or -1:
+    uint32_t prev_span = 0u;                                      // unknown predecessor (run start, or a filler stage 2 may drop)
+    const int64_t text_limit = nbytes + MC_TEXT_PAD - 64;
+    auto flush = [&](int n) { scan_flush(S, d_rec, d_text, text_limit, n, q_n, prev_line, prev_span); };
 
     while (chunk < n_chunks) {
         const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
@@ -655,7 +649,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
             uint32_t status = 0u;
             int cid = -1, pos = 0, s = 0;
-            bool staged = false;       // first 12 columns inside the staged bytes (else: classified from global memory)
             if (lane < n_pass) {
                 s = S.lstart[lane];
                 const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : (e_last >= 0 ? e_last : next_bit(S.nl, s));
@@ -663,7 +656,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 int f0, f1, f9, f11;
                 line_fields(S, s, f0, f1, f9, f11);
                 if (f11 < e) {
-                    staged = true;
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
                     const unsigned long long k8 = load8(text, f0);
                     // names of up to 7 bytes compare in registers: the name bytes and the whitespace right after them
@@ -709,58 +701,46 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 const int new_hint = __shfl_sync(0xffffffffu, cid, top);       // contig hint follows the last kept line
                 if (new_hint != hint) set_hint(new_hint);
             }
-            // ---- 5. records: finished from the staged bytes, raw only for unusual shapes -------------------------------------
-            int ev_idx = 0, name_off = 0, name_len = 0;
-            double diff = 0.0;
-            uint32_t fl = 0u;
-            bool fin = false;
+            // ---- 5. records: written raw, their slots queued; 32 at a time are finished from the (L2-hot) text -----------------
+            bool queued = false;
+            unsigned long long slot = 0ull;
             if (emit) {
-                fl = 0u;
-                if (status & ST_CAND) {
-                    // the targets inside this line's k-mer on either strand (meth_ref[pos:pos+k], :176) travel with the record
-                    const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
-                    fl = MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
-                }
-                Finished F;
-#if MC_SCAN_FINISH
-                fin = staged && finish_line(S.nw, text, s, &F);
-#endif
-                if (fin) { fl |= F.eq; ev_idx = F.ev_idx; diff = F.diff; name_off = F.name_off; name_len = F.name_len; }
-                else { fl |= MC_RF_RAW; atomicAdd(&S.cnt[6], 1u); }
-            }
-            // read name of the previous recorded line of this pass (same read <=> equal bytes, extract_contexts.py:161);
-            // the first record of a pass and neighbours of raw records are compared in stage 3 instead
-            {
-                // (a run-first "filler" record may still be dropped by stage 2, so it is nobody's known predecessor)
-                const uint32_t my_span = (fin && !filler_lane) ? ((uint32_t)(s + name_off) | ((uint32_t)name_len << 16)) : 0xFFFFFFFFu;
-                const uint32_t below_e = emit_m & lt_mask;
-                const uint32_t prev_span = __shfl_sync(0xffffffffu, my_span, below_e ? 31 - __clz(below_e) : lane);
-                if (fin && below_e && prev_span != 0xFFFFFFFFu) {
-                    fl |= MC_RF_SEGKNOWN;
-                    if ((int)(prev_span >> 16) != name_len || staged_differ(text, (int)(prev_span & 0xFFFFu), s + name_off, name_len))
-                        fl |= MC_RF_NEWREAD;
-                }
-            }
-            if (emit) {
-                const unsigned long long slot = slot_cur + __popc(emit_m & lt_mask);
+                slot = slot_cur + __popc(emit_m & lt_mask);
                 if (slot < rec_cap) {
+                    uint32_t fl = MC_RF_RAW;
+                    if (status & ST_CAND) {
+                        // the targets inside this line's k-mer on either strand (meth_ref[pos:pos+k], :176) travel with the record
+                        const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
+                        fl |= MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
+                    }
+                    if (filler_lane) fl |= 1u << 24;                                    // internal (pad byte): run-first filler
                     const int64_t goff = G0 + s;
                     uint4 a, b;
                     a.x = (uint32_t)(goff & 0xFFFFFFFFll);                              // line_lo
-                    a.y = ((uint32_t)(goff >> 32) & 0xFFFFu) | ((uint32_t)name_off << 16);   // line_hi | name_off
+                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                             // line_hi | name_off (0)
                     a.z = (uint32_t)pos;                                                // pos
-                    a.w = (uint32_t)ev_idx;                                             // event_idx
-                    const unsigned long long db = (unsigned long long)__double_as_longlong(diff);
-                    b.x = (uint32_t)db; b.y = (uint32_t)(db >> 32);                     // diff
-                    b.z = (uint32_t)name_len | ((uint32_t)cid << 16);                   // name_len | contig
+                    a.w = 0u;                                                           // event_idx
+                    b.x = 0u; b.y = 0u;                                                 // diff
+                    b.z = (uint32_t)cid << 16;                                          // name_len (0) | contig
                     b.w = fl;                                                           // flags | kbits_fwd | kbits_rev | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
                     dst[0] = a;
                     dst[1] = b;
+                    queued = true;
                 } else {
                     atomicAdd(&S.cnt[5], 1u);
                 }
             }
+#if MC_SCAN_FINISH
+            {
+                const uint32_t queued_m = __ballot_sync(0xffffffffu, queued);
+                if (queued) S.q[q_n + __popc(queued_m & lt_mask)] = (uint32_t)slot;
+                q_n += __popc(queued_m);
+                if (q_n >= 32) flush(32);
+            }
+#else
+            if (queued) atomicAdd(&S.cnt[6], 1u);
+#endif
             {
                 const unsigned ne = (unsigned)__popc(emit_m);
                 slot_cur += ne;
@@ -781,6 +761,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // per-run entry for stage 2 (which orders the records run by run): {records of the run, first record is a filler |
             // state of the run's last kept line (0 none, 1 not a candidate, 2 candidate) << 1}
             if (lane == 0) reinterpret_cast<uint2 *>(d_run_tab)[chunk / run_len] = make_uint2(run_total, run_filler | ((uint32_t)(prev_state + 1) << 1));
+            while (q_n > 0) flush(q_n < 32 ? q_n : 32);           // the next run's first record has no known predecessor
+            prev_line = -1;
             run_total = 0u;
             run_filler = 0u;
             prev_state = -1;
