@@ -84,8 +84,7 @@ typedef struct mc_record {
 #define MC_RF_CAND 2u      /* k-mer window touches a target on either strand */
 #define MC_RF_BADNUM 4u    /* event/model mean not a plain decimal (<= 18 digits) */
 #define MC_RF_BADIDX 8u    /* event index not a plain integer */
-#define MC_RF_RAW 16u      /* stage-1 form of a line mc_scan could not finish from its staged bytes (unusual number shapes, very
-                              long lines): event_idx / diff / name span are filled in by mc_order_records, which clears the flag */
+#define MC_RF_RAW 16u      /* stage-1 form: event_idx / diff / name span are not filled in yet; mc_order_records does and clears the flag */
 #define MC_RF_NEWREAD 32u  /* read name differs from the previous record's (valid when MC_RF_SEGKNOWN is set) */
 #define MC_RF_SEGKNOWN 64u /* mc_order_records compared the read name with the previous record's */
 
@@ -101,7 +100,6 @@ enum {
     MC_C_LONGLINE,         /* lines whose first 12 columns outran the look-ahead and took the byte-wise slow path (informational) */
     MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
     MC_C_RUN_CURSOR,       /* internal: next unclaimed run of chunks (dynamic work distribution of mc_scan) */
-    MC_C_RAW,              /* records left in raw form (MC_RF_RAW) for mc_order_records to finish (informational) */
     MC_C_COUNT = 16
 };
 
@@ -186,9 +184,8 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
  * holes); d_tile_tab[chunk] = {first record slot, count | flags} and d_run_tab[run] = {records of the run, flags} are consumed
  * by mc_order_records, which also drops the run-first records whose predecessor line turns out not to be a candidate.
- * Records are finished here while the line is staged in shared memory (event index, np.round(event_mean - model_mean, 4),
- * k-mer equality, read-name span, target bits of the k-mer, read-change flag against the previous record of the pass); only
- * unusual shapes are left raw (MC_RF_RAW, counted in MC_C_RAW).
+ * Records leave this stage raw (MC_RF_RAW): line offset, position, contig, candidate flag and the target bits of the k-mer on
+ * both strands; their values are parsed by mc_order_records at full lane occupancy.
  * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
  * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
  * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
@@ -216,10 +213,10 @@ int64_t mc_workspace_bytes(int64_t n);
 
 /* Stage 2 -- put the records into file order (exclusive scan of the run table, then one warp per run gathers its chunks).  d_rec_in is the stage-1
  * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
- * records, which land densely in d_rec_out (rec_out_cap slots; rec_in_cap is always enough).  Records that stage 1 left
- * in raw form (MC_RF_RAW) are finished here, one thread per record: event index, the float64 np.round(event_mean -
- * model_mean, 4) from exact decimal parsing, and the k-mer equality flag (extract_contexts.py:150, :169, :286); read-name
- * changes between neighbouring records are flagged (MC_RF_NEWREAD).  d_scan_counters: the counter block mc_scan wrote
+ * records, which land densely in d_rec_out (rec_out_cap slots; rec_in_cap is always enough).  Records arrive in raw form
+ * (MC_RF_RAW) and are finished here, one thread per record: event index, the float64 np.round(event_mean - model_mean, 4)
+ * from exact decimal parsing, the k-mer equality flag (extract_contexts.py:150, :169, :286) and the read-name span;
+ * read-name changes between neighbouring records are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD).  d_scan_counters: the counter block mc_scan wrote
  * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
  * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
 int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uint32_t *d_tile_tab, int64_t n_tiles, uint32_t *d_run_tab,

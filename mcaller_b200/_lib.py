@@ -15,7 +15,7 @@ MC_TILE_BYTES = 3840
 MC_TEXT_PAD = 4096
 MC_MAXK = 8
 MC_C_COUNT = 16
-COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor", "raw"]
+COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor"]
 
 MC_ABI_VERSION = 2
 MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M, MC_NONE = 0, 1, 2, 3

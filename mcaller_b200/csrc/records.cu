@@ -234,21 +234,36 @@ __global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict_
 
 __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
 
-// Stage 1 finishes its records itself, in batches of 32 while their lines are still in L2 (mc_finish_record, parse.cuh).
-// This kernel only exists for records that arrive raw some other way (tuning builds with MC_SCAN_FINISH=0, callers that
-// fill records themselves): one thread per record, and the whole grid leaves at once when stage 1 reports no raw record.
+// Stage 1 leaves its records raw {line offset, position, contig, flags, k-mer target bits}; they are finished here at
+// full lane occupancy (mc_finish_record, parse.cuh: column walk, event index, np.round(event_mean - model_mean, 4), k-mer
+// equality, read-name span).  A warp finishes 31 records; lane 0 re-walks the record before them (the previous warp's
+// last) only to know its read-name span, so that every lane can compare its read name with its predecessor's, handed over
+// by one shuffle while both lines are still in L1.  That comparison is the read segmentation flag (MC_RF_NEWREAD).
 __global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
-                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap,
-                                                       const unsigned long long *__restrict__ scan_counters) {
-    if (scan_counters && scan_counters[MC_C_RAW] == 0ull) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dev_count(d_n, rec_cap)) return;
-    alignas(16) mc_record r = rec[i];
-    if (!(r.flags & MC_RF_RAW)) return;
-    mc_finish_record(text, limit, r);
+                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long i = warp * 31 + lane - 1;
+    const bool active = i >= 0 && i < dev_count(d_n, rec_cap);
+    alignas(16) mc_record r;
+    if (active) r = rec[i];
+    else { r.line_lo = 0u; r.line_hi = 0; r.name_off = 0; r.name_len = 0; r.flags = 0; r.pos = 0; r.contig = 0; r.event_idx = 0; r.diff = 0.0; }
+    // lane 0 always walks: the record's owner (previous warp) may be rewriting it right now, only its line offset is stable
+    const bool raw = active && (lane == 0 || (r.flags & MC_RF_RAW));
+    const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
+    if (raw) mc_finish_record(text, limit, r);
+    // read segmentation: same read as the previous record <=> equal name length and bytes (extract_contexts.py:161, :179)
+    const unsigned long long prev_line = __shfl_up_sync(0xffffffffu, (unsigned long long)line, 1);
+    const uint32_t prev_span = __shfl_up_sync(0xffffffffu, (uint32_t)r.name_off | ((uint32_t)r.name_len << 16), 1);
+    if (!active || lane == 0) return;
+    uint32_t fl = r.flags | MC_RF_SEGKNOWN;
+    if (i == 0 || (prev_span >> 16) != r.name_len ||
+        bytes_differ(text + (int64_t)prev_line + (prev_span & 0xFFFFu), text + line + r.name_off, r.name_len))
+        fl |= MC_RF_NEWREAD;
+    r.flags = (uint8_t)fl;
     uint4 *dst = reinterpret_cast<uint4 *>(rec + i);
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    dst[0] = src[0];
+    if (raw) dst[0] = src[0];
     dst[1] = src[1];
 }
 
@@ -342,9 +357,9 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uin
                                                                         (unsigned long long)rec_in_cap, d_rec_out, (unsigned long long)rec_out_cap);
     MC_LAUNCH_CHECK();
     // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
-    k_finish_records<<<(unsigned)((rec_out_cap + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
-                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap,
-                                                                            reinterpret_cast<const unsigned long long *>(d_scan_counters));
+    // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
+    k_finish_records<<<(unsigned)((rec_out_cap + 247) / 248), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
+                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

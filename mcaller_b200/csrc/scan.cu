@@ -24,12 +24,10 @@
 //      finds columns 1, 2, 10 and 12 without touching the bytes in between (the ~58 B read name is never walked); 12-column
 //      check, contig lookup, NNNNNN test, position, candidate bit;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the run, or
-//      every kept line in dense mode); those get a 32-byte record {line offset, position, contig, flags, the k-mer's target
-//      bits on both strands} and their slot goes into a 64-entry queue of the warp.  Whenever 32 are queued (and at the end
-//      of a run) the warp FINISHES them together, one lane per record, from the text that is still in L2: column walk,
-//      event index, np.round(event_mean - model_mean, 4) in float64, k-mer equality, read-name span, and the read-change
-//      flag against the previous record (mc_finish_record, parse.cuh) -- the value parse runs at full lane occupancy
-//      although only ~3 % of the lines are recorded.
+//      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags, the k-mer's
+//      target bits on both strands}.  Their values (event index, currents, k-mer equality, read-name span) are parsed in
+//      stage 2 at full lane occupancy: finishing them here, from the staged bytes or in L2-hot batches, was measured at
+//      +3 ms and +10 ms on this kernel (long dependent chains in a warp that has a single chunk of prefetch in flight).
 //      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
 // Algorithmic HBM traffic: the text itself (once) + 32 B per record (~1 B per line in sparse mode).
@@ -51,9 +49,6 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_RUN
 #define MC_SCAN_RUN 32
 #endif
-#ifndef MC_SCAN_FINISH
-#define MC_SCAN_FINISH 1                      // 0 (tuning builds): leave every record raw for stage 2, as in round 1
-#endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int LCAP = 32;                      // lines per pass (one per lane)
@@ -64,11 +59,10 @@ static_assert(MC_TEXT_PAD >= LOOKA + 64, "text padding must cover the look-ahead
 
 struct WarpSmem {
     alignas(16) uint8_t text[2][WB];     // double-buffered staged bytes (TMA destination, 16-byte aligned)
-    alignas(16) uint32_t nw[NW + 8];     // non-whitespace bits (byte > 0x20; zero padded): field starts / ends are derived from it
+    alignas(16) uint32_t fs[NW + 8];     // field-start bits (zero padded)
     alignas(16) uint32_t nl[NW + 4];     // newline bits
     uint16_t lstart[LCAP + 4];
-    uint32_t cnt[8];                     // per-warp event counters (flushed once at the end); [6] = records left raw
-    uint32_t q[64];                      // slots of recorded lines waiting to be finished (32 at a time)
+    uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
     unsigned long long key[4];           // the hint contig's name in 8-byte pieces (quiet test; names of up to 31 bytes)
     alignas(8) unsigned long long bar[2];
 };
@@ -119,19 +113,14 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
 
 // ---- generic field walk (rare: lines whose first 12 columns do not fit the 160-bit window) ------------------------------
 // position of the n-th (0-based) field start at or after smem offset s; NW*32 when it lies beyond the staged bytes
-// field-start bits of mask word w: non-whitespace bytes whose predecessor is whitespace
-__device__ __forceinline__ uint32_t fs_word(const uint32_t *nw, int w) {
-    const uint32_t v = nw[w];
-    return v & ~((v << 1) | (w > 0 ? nw[w - 1] >> 31 : 0u));
-}
-__device__ __noinline__ int select_fs_walk(const uint32_t *nw, int s, int n) {
+__device__ __noinline__ int select_fs_walk(const uint32_t *fs, int s, int n) {
     int w = s >> 5;
-    uint32_t m = fs_word(nw, w) & (0xFFFFFFFFu << (s & 31));
+    uint32_t m = fs[w] & (0xFFFFFFFFu << (s & 31));
     int c = __popc(m);
     while (c <= n) {
         n -= c;
         if (++w >= NW) return NW * 32;
-        m = fs_word(nw, w);
+        m = fs[w];
         c = __popc(m);
     }
     for (; n > 0; --n) m &= m - 1u;
@@ -155,30 +144,11 @@ __device__ __forceinline__ int nth_bit(uint32_t m, int j) {     // position of t
     for (int t = 6; t < j; ++t) m &= m - 1u;                     // words with more than 7 field starts: rare
     return __ffs(m) - 1;
 }
-// 160-bit window aligned at the line start s: N = non-whitespace bits, F = field-start bits (the byte before a line start
-// is a newline, so bit 0 of the window has a whitespace predecessor)
-struct LineWindow {
-    uint32_t N0, N1, N2, N3, N4, F0, F1, F2, F3, F4;
-};
-__device__ __forceinline__ LineWindow line_window(const WarpSmem &S, int s) {
-    const int w0 = s >> 5, sh = s & 31;
-    const uint32_t a0 = S.nw[w0], a1 = S.nw[w0 + 1], a2 = S.nw[w0 + 2], a3 = S.nw[w0 + 3], a4 = S.nw[w0 + 4], a5 = S.nw[w0 + 5];
-    LineWindow L;
-    L.N0 = __funnelshift_r(a0, a1, sh);
-    L.N1 = __funnelshift_r(a1, a2, sh);
-    L.N2 = __funnelshift_r(a2, a3, sh);
-    L.N3 = __funnelshift_r(a3, a4, sh);
-    L.N4 = __funnelshift_r(a4, a5, sh);
-    L.F0 = L.N0 & ~(L.N0 << 1);
-    L.F1 = L.N1 & ~((L.N1 << 1) | (L.N0 >> 31));
-    L.F2 = L.N2 & ~((L.N2 << 1) | (L.N1 >> 31));
-    L.F3 = L.N3 & ~((L.N3 << 1) | (L.N2 >> 31));
-    L.F4 = L.N4 & ~((L.N4 << 1) | (L.N3 >> 31));
-    return L;
-}
 __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11) {
-    const LineWindow L = line_window(S, s);
-    const uint32_t W0 = L.F0, W1 = L.F1, W2 = L.F2, W3 = L.F3, W4 = L.F4;
+    const int w0 = s >> 5, sh = s & 31;
+    const uint32_t a0 = S.fs[w0], a1 = S.fs[w0 + 1], a2 = S.fs[w0 + 2], a3 = S.fs[w0 + 3], a4 = S.fs[w0 + 4], a5 = S.fs[w0 + 5];
+    const uint32_t W0 = __funnelshift_r(a0, a1, sh), W1 = __funnelshift_r(a1, a2, sh), W2 = __funnelshift_r(a2, a3, sh),
+                   W3 = __funnelshift_r(a3, a4, sh), W4 = __funnelshift_r(a4, a5, sh);
     const int c0 = __popc(W0), c1 = c0 + __popc(W1), c2 = c1 + __popc(W2), c3 = c2 + __popc(W3), c4 = c3 + __popc(W4);
     if (c4 >= 12) {
         auto sel = [&](int k) {
@@ -212,10 +182,10 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
         }
     } else {
         // fewer than 12 field starts within 160 bytes: short line or unusually wide columns -> generic walk
-        f0 = select_fs_walk(S.nw, s, 0);
-        f1 = select_fs_walk(S.nw, s, 1);
-        f9 = select_fs_walk(S.nw, s, 9);
-        f11 = select_fs_walk(S.nw, s, 11);
+        f0 = select_fs_walk(S.fs, s, 0);
+        f1 = select_fs_walk(S.fs, s, 1);
+        f9 = select_fs_walk(S.fs, s, 9);
+        f11 = select_fs_walk(S.fs, s, 11);
     }
 }
 
@@ -290,57 +260,6 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
     }
     if (nf < 12) return ST_SHORT;
     return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, -1, cid, pos);
-}
-
-// ---- batched finishing of queued records: the first n (<= 32) slots of the warp's queue, one lane each ------------------------
-// Out of line: it runs once per 32 recorded lines and must not sit in the scan loop's instruction stream.
-__device__ __noinline__ void scan_flush(WarpSmem &S, mc_record *d_rec, const uint8_t *__restrict__ d_text, int64_t text_limit, int n,
-                                        int &q_n, long long &prev_line, uint32_t &prev_span) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    const bool act = lane < n;
-    alignas(16) mc_record r;
-    uint32_t slot = 0u, internal = 0u;
-    if (act) {
-        slot = S.q[lane];
-        const uint4 *src = reinterpret_cast<const uint4 *>(d_rec + slot);
-        uint4 *dr = reinterpret_cast<uint4 *>(&r);
-        dr[0] = __ldcg(src);                                      // written by this warp a few chunks ago (L2)
-        dr[1] = __ldcg(src + 1);
-        internal = r.pad;                                         // bit 0: run-first filler
-        r.pad = 0;
-        mc_finish_record(d_text, text_limit, r);
-    }
-    const long long line = act ? (((long long)r.line_hi << 32) | (long long)r.line_lo) : -1;
-    const uint32_t span = act ? ((uint32_t)r.name_off | ((uint32_t)r.name_len << 16)) : 0u;
-    // a filler is nobody's known predecessor (stage 2 may drop it), nor is a record whose walk failed
-    const bool walk_failed = act && (r.flags & MC_RF_BADIDX) && r.name_len == 0;
-    const long long line_pub = (act && !(internal & 1u) && !walk_failed) ? line : -1;
-    long long pl = __shfl_up_sync(0xffffffffu, line_pub, 1);
-    uint32_t ps = __shfl_up_sync(0xffffffffu, span, 1);
-    if (lane == 0) { pl = prev_line; ps = prev_span; }
-    if (act) {
-        if (pl >= 0 && !walk_failed) {
-            uint32_t fl = r.flags | MC_RF_SEGKNOWN;
-            if ((ps >> 16) != r.name_len || bytes_differ(d_text + pl + (ps & 0xFFFFu), d_text + line + r.name_off, r.name_len))
-                fl |= MC_RF_NEWREAD;
-            r.flags = (uint8_t)fl;
-        }
-        uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
-        const uint4 *sr = reinterpret_cast<const uint4 *>(&r);
-        dst[0] = sr[0];
-        dst[1] = sr[1];
-    }
-    prev_line = __shfl_sync(0xffffffffu, line_pub, n - 1);
-    prev_span = __shfl_sync(0xffffffffu, span, n - 1);
-    // move the rest of the queue down
-    const int rest = q_n - n;
-    uint32_t tmp = 0u;
-    if (lane < rest) tmp = S.q[n + lane];
-    __syncwarp();
-    if (lane < rest) S.q[lane] = tmp;
-    q_n = rest;
-    __syncwarp();
 }
 
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
@@ -432,12 +351,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     if (chunk < n_chunks) cur_async = stage(chunk, 0);
     int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
     unsigned run_total = 0u, run_filler = 0u;                     // records / filler flag of the run so far
-    // ---- batched finishing of the queued records (see 4. above) ---------------------------------------------------------------
-    int q_n = 0;                                                  // queued slots (warp-uniform)
-    long long prev_line = -1;                                     // line / name span of the last finished record of this run, or -1:
-    uint32_t prev_span = 0u;                                      // unknown predecessor (run start, or a filler stage 2 may drop)
-    const int64_t text_limit = nbytes + MC_TEXT_PAD - 64;
-    auto flush = [&](int n) { scan_flush(S, d_rec, d_text, text_limit, n, q_n, prev_line, prev_span); };
 
     while (chunk < n_chunks) {
         const int64_t G0 = (int64_t)chunk * CHUNK - LOOKB;        // global offset of staged byte 0
@@ -622,6 +535,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // ---- 3. full parse: field-start map of the chunk (once), then one lane per line -------------------------------
             if (!full_ready) {
                 full_ready = true;
+                uint32_t prev_top = 0u;                               // was the last byte of word 32r-1 non-whitespace
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int w = 32 * r + lane;
@@ -629,9 +543,14 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
                     const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x),
                                                   gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w));
-                    S.nw[w] = nonws;
+                    // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
+                    const uint32_t top = nonws >> 31;
+                    uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
+                    if (lane == 0) pt = prev_top;
+                    prev_top = __shfl_sync(0xffffffffu, top, 31);
+                    S.fs[w] = nonws & ~((nonws << 1) | pt);
                 }
-                if (lane < 8) S.nw[NW + lane] = 0u;
+                if (lane < 8) S.fs[NW + lane] = 0u;
                 // end of the chunk's last line = first newline at or after the last owned byte; found by the lanes that hold
                 // the look-ahead words instead of a single lane walking the bit map
                 if (!tail) {
@@ -701,46 +620,32 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 const int new_hint = __shfl_sync(0xffffffffu, cid, top);       // contig hint follows the last kept line
                 if (new_hint != hint) set_hint(new_hint);
             }
-            // ---- 5. records: written raw, their slots queued; 32 at a time are finished from the (L2-hot) text -----------------
-            bool queued = false;
-            unsigned long long slot = 0ull;
+            // ---- 5. raw records ------------------------------------------------------------------------------------------
             if (emit) {
-                slot = slot_cur + __popc(emit_m & lt_mask);
+                const unsigned long long slot = slot_cur + __popc(emit_m & lt_mask);
                 if (slot < rec_cap) {
+                    const int64_t goff = G0 + s;
                     uint32_t fl = MC_RF_RAW;
                     if (status & ST_CAND) {
                         // the targets inside this line's k-mer on either strand (meth_ref[pos:pos+k], :176) travel with the record
                         const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
                         fl |= MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
                     }
-                    if (filler_lane) fl |= 1u << 24;                                    // internal (pad byte): run-first filler
-                    const int64_t goff = G0 + s;
                     uint4 a, b;
-                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                              // line_lo
-                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                             // line_hi | name_off (0)
-                    a.z = (uint32_t)pos;                                                // pos
-                    a.w = 0u;                                                           // event_idx
-                    b.x = 0u; b.y = 0u;                                                 // diff
-                    b.z = (uint32_t)cid << 16;                                          // name_len (0) | contig
-                    b.w = fl;                                                           // flags | kbits_fwd | kbits_rev | pad
+                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                   // line_lo
+                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                  // line_hi | name_off (0)
+                    a.z = (uint32_t)pos;                                     // pos
+                    a.w = 0u;                                                // event_idx
+                    b.x = 0u; b.y = 0u;                                      // diff
+                    b.z = (uint32_t)cid << 16;                               // name_len (0) | contig
+                    b.w = fl;                                                // flags | kbits_fwd | kbits_rev | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
                     dst[0] = a;
                     dst[1] = b;
-                    queued = true;
                 } else {
                     atomicAdd(&S.cnt[5], 1u);
                 }
             }
-#if MC_SCAN_FINISH
-            {
-                const uint32_t queued_m = __ballot_sync(0xffffffffu, queued);
-                if (queued) S.q[q_n + __popc(queued_m & lt_mask)] = (uint32_t)slot;
-                q_n += __popc(queued_m);
-                if (q_n >= 32) flush(32);
-            }
-#else
-            if (queued) atomicAdd(&S.cnt[6], 1u);
-#endif
             {
                 const unsigned ne = (unsigned)__popc(emit_m);
                 slot_cur += ne;
@@ -761,8 +666,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             // per-run entry for stage 2 (which orders the records run by run): {records of the run, first record is a filler |
             // state of the run's last kept line (0 none, 1 not a candidate, 2 candidate) << 1}
             if (lane == 0) reinterpret_cast<uint2 *>(d_run_tab)[chunk / run_len] = make_uint2(run_total, run_filler | ((uint32_t)(prev_state + 1) << 1));
-            while (q_n > 0) flush(q_n < 32 ? q_n : 32);           // the next run's first record has no known predecessor
-            prev_line = -1;
             run_total = 0u;
             run_filler = 0u;
             prev_state = -1;
@@ -780,9 +683,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         if (c_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)c_lines);
         if (c_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)c_kept);
     }
-    if (lane < 7) {
+    if (lane < 6) {
         const int which = lane == 0 ? MC_C_SHORT : lane == 1 ? MC_C_UNKNOWN_CONTIG : lane == 2 ? MC_C_NNN : lane == 3 ? MC_C_BADPOS
-                        : lane == 4 ? MC_C_LONGLINE : lane == 5 ? MC_C_OVERFLOW : MC_C_RAW;
+                        : lane == 4 ? MC_C_LONGLINE : MC_C_OVERFLOW;
         const unsigned v = S.cnt[lane];
         if (v) atomicAdd(&d_counters[which], (unsigned long long)v);
     }
