@@ -306,9 +306,11 @@ int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64_t *d_next_
 /*
  * Stage 6 -- classifier: model[key].predict_proba([x])[0][1] and the 0.5 label threshold
  * (extract_contexts.py:195-207) for every MC_CALL row; float64 arithmetic.  models[0] = 'MH'/'general',
- * models[1] = 'MG' (only read when a row has model_sel == 1).  d_nrows[0] (device) rows, row_cap >= it.
+ * models[1] = 'MG' (only read when a row has model_sel == 1).  d_nrows[0] (device) rows, row_cap >= it.  d_ws: scratch of
+ * mc_classify_workspace_bytes(row_cap) bytes (index list of the call rows, so the kernels run with every lane busy).
  */
-int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, const mc_model *models, void *stream);
+int64_t mc_classify_workspace_bytes(int64_t row_cap);
+int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t row_cap, const mc_model *models, void *d_ws, void *stream);
 
 /*
  * Stage 7 -- per-position aggregation (make_bed.py:86-96): depth and methylated counts per site slot, plus the

@@ -111,8 +111,9 @@ _PROTOS = {
     # d_carry, closing_contig, d_next_contigs, from, count, d_row_out, d_depth, d_meth, d_first, n_sites, d_row_base, stream
     "mc_carry_close": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_void_p, C.c_void_p]),
-    # d_calls, d_nrows, row_cap, models, stream
-    "mc_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Model), C.c_void_p]),
+    "mc_classify_workspace_bytes": (C.c_int64, [C.c_int64]),
+    # d_calls, d_nrows, row_cap, models, d_ws, stream
+    "mc_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Model), C.c_void_p, C.c_void_p]),
     # d_calls, d_nrows, row_cap, d_depth, d_meth, d_first, n_sites, d_row_base, d_odd, odd_cap, d_n_odd, d_abort, stream
     "mc_hist_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

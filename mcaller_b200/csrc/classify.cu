@@ -15,9 +15,38 @@ constexpr int WARPS = 8;
 
 __device__ __forceinline__ double expit(double x) { return x < 0.0 ? exp(x) / (1.0 + exp(x)) : 1.0 / (1.0 + exp(-x)); }
 
+// tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2|x|), without branches: n = rint(y log2 e), r = y - n ln 2 (two-step), exp(r) by
+// its degree-13 Taylor polynomial on |r| <= ln2 / 2 (remainder < 5e-18), 2^n through the exponent field.  Absolute error
+// ~2e-16 -- the hidden activations feed a dot product whose result only has to match scikit-learn's float64 to 1e-12 --
+// at a third of the instructions of the library routine and with every lane on the same path (the float64 tanh was 55 % of
+// k_mlp_1hidden's instructions at 14 of 32 lanes active).
+__device__ __forceinline__ double mc_tanh(double x) {
+    double y = -2.0 * fabs(x);
+    y = fmax(y, -80.0);                                        // t < 2e-35: the quotient is 1 to the last bit
+    const double n = rint(y * 1.4426950408889634074);
+    double r = fma(n, -6.93147180369123816490e-01, y);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                         // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);                     // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);                     // 1/11!
+    p = fma(p, r, 2.7557319223985890e-07);                     // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                     // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);                     // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);                     // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);                     // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);                     // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                     // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                     // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double t = p * __longlong_as_double((long long)(1023 + (int)n) << 52);
+    return copysign(__ddiv_rn(1.0 - t, 1.0 + t), x);
+}
+
 __device__ __forceinline__ double activate(double v, int act) {
     switch (act) {
-        case MC_ACT_TANH: return tanh(v);
+        case MC_ACT_TANH: return mc_tanh(v);
         case MC_ACT_LOGISTIC: return expit(v);
         case MC_ACT_RELU: return v > 0.0 ? v : 0.0;
         default: return v;
@@ -134,11 +163,34 @@ k_mlp(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__re
 // one, nothing passes through shared memory but the staged weights, and the output dot product is finished with two
 // shuffles.  Same arithmetic as k_mlp: dot product in input order, then the intercept, activation, logistic output.
 constexpr int MLP_MAX_IN = MC_MAXK + 1;
-__global__ void __launch_bounds__(WARPS * 32)
-k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n, mc_model m0, mc_model m1, int nw0,
-              int nb0, int nw1, int nb1, int alias) {
-    extern __shared__ __align__(16) double s_mlp[];          // [weights 0][biases 0][weights 1][biases 1]
+
+// rows that need a probability (kind MC_CALL) -> dense index list, so the classifier kernels run with every lane busy
+// (rows of other kinds -- too-many-skips and multi-M events, empty slots -- are ~30 % of the rows for GATC)
+__global__ void __launch_bounds__(256) k_call_index(const mc_call *__restrict__ calls, int64_t n_cap, const unsigned long long *__restrict__ d_n,
+                                                   uint32_t *__restrict__ idx, unsigned long long *__restrict__ d_nidx) {
+    __shared__ unsigned int s_warp[8];
+    __shared__ unsigned long long s_base;
     const int64_t n = mc_dev_count(d_n, n_cap);
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;       // block-uniform
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_call = i < n && calls[i].kind == MC_CALL;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t m = __ballot_sync(0xffffffffu, is_call);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tot = 0u;
+        for (int w = 0; w < 8; ++w) { const unsigned int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(d_nidx, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (is_call) idx[s_base + s_warp[wid] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(WARPS * 32)
+k_mlp_1hidden(mc_call *__restrict__ calls, const uint32_t *__restrict__ idx, const unsigned long long *__restrict__ d_nidx, mc_model m0,
+              mc_model m1, int nw0, int nb0, int nw1, int nb1, int alias) {
+    extern __shared__ __align__(16) double s_mlp[];          // [weights 0][biases 0][weights 1][biases 1]
+    const int64_t n = (int64_t)*d_nidx;                      // call rows in the index list
     if ((int64_t)blockIdx.x * WARPS * 8 >= n) return;        // nothing for this block: skip staging the weights
     for (int j = threadIdx.x; j < nw0; j += WARPS * 32) s_mlp[j] = __ldg(m0.d_weights + j);
     for (int j = threadIdx.x; j < nb0; j += WARPS * 32) s_mlp[nw0 + j] = __ldg(m0.d_biases + j);
@@ -148,18 +200,17 @@ k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long lo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 3, grp = lane >> 2;
     const int64_t stride = (int64_t)gridDim.x * WARPS * 8;
     for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * 8; base < n; base += stride) {      // warp-uniform
-        const int64_t i = base + grp;
+        int64_t i = base + grp;
         int ks = -1;
         double x[MLP_MAX_IN];
 #pragma unroll
         for (int k = 0; k < MLP_MAX_IN; ++k) x[k] = 0.0;
         if (i < n) {
+            i = (int64_t)__ldg(idx + i);
             const mc_call &c = calls[i];
-            if (c.kind == MC_CALL) {
-                ks = (int)c.model_sel;
+            ks = (int)c.model_sel;
 #pragma unroll
-                for (int k = 0; k < MLP_MAX_IN; ++k) x[k] = c.feat[k];
-            }
+            for (int k = 0; k < MLP_MAX_IN; ++k) x[k] = c.feat[k];
         }
         const bool second = ks > 0;
         const mc_model &m = second ? m1 : m0;
@@ -186,7 +237,7 @@ k_mlp_1hidden(mc_call *__restrict__ calls, int64_t n_cap, const unsigned long lo
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int o = o0 + 4 * j;
-                    if (o < H) out = fma(activate(z[j] + b0[o], act), w1[o], out);     // dot product first, then the intercept
+                    if (o < H) out = fma(act == MC_ACT_TANH ? mc_tanh(z[j] + b0[o]) : activate(z[j] + b0[o], act), w1[o], out);   // dot product first, then the intercept
                 }
             }
         }
@@ -550,9 +601,11 @@ extern "C" int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64
     return MC_OK;
 }
 
+extern "C" int64_t mc_classify_workspace_bytes(int64_t row_cap) { return 256 + 4 * (row_cap < 1 ? 1 : row_cap); }
+
 extern "C" int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t n_calls /* capacity */, const mc_model *models,
-                           void *stream) {
-    MC_REQUIRE(d_calls && d_nrows && models, "null pointer");
+                           void *d_ws, void *stream) {
+    MC_REQUIRE(d_calls && d_nrows && models && d_ws, "null pointer");
     if (n_calls <= 0) return MC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_nrows);
@@ -591,8 +644,14 @@ extern "C" int mc_classify(mc_call *d_calls, const uint64_t *d_nrows, int64_t n_
             if (one_hidden(m0) && (alias || m1.kind != MC_MLP || one_hidden(m1)) && weight_bytes <= 100 * 1024) {
                 int64_t b2 = (n_calls + WARPS * 8 - 1) / (WARPS * 8);
                 if (b2 > (int64_t)sms * 8) b2 = (int64_t)sms * 8;
+                // index list of the MC_CALL rows first: [count (u64, 256-byte slot)][row indices u32]
+                unsigned long long *d_nidx = reinterpret_cast<unsigned long long *>(d_ws);
+                uint32_t *d_idx = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_ws) + 256);
+                MC_CUDA_CHECK(cudaMemsetAsync(d_nidx, 0, 8, st));
+                k_call_index<<<(unsigned)((n_calls + 255) / 256), 256, 0, st>>>(d_calls, n_calls, dn, d_idx, d_nidx);
+                MC_LAUNCH_CHECK();
                 MC_CUDA_CHECK(cudaFuncSetAttribute(k_mlp_1hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)weight_bytes));
-                k_mlp_1hidden<<<(unsigned)b2, WARPS * 32, weight_bytes, st>>>(d_calls, n_calls, dn, m0, m1, nw0, nb0, nw1, nb1, alias);
+                k_mlp_1hidden<<<(unsigned)b2, WARPS * 32, weight_bytes, st>>>(d_calls, d_idx, d_nidx, m0, m1, nw0, nb0, nw1, nb1, alias);
             } else if (staged_bytes <= 100 * 1024) {
                 MC_CUDA_CHECK(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
                 k_mlp<true><<<(unsigned)blocks, WARPS * 32, staged_bytes, st>>>(d_calls, n_calls, dn, m0, m1, width, nw0, nb0, nw1, nb1, alias);

@@ -274,8 +274,9 @@ class Engine(object):
         # + 7 windows (first-'M', 2 passes, 3 scan kernels, capacity check) + guard + carry
         self.launches += 1 + 6 + 5 + 1 + 7 + 2
         if self.models is not None:
-            check(L.mc_classify(V(calls.data_ptr()), self._status_ptr(S_NROWS), call_cap + 1, self.models.array, st))
-            self.launches += 1
+            cls_ws = self._buf("cls_ws", L.mc_classify_workspace_bytes(call_cap + 1))
+            check(L.mc_classify(V(calls.data_ptr()), self._status_ptr(S_NROWS), call_cap + 1, self.models.array, V(cls_ws.data_ptr()), st))
+            self.launches += 2                       # index list of the call rows + the classifier
             if self.histogram:
                 check(L.mc_hist_accumulate(V(calls.data_ptr()), self._status_ptr(S_NROWS), call_cap + 1, V(self.d_depth.data_ptr()),
                                            V(self.d_meth.data_ptr()), V(self.d_first.data_ptr()), self.ref.n_sites, self._persist_ptr(P_ROW_BASE),

@@ -183,7 +183,8 @@ def test_classifiers_match_sklearn(kind, tol, cuda_lib, oracle):
     n_live = len(X) - 20
     d = torch.from_numpy(calls.view(np.uint8).reshape(-1).copy()).cuda()
     d_n = torch.tensor([n_live], dtype=torch.int64, device="cuda")
-    _lib.check(cuda_lib.mc_classify(C.c_void_p(d.data_ptr()), C.c_void_p(d_n.data_ptr()), len(X), dm.array,
+    d_ws = torch.zeros(int(cuda_lib.mc_classify_workspace_bytes(len(X))), dtype=torch.uint8, device="cuda")
+    _lib.check(cuda_lib.mc_classify(C.c_void_p(d.data_ptr()), C.c_void_p(d_n.data_ptr()), len(X), dm.array, C.c_void_p(d_ws.data_ptr()),
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     out = d.cpu().numpy().view(_lib.CALL_DTYPE)
     assert np.all(out["prob"][n_live:] == 0)
