@@ -575,6 +575,25 @@ def main():
     total_calls = calls_per_step * args.steps
     value = total_calls / (elapsed_ms / 1e3)
 
+    # N > 1 runs configs[2] while the driver's N = 1 run is configs[1] (fewer calls per byte): so that the scaling of THIS
+    # workload can be read off the line, rank 0 also times its own slice alone (no collectives, the other ranks wait)
+    solo = None
+    if use_dist:
+        if rank == 0:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                engine.reset_histogram(0)
+                engine.run_chunk(d_text, nbytes)
+                engine.close_carry(-1, fetch=False)
+                engine.bed_select(BED_DEPTH, BED_THRESH)
+            s1.record()
+            torch.cuda.synchronize()
+            solo_calls = int(engine.d_depth.sum().item()) + len(engine.odd_rows())
+            solo = {"value": solo_calls * args.steps / (s0.elapsed_time(s1) / 1e3), "unit": UNIT, "ms_per_step": s0.elapsed_time(s1) / args.steps,
+                    "what": "rank 0's slice of the same workload timed alone on one GPU after the multi-GPU region (no collectives)"}
+        dist.barrier()
+
     # roofline of the dominant kernel (k_scan): algorithmic bytes = the text once + 32 B per record written
     peak, peak_src = measured_peak_hbm()
     alg_bytes = nbytes + 32 * res.n_records
@@ -705,7 +724,7 @@ def main():
                            "parallelism": "reads sharded over %d GPU(s); slice-edge window closed across ranks + one SUM and one MIN "
                                           "all-reduce of the per-site histogram per step" % world,
                            "calls_per_step": calls_per_step, "lines_per_step_per_gpu": res.counters["lines"],
-                           "records_per_step_per_gpu": res.n_records, "bed_loci": bed_loci, "chunks_redone": engine.redone - redone0,
+                           "records_per_step_per_gpu": res.n_records, "bed_loci": bed_loci, "single_gpu_same_workload": solo, "chunks_redone": engine.redone - redone0,
                            "binding": binding},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "parity_check": parity}

@@ -184,8 +184,8 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
  * holes); d_tile_tab[chunk] = {first record slot, count | flags} and d_run_tab[run] = {records of the run, flags} are consumed
  * by mc_order_records, which also drops the run-first records whose predecessor line turns out not to be a candidate.
- * Records leave this stage raw (MC_RF_RAW): line offset, position, contig, candidate flag and the target bits of the k-mer on
- * both strands; their values are parsed by mc_order_records at full lane occupancy.
+ * Records leave this stage raw (MC_RF_RAW): line offset, position, contig, candidate flag and -- parked in the fields that are
+ * still empty -- the first 128 field-start bits of the line; mc_order_records finishes them at full lane occupancy.
  * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
  * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
  * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
@@ -215,12 +215,13 @@ int64_t mc_workspace_bytes(int64_t n);
  * buffer (rec_in_cap = its capacity; slots are reserved in blocks, so it has holes); d_n_out[0] receives the number of
  * records, which land densely in d_rec_out (rec_out_cap slots; rec_in_cap is always enough).  Records arrive in raw form
  * (MC_RF_RAW) and are finished here, one thread per record: event index, the float64 np.round(event_mean - model_mean, 4)
- * from exact decimal parsing, the k-mer equality flag (extract_contexts.py:150, :169, :286) and the read-name span;
- * read-name changes between neighbouring records are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD).  d_scan_counters: the counter block mc_scan wrote
+ * from exact decimal parsing, the k-mer equality flag (extract_contexts.py:150, :169, :286), the read-name span and the
+ * target bits of the k-mer on both strands (kbits_fwd / kbits_rev, from `ref`); read-name changes between neighbouring
+ * records of a run are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD), the others are left to mc_segment_reads.  d_scan_counters: the counter block mc_scan wrote
  * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
  * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
-int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uint32_t *d_tile_tab, int64_t n_tiles, uint32_t *d_run_tab,
-                     int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
+int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
+                     uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
                      mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
 
 /*

@@ -283,3 +283,59 @@ __device__ __forceinline__ void mc_finish_record(const uint8_t *__restrict__ tex
     r.diff = diff;
     r.flags = (uint8_t)fl;
 }
+
+// Stage 1 parks the first 128 field-start bits of the recorded line (bit b: a column starts at line offset b) in the
+// raw record's event_idx / diff / name_off / name_len fields (pad bit 1: none).  With them the columns are located by
+// rank/select and only the bytes of the needed tokens are read: columns 3, 6, 7, 10, 11 and the end of the read name.
+// Falls back to the walk above when a needed column starts beyond the window or a token has an unusual shape.
+__device__ __forceinline__ int mc_nth_bit(uint32_t m, int j) {     // position of the j-th (0-based) set bit, j < popc(m)
+#pragma unroll
+    for (int t = 0; t < 6; ++t)
+        if (j > t) m &= m - 1u;
+    for (int t = 6; t < j; ++t) m &= m - 1u;
+    return __ffs(m) - 1;
+}
+__device__ __forceinline__ void mc_finish_record_win(const uint8_t *__restrict__ text, int64_t limit, mc_record &r) {
+    const uint32_t *rw = reinterpret_cast<const uint32_t *>(&r);
+    const uint32_t W0 = rw[3], W1 = rw[4], W2 = rw[5], W3 = (rw[1] >> 16) | (rw[6] << 16);
+    const int c0 = __popc(W0), c1 = c0 + __popc(W1), c2 = c1 + __popc(W2), c3 = c2 + __popc(W3);
+    const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
+    if ((r.pad & 2u) || c3 < 11 || line + 160 >= limit) {            // no window / column 11 beyond it: walk the line
+        r.pad = 0;
+        mc_finish_record(text, limit, r);
+        return;
+    }
+    auto sel = [&](int k) {                                          // line offset at which column k + 1 starts
+        const int wi = (k >= c0) + (k >= c1) + (k >= c2);
+        const uint32_t m = wi == 0 ? W0 : wi == 1 ? W1 : wi == 2 ? W2 : W3;
+        const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : c2;
+        return 32 * wi + mc_nth_bit(m, k - base);
+    };
+    const int f2 = sel(2), f3 = sel(3), f4 = sel(4), f5 = sel(5), f6 = sel(6), f9 = sel(9), f10 = sel(10);
+    const uint8_t *lp = text + line;
+    // end of the read name: the bytes before column 5 are whitespace; step back over them (one tab in nanopolish output)
+    int name_end = f4 - 1;
+    while (name_end > f3 && __ldg(lp + name_end - 1) <= 0x20) --name_end;
+    uint32_t fl = r.flags & ~MC_RF_RAW;
+    int ev_idx = 0;
+    double diff = 0.0;
+    uint32_t m_ev = 0u, m_md = 0u;
+    int n_ev = 0, n_md = 0;
+    const int teq = fast_tokens_equal8(load8_unaligned(lp + f2), load8_unaligned(lp + f9));
+    if (teq >= 0 && fast_uint8(load8_unaligned(lp + f5), ev_idx) && fast_decimal8(load8_unaligned(lp + f6), m_ev, n_ev) &&
+        fast_decimal8(load8_unaligned(lp + f10), m_md, n_md)) {
+        const double ev = __ddiv_rn((double)m_ev, c_pow10[n_ev]), md = __ddiv_rn((double)m_md, c_pow10[n_md]);
+        diff = __ddiv_rn(rint(__dmul_rn(__dsub_rn(ev, md), 1e4)), 1e4);
+        if (teq) fl |= MC_RF_EQ;
+    } else {
+        const GlobalBytes t{lp, limit - line};
+        ev_idx = 0;
+        parse_values(t, f2, f5, f6, f9, f10, ev_idx, diff, fl);
+    }
+    r.name_off = (uint16_t)f3;
+    r.name_len = (uint16_t)(name_end - f3);
+    r.event_idx = ev_idx;
+    r.diff = diff;
+    r.flags = (uint8_t)fl;
+    r.pad = 0;
+}

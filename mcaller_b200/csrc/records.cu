@@ -185,12 +185,18 @@ __global__ void __launch_bounds__(256) k_run_resolve(uint32_t *__restrict__ run_
     cnt_clean[r] = count;
 }
 
-__global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ run_tab,
-                                                    const uint32_t *__restrict__ run_dst, int64_t n_tiles, int64_t n_runs, int run_len,
-                                                    const mc_record *__restrict__ in, unsigned long long in_cap, mc_record *__restrict__ out,
-                                                    unsigned long long out_cap) {
-    // a warp owns a run; lane j looks at the run's j-th chunk (32 at a time), the warp then copies each non-empty chunk's
-    // records with one lane per 16-byte half record (coalesced 32-byte records, no per-thread copy loops)
+// A warp owns a run: it reads the run's chunk entries (lane j <-> j-th chunk, 32 at a time), prefix-sums their counts and
+// then takes the run's records 32 at a time, ONE LANE PER RECORD: the raw record is fetched from stage 1's buffer,
+// finished (mc_finish_record_win, parse.cuh: columns from the field-start bits stage 1 left in the record, event index,
+// np.round(event_mean - model_mean, 4), k-mer equality, read-name span), given the target bits of its k-mer on both
+// strands (meth_ref[pos:pos+k], extract_contexts.py:176) and the read-change flag against the record before it in the
+// run (MC_RF_NEWREAD: one shuffle, both lines still in L1), and written to its place in file order.  The first record of
+// a run leaves the flag to stage 3 (its predecessor belongs to another warp).
+__global__ void __launch_bounds__(256) k_gather_finish(const uint8_t *__restrict__ text, int64_t limit, mc_refindex R,
+                                                      const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ run_tab,
+                                                      const uint32_t *__restrict__ run_dst, int64_t n_tiles, int64_t n_runs, int run_len,
+                                                      const mc_record *__restrict__ in, unsigned long long in_cap, mc_record *__restrict__ out,
+                                                      unsigned long long out_cap) {
     const int lane = threadIdx.x & 31;
     const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (run >= n_runs) return;
@@ -199,6 +205,8 @@ __global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict_
     const bool drop = (rv >> 31) != 0u;
     unsigned long long d_run = __ldg(run_dst + run);
     const int64_t c0 = run * run_len, c1 = min(c0 + (int64_t)run_len, n_tiles);
+    long long carry_line = -1;                                   // line / name span of the last record written (-1: none yet)
+    uint32_t carry_span = 0u;
     for (int64_t cb = c0; cb < c1; cb += 32) {
         const int64_t c = cb + lane;
         unsigned long long src = 0ull;
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict_
             const uint2 e = __ldg(reinterpret_cast<const uint2 *>(tile_tab) + c);
             src = e.x;
             cnt = e.y & 0xFFFFu;
-            if (drop && ((e.y >> 16) & 1u) && cnt > 0u) { src += 1ull; --cnt; }
+            if (drop && ((e.y >> 16) & 1u) && cnt > 0u) { src += 1ull; --cnt; }     // the filler is the first record of its chunk
         }
         uint32_t incl = cnt;
 #pragma unroll
@@ -215,57 +223,68 @@ __global__ void __launch_bounds__(256) k_gather_runs(const uint32_t *__restrict_
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        const unsigned long long dst = d_run + (incl - cnt);
-        d_run += __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t busy = __ballot_sync(0xffffffffu, cnt != 0u);
-        while (busy) {
-            const int l = __ffs(busy) - 1;
-            busy &= busy - 1u;
-            const unsigned long long s0 = __shfl_sync(0xffffffffu, src, l), d0 = __shfl_sync(0xffffffffu, dst, l);
-            const uint32_t n = __shfl_sync(0xffffffffu, cnt, l);
-            for (uint32_t h = lane; h < 2u * n; h += 32u) {              // half records
-                const unsigned long long j = h >> 1;
-                if (s0 + j >= in_cap || d0 + j >= out_cap) continue;     // records dropped by a capacity overflow
-                reinterpret_cast<uint4 *>(out + d0 + j)[h & 1u] = __ldg(reinterpret_cast<const uint4 *>(in + s0 + j) + (h & 1u));
+        const uint32_t excl = incl - cnt, tot = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t k0 = 0; k0 < tot; k0 += 32) {
+            const uint32_t idx = k0 + lane;
+            const bool act = idx < tot;
+            // owning chunk: the last lane whose exclusive prefix is <= idx (empty chunks share the prefix of the next
+            // non-empty one and come before it, trailing ones have prefix == tot)
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                const int mid = (lo + hi + 1) >> 1;
+                const uint32_t e_mid = __shfl_sync(0xffffffffu, excl, mid);
+                if (e_mid <= idx) lo = mid; else hi = mid - 1;
             }
+            const unsigned long long s_own = __shfl_sync(0xffffffffu, src, lo);
+            const uint32_t e_own = __shfl_sync(0xffffffffu, excl, lo);
+            const unsigned long long slot = s_own + (idx - e_own), dst = d_run + idx;
+            const bool ok = act && slot < in_cap && dst < out_cap;     // else: dropped by a capacity overflow (redone by the host)
+            alignas(16) mc_record r;
+            long long line = -1;
+            uint32_t span = 0u;
+            if (ok) {
+                const uint4 *sp = reinterpret_cast<const uint4 *>(in + slot);
+                uint4 *dr = reinterpret_cast<uint4 *>(&r);
+                dr[0] = __ldg(sp);
+                dr[1] = __ldg(sp + 1);
+                if (r.flags & MC_RF_RAW) mc_finish_record_win(text, limit, r);
+                if (r.flags & MC_RF_CAND) {
+                    const int cid = r.contig;
+                    if (r.pos < __ldg(R.d_len + cid)) {
+                        const int64_t g = __ldg(R.d_base + cid) + r.pos;
+                        r.kbits_fwd = (uint8_t)mc_kmer_bits(R.d_site_fwd, g, R.k);
+                        r.kbits_rev = (uint8_t)mc_kmer_bits(R.d_site_rev, g, R.k);
+                    }
+                }
+                line = ((long long)r.line_hi << 32) | (long long)r.line_lo;
+                span = (uint32_t)r.name_off | ((uint32_t)r.name_len << 16);
+            }
+            // read name against the previous record of the run (same read <=> equal bytes, extract_contexts.py:161)
+            long long pl = __shfl_up_sync(0xffffffffu, line, 1);
+            uint32_t ps = __shfl_up_sync(0xffffffffu, span, 1);
+            if (lane == 0) { pl = carry_line; ps = carry_span; }
+            if (ok) {
+                if (pl >= 0) {
+                    uint32_t fl = r.flags | MC_RF_SEGKNOWN;
+                    if ((ps >> 16) != r.name_len || bytes_differ(text + pl + (ps & 0xFFFFu), text + line + r.name_off, r.name_len))
+                        fl |= MC_RF_NEWREAD;
+                    r.flags = (uint8_t)fl;
+                }
+                uint4 *dp = reinterpret_cast<uint4 *>(out + dst);
+                const uint4 *sr = reinterpret_cast<const uint4 *>(&r);
+                dp[0] = sr[0];
+                dp[1] = sr[1];
+            }
+            const int last = (int)min(tot - k0, 32u) - 1;
+            carry_line = __shfl_sync(0xffffffffu, line, last);
+            carry_span = __shfl_sync(0xffffffffu, span, last);
         }
+        d_run += tot;
     }
 }
 
 __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
-
-// Stage 1 leaves its records raw {line offset, position, contig, flags, k-mer target bits}; they are finished here at
-// full lane occupancy (mc_finish_record, parse.cuh: column walk, event index, np.round(event_mean - model_mean, 4), k-mer
-// equality, read-name span).  A warp finishes 31 records; lane 0 re-walks the record before them (the previous warp's
-// last) only to know its read-name span, so that every lane can compare its read name with its predecessor's, handed over
-// by one shuffle while both lines are still in L1.  That comparison is the read segmentation flag (MC_RF_NEWREAD).
-__global__ void __launch_bounds__(256) k_finish_records(const uint8_t *__restrict__ text, int64_t limit, mc_record *__restrict__ rec,
-                                                       const unsigned long long *__restrict__ d_n, int64_t rec_cap) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long i = warp * 31 + lane - 1;
-    const bool active = i >= 0 && i < dev_count(d_n, rec_cap);
-    alignas(16) mc_record r;
-    if (active) r = rec[i];
-    else { r.line_lo = 0u; r.line_hi = 0; r.name_off = 0; r.name_len = 0; r.flags = 0; r.pos = 0; r.contig = 0; r.event_idx = 0; r.diff = 0.0; }
-    // lane 0 always walks: the record's owner (previous warp) may be rewriting it right now, only its line offset is stable
-    const bool raw = active && (lane == 0 || (r.flags & MC_RF_RAW));
-    const int64_t line = ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo;
-    if (raw) mc_finish_record(text, limit, r);
-    // read segmentation: same read as the previous record <=> equal name length and bytes (extract_contexts.py:161, :179)
-    const unsigned long long prev_line = __shfl_up_sync(0xffffffffu, (unsigned long long)line, 1);
-    const uint32_t prev_span = __shfl_up_sync(0xffffffffu, (uint32_t)r.name_off | ((uint32_t)r.name_len << 16), 1);
-    if (!active || lane == 0) return;
-    uint32_t fl = r.flags | MC_RF_SEGKNOWN;
-    if (i == 0 || (prev_span >> 16) != r.name_len ||
-        bytes_differ(text + (int64_t)prev_line + (prev_span & 0xFFFFu), text + line + r.name_off, r.name_len))
-        fl |= MC_RF_NEWREAD;
-    r.flags = (uint8_t)fl;
-    uint4 *dst = reinterpret_cast<uint4 *>(rec + i);
-    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    if (raw) dst[0] = src[0];
-    dst[1] = src[1];
-}
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, mc_record *__restrict__ rec, int64_t n_cap,
@@ -336,10 +355,11 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 
 }  // namespace
 
-extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uint32_t *d_tile_tab, int64_t n_tiles, uint32_t *d_run_tab,
-                                int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
-                                mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream) {
-    MC_REQUIRE(d_text && d_tile_tab && d_run_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
+extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
+                                uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap,
+                                const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws,
+                                void *stream) {
+    MC_REQUIRE(d_text && ref && d_tile_tab && d_run_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     MC_REQUIRE(run_len >= 1, "run length must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles <= 0) {
@@ -353,13 +373,9 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const uin
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(cnt, dst, n_runs, d_n_out, ws_s(d_ws, n_runs), st);
     if (rc) return rc;
-    k_gather_runs<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_tile_tab, d_run_tab, dst, n_tiles, n_runs, run_len, d_rec_in,
-                                                                        (unsigned long long)rec_in_cap, d_rec_out, (unsigned long long)rec_out_cap);
-    MC_LAUNCH_CHECK();
-    // the record count lives on the device; the grid covers the output capacity and threads beyond the count exit
-    // 31 records per warp (see k_finish_records): 8 warps of a block cover 248 records
-    k_finish_records<<<(unsigned)((rec_out_cap + 247) / 248), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, d_rec_out,
-                                                                            reinterpret_cast<const unsigned long long *>(d_n_out), rec_out_cap);
+    k_gather_finish<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, *ref, d_tile_tab, d_run_tab, dst, n_tiles,
+                                                                          n_runs, run_len, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
+                                                                          (unsigned long long)rec_out_cap);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

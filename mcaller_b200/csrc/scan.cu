@@ -24,10 +24,12 @@
 //      finds columns 1, 2, 10 and 12 without touching the bytes in between (the ~58 B read name is never walked); 12-column
 //      check, contig lookup, NNNNNN test, position, candidate bit;
 //   4. warp ballots decide which lines matter (candidate, successor of a candidate, first kept line of the run, or
-//      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags, the k-mer's
-//      target bits on both strands}.  Their values (event index, currents, k-mer equality, read-name span) are parsed in
-//      stage 2 at full lane occupancy: finishing them here, from the staged bytes or in L2-hot batches, was measured at
-//      +3 ms and +10 ms on this kernel (long dependent chains in a warp that has a single chunk of prefetch in flight).
+//      every kept line in dense mode); those get a 32-byte raw record {line offset, position, contig, flags, the first 128
+//      field-start bits of the line}.  Their values (event index, currents, k-mer equality, read-name span, the k-mer's
+//      target bits) are filled in by stage 2 at full lane occupancy, which finds the columns from the field-start bits
+//      instead of walking the line again.  Finishing the records here -- from the staged bytes, or in L2-hot batches of 32 --
+//      was measured at +3 ms and +10 ms on this kernel: long dependent chains in a warp that has one chunk of prefetch
+//      in flight starve the memory pipeline.
 //      Record slots are reserved per warp in blocks of 256, so the global allocation counter sees ~1 atomic per 300 chunks.
 // Lines whose first 12 columns do not fit the look-ahead are classified byte-wise straight from global memory.
 // Algorithmic HBM traffic: the text itself (once) + 32 B per record (~1 B per line in sparse mode).
@@ -568,6 +570,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             }
             uint32_t status = 0u;
             int cid = -1, pos = 0, s = 0;
+            bool staged = false;       // first 12 columns inside the staged bytes (else: classified from global memory)
             if (lane < n_pass) {
                 s = S.lstart[lane];
                 const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : (e_last >= 0 ? e_last : next_bit(S.nl, s));
@@ -575,6 +578,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 int f0, f1, f9, f11;
                 line_fields(S, s, f0, f1, f9, f11);
                 if (f11 < e) {
+                    staged = true;
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
                     const unsigned long long k8 = load8(text, f0);
                     // names of up to 7 bytes compare in registers: the name bytes and the whitespace right after them
@@ -624,21 +628,31 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             if (emit) {
                 const unsigned long long slot = slot_cur + __popc(emit_m & lt_mask);
                 if (slot < rec_cap) {
-                    const int64_t goff = G0 + s;
-                    uint32_t fl = MC_RF_RAW;
-                    if (status & ST_CAND) {
-                        // the targets inside this line's k-mer on either strand (meth_ref[pos:pos+k], :176) travel with the record
-                        const int64_t g = ((cid == hint) ? hint_base : __ldg(R.d_base + cid)) + pos;
-                        fl |= MC_RF_CAND | (mc_kmer_bits(R.d_site_fwd, g, R.k) << 8) | (mc_kmer_bits(R.d_site_rev, g, R.k) << 16);
+                    // raw record: line offset, position, contig, candidate flag and -- so that stage 2 need not walk the line
+                    // again -- the first 128 field-start bits of the line (where its columns begin), parked in the fields
+                    // stage 2 fills in: event_idx, diff, name_off, name_len.  pad bit 1: no window (line classified from
+                    // global memory).
+                    uint32_t fl = MC_RF_RAW | ((status & ST_CAND) ? MC_RF_CAND : 0u);
+                    uint32_t W0 = 0u, W1 = 0u, W2 = 0u, W3 = 0u;
+                    if (staged) {
+                        const int w0 = s >> 5, sh = s & 31;
+                        const uint32_t a0 = S.fs[w0], a1 = S.fs[w0 + 1], a2 = S.fs[w0 + 2], a3 = S.fs[w0 + 3], a4 = S.fs[w0 + 4];
+                        W0 = __funnelshift_r(a0, a1, sh);
+                        W1 = __funnelshift_r(a1, a2, sh);
+                        W2 = __funnelshift_r(a2, a3, sh);
+                        W3 = __funnelshift_r(a3, a4, sh);
+                    } else {
+                        fl |= 2u << 24;
                     }
+                    const int64_t goff = G0 + s;
                     uint4 a, b;
-                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                   // line_lo
-                    a.y = (uint32_t)(goff >> 32) & 0xFFFFu;                  // line_hi | name_off (0)
-                    a.z = (uint32_t)pos;                                     // pos
-                    a.w = 0u;                                                // event_idx
-                    b.x = 0u; b.y = 0u;                                      // diff
-                    b.z = (uint32_t)cid << 16;                               // name_len (0) | contig
-                    b.w = fl;                                                // flags | kbits_fwd | kbits_rev | pad
+                    a.x = (uint32_t)(goff & 0xFFFFFFFFll);                              // line_lo
+                    a.y = ((uint32_t)(goff >> 32) & 0xFFFFu) | (W3 << 16);              // line_hi | window bits 96..111
+                    a.z = (uint32_t)pos;                                                // pos
+                    a.w = W0;                                                           // window bits 0..31
+                    b.x = W1; b.y = W2;                                                 // window bits 32..95
+                    b.z = (W3 >> 16) | ((uint32_t)cid << 16);                           // window bits 112..127 | contig
+                    b.w = fl;                                                           // flags | kbits (stage 2) | pad
                     uint4 *dst = reinterpret_cast<uint4 *>(d_rec + slot);
                     dst[0] = a;
                     dst[1] = b;

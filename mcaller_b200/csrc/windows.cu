@@ -21,19 +21,25 @@
 // one thread per unit through the literal state machine -- every per-record step is then a shared-memory read instead of
 // a dependent global load.  Two passes (count rows / write rows) so rows land in file order.
 //
-// Column values are not accumulated while the lines go by: the state machine only tags every fed record with the column
-// slot it went to and remembers where each slot's current contents begin.  When a window closes, the values of a column
-// are read back from the staged records in file order and summed exactly like numpy does (np.mean -> add.reduce:
-// sequential below 8 values, 8 running lanes + tail up to 128, recursive halving above), so the float64 column means are
-// reproduced bit for bit for ANY number of events per column; nothing lives in local memory.
+// Column sums follow numpy (np.mean -> add.reduce) bit for bit.  Below 8 values numpy adds left to right, which is an
+// online running sum: one float64 per column slot and thread in shared memory, updated as the lines go by (99 % of the
+// columns).  The state machine also tags every fed record with the column slot it went to; a column that reaches 8 values
+// (8 running lanes + tail up to 128, recursive halving above) is re-read from the staged records in file order when its
+// window closes, so ANY number of events per column is handled; nothing lives in local memory.
 #include "common.cuh"
 
 namespace {
 
 #ifndef MC_WIN_ITEMS
-#define MC_WIN_ITEMS 10
+#define MC_WIN_ITEMS 12
 #endif
-constexpr int WIN_THREADS = 256, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 2560 records per block
+#ifndef MC_WIN_THREADS
+#define MC_WIN_THREADS 128
+#endif
+#ifndef MC_WIN_BLOCKS
+#define MC_WIN_BLOCKS 4
+#endif
+constexpr int WIN_THREADS = MC_WIN_THREADS, WIN_ITEMS = MC_WIN_ITEMS, WIN_RECS = WIN_THREADS * WIN_ITEMS;   // 1536 records per block: ~115 units
 constexpr int WIN_UNITS = WIN_RECS / 2 + 2;       // a unit holds a candidate and is followed by a non-candidate: <= ceil(n/2) units
 static_assert(WIN_RECS < 65536, "unit / read counts of a block are packed in 16 bits");
 constexpr uint32_t TAG_NONE = 0xFu;               // record fed no column
@@ -48,11 +54,21 @@ __device__ __forceinline__ double stage_diff(const mc_record *p) {
     return __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
 }
 
-__device__ __forceinline__ int cnt_get(unsigned long long cnts, int c) { return (int)((cnts >> (8 * c)) & 0xFFull); }
-__device__ __forceinline__ void cnt_inc(unsigned long long &cnts, int c) {
-    if (cnt_get(cnts, c) < 255) cnts += 1ull << (8 * c);           // saturates: 255 means "255 or more", recounted when it matters
+// events per column slot: 8 x 16 bits in two registers (slots 0-3 / 4-7), saturating at 65535 (flagged as MC_CE_COLUMN)
+struct Counts {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ int cnt_get(const Counts &q, int c) { return (int)(((c < 4 ? q.lo : q.hi) >> (16 * (c & 3))) & 0xFFFFull); }
+__device__ __forceinline__ void cnt_inc(Counts &q, int c) {
+    if (cnt_get(q, c) < 65535) {
+        const unsigned long long one = 1ull << (16 * (c & 3));
+        if (c < 4) q.lo += one; else q.hi += one;
+    }
 }
-__device__ __forceinline__ void cnt_clear(unsigned long long &cnts, int c) { cnts &= ~(0xFFull << (8 * c)); }
+__device__ __forceinline__ void cnt_clear(Counts &q, int c) {
+    const unsigned long long m = ~(0xFFFFull << (16 * (c & 3)));
+    if (c < 4) q.lo &= m; else q.hi &= m;
+}
 __device__ __forceinline__ int map_get(uint32_t mp, int c) { return (int)((mp >> (4 * c)) & 0xFu); }
 
 __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64_t)r.line_hi << 32) | (int64_t)r.line_lo; }
@@ -125,8 +141,15 @@ __device__ __forceinline__ double cs_diff(const ColSrc &S, uint32_t i) {
 }
 // np.add.reduce of a column with 8 or more values (rare: P(8+ events on one position) < 1 %), kept out of line so the
 // common path stays small: 8 running lanes + sequential tail up to 128 values, recursive halving above
-__device__ __noinline__ double col_sum_big(const ColSrc S, uint32_t src, uint32_t f0, uint32_t upto, int n, Spill spill, uint32_t *err,
-                                           int *n_out) {
+__device__ __noinline__ double col_sum_big(const ColSrc S, uint32_t src, uint32_t unit_b, uint32_t upto, int n, Spill spill, uint32_t *err) {
+    // the column's current contents are the last n records before `upto` that carry its tag (older ones with the same tag
+    // belong to an earlier window whose column was cleared since)
+    uint32_t f0 = upto;
+    for (int need = n; need > 0 && f0 > unit_b;) {
+        --f0;
+        if (cs_tag(S, f0) == src) --need;
+    }
+    if (n >= 65535) { *err |= MC_CE_COLUMN; return 0.0; }          // counter saturated: the span is not known
     double res = 0.0;
     if (n <= 128) {
         double r[8];
@@ -147,14 +170,10 @@ __device__ __noinline__ double col_sum_big(const ColSrc S, uint32_t src, uint32_
         res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
         for (; j < upto; ++j)
             if (cs_tag(S, j) == src) res = __dadd_rn(res, cs_diff(S, j));
-        *n_out = n;
         return res;
     }
-    // more than 128 events in one column (a stalled read): the 8-bit counter saturates at 255, so recount; numpy halves
-    // recursively, which needs the values side by side -> gather them into the spill arena
-    n = 0;
-    for (uint32_t j = f0; j < upto; ++j) n += (cs_tag(S, j) == src);
-    *n_out = n;
+    // more than 128 events in one column (a stalled read): numpy halves recursively, which needs the values side by side
+    // -> gather them into the spill arena
     const unsigned long long at = atomicAdd(spill.cursor, (unsigned long long)n);
     if (at + (unsigned long long)n > spill.cap) { *err |= MC_CE_COLUMN; return 0.0; }
     double *a = spill.buf + at;
@@ -165,7 +184,7 @@ __device__ __noinline__ double col_sum_big(const ColSrc S, uint32_t src, uint32_
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(WIN_THREADS, 3)
+__global__ void __launch_bounds__(WIN_THREADS, MC_WIN_BLOCKS)
 k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned long long *__restrict__ d_n_records,
           const uint32_t *__restrict__ seg_start, int64_t seg_cap, const unsigned long long *__restrict__ d_nseg,
           const double *__restrict__ seg_qual, const uint32_t *__restrict__ first_idx, const int32_t *__restrict__ first_ind_arr,
@@ -177,9 +196,11 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     __shared__ uint16_t s_seg[WIN_UNITS];         // read segment of each unit, relative to the block's first record's
     __shared__ int s_warp[WIN_THREADS / 32 + 1];
     __shared__ int64_t s_seg0;
-    extern __shared__ __align__(16) uint4 s_dyn[];                // [WIN_RECS] staged records, then (write pass) [WIN_RECS] float64 deviations
+    // [WIN_RECS] staged records, then (write pass) [WIN_RECS] float64 deviations and [MC_MAXK][WIN_THREADS] running column sums
+    extern __shared__ __align__(16) uint4 s_dyn[];
     uint4 *s_rec = s_dyn;
     double *s_diff = reinterpret_cast<double *>(s_dyn + WIN_RECS);
+    double *s_seq = s_diff + WIN_RECS + threadIdx.x;              // this thread's slice: element [slot] at s_seq[slot * WIN_THREADS]
     const int k = R.k;
     // the record / segment counts live on the device; the grid was sized for rec_cap records
     const int64_t n_records = mc_dev_count(d_n_records, rec_cap), n_seg = mc_dev_count(d_nseg, seg_cap);
@@ -306,11 +327,8 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
     uint32_t out_pos = WRITE ? s_off[un] : 0u;
     const uint32_t fidx = __ldg(first_idx + seg);
 
-    unsigned long long cnts = 0ull;                // events per column slot
+    Counts cnts{0ull, 0ull};                       // events per column slot
     uint32_t mp = 0x76543210u;                     // window column -> column slot (the multi-M carry permutes it)
-    uint32_t fst[MC_MAXK];                         // record at which the current contents of each column slot begin
-#pragma unroll
-    for (int c = 0; c < MC_MAXK; ++c) fst[c] = b;
     bool started = b > fidx;     // read_name == last_read  (this read already had a line with 'M')
     bool has_mpos = false;
     int mpos = 0, first_ind = started ? __ldg(first_ind_arr + seg) : 0, last_rev = 0, last_cid = 0;
@@ -319,21 +337,15 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
 
 #define MPOS_TRUTHY (has_mpos && mpos != 0)
 
-    // np.mean of the values that column slot `src` holds when the window closes at record `upto` (exclusive): the records
-    // tagged with the slot since fst[src], in file order, summed like numpy's add.reduce
+    // np.mean of the values that column slot `src` holds when the window closes at record `upto` (exclusive), summed like
+    // numpy's add.reduce
     auto col_mean = [&](int src, uint32_t upto, uint32_t &err) -> double {
-        int n = cnt_get(cnts, src);
-        uint32_t f0 = b;
-#pragma unroll
-        for (int c = 0; c < MC_MAXK; ++c)
-            if (c == src) f0 = fst[c];
-        double res = 0.0;
-        if (n < 8) {
-            for (uint32_t j = f0; j < upto; ++j)
-                if (tag_get(j) == (uint32_t)src) res = __dadd_rn(res, rec_diff(j));
-        } else {
+        const int n = cnt_get(cnts, src);
+        double res;
+        if (n < 8) res = s_seq[src * WIN_THREADS];                 // numpy adds fewer than 8 values left to right: the running sum
+        else {
             const ColSrc S{s_rec, s_diff, rec, g_tag, base};
-            res = col_sum_big(S, (uint32_t)src, f0, upto, n, spill, &err, &n);
+            res = col_sum_big(S, (uint32_t)src, b, upto, n, spill, &err);
         }
         return __ddiv_rn(res, (double)n);
     };
@@ -432,7 +444,7 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
         }
         ++n_out;
     };
-    auto reset_cols = [&]() { cnts = 0ull; };
+    auto reset_cols = [&]() { cnts.lo = 0ull; cnts.hi = 0ull; };
 
     // The row-producing code (column means, divisions, context look-ups) is by far the heaviest path and a lane needs it
     // only once per ~20 records.  Run in rounds so the warp executes it together: each lane advances through its records
@@ -462,11 +474,10 @@ k_windows(const mc_record *__restrict__ rec, int64_t rec_cap, const unsigned lon
             if (r.z & MC_RF_BADNUM) sticky_err |= MC_CE_BADNUM;
             const int slot = map_get(mp, first_m);
             if (WRITE) {
-                if (cnt_get(cnts, slot) == 0) {
-#pragma unroll
-                    for (int c = 0; c < MC_MAXK; ++c)
-                        if (c == slot) fst[c] = i;
-                }
+                // running left-to-right sum of the column (numpy starts from 0.0, which also turns a leading -0.0 into 0.0)
+                const double v = rec_diff(i);
+                double *q = s_seq + slot * WIN_THREADS;
+                *q = __dadd_rn(cnt_get(cnts, slot) == 0 ? 0.0 : *q, v);
                 tag_set(i, (uint32_t)slot);
             }
             cnt_inc(cnts, slot);
@@ -605,7 +616,7 @@ extern "C" int mc_build_windows(const mc_record *d_rec, const uint64_t *d_n_reco
     uint32_t *first_idx = d_seg_count;                             // caller's seg_cap-sized scratch
     k_first_m<<<(unsigned)((seg_cap + 127) / 128), 128, 0, st>>>(d_rec, d_seg_start, seg_cap, ds, first_idx, first_ind);
     MC_LAUNCH_CHECK();
-    constexpr size_t rec_bytes = sizeof(uint4) * WIN_RECS, diff_bytes = sizeof(double) * WIN_RECS;
+    constexpr size_t rec_bytes = sizeof(uint4) * WIN_RECS, diff_bytes = sizeof(double) * (WIN_RECS + MC_MAXK * WIN_THREADS);
     MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes));
     MC_CUDA_CHECK(cudaFuncSetAttribute(k_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rec_bytes + diff_bytes)));
     k_windows<false><<<(unsigned)nb, WIN_THREADS, rec_bytes, st>>>(d_rec, rec_cap, dn, d_seg_start, seg_cap, ds, d_seg_qual, first_idx, first_ind,

@@ -254,7 +254,7 @@ class Engine(object):
         if self.scan_events is not None:
             e1.record()
             self.scan_events.append((e0, e1))
-        check(L.mc_order_records(V(d_text.data_ptr()), nbytes, V(tile_tab.data_ptr()), n_tiles, V(run_tab.data_ptr()), run_len, V(rec_a.data_ptr()), rec_cap,
+        check(L.mc_order_records(V(d_text.data_ptr()), nbytes, self.ref.ref(), V(tile_tab.data_ptr()), n_tiles, V(run_tab.data_ptr()), run_len, V(rec_a.data_ptr()), rec_cap,
                                  V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(ws.data_ptr()), st))
         check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()),
                                  self._status_ptr(S_NSEG), V(ws.data_ptr()), st))
@@ -270,9 +270,9 @@ class Engine(object):
         check(L.mc_carry_rows(V(calls.data_ptr()), self._status_ptr(S_NCALLS), V(rec_b.data_ptr()), self._status_ptr(S_NREC),
                               V(seg_start.data_ptr()), self._status_ptr(S_NSEG), V(seg_qual.data_ptr()), self.qual_thresh,
                               V(self.d_carry.data_ptr()), self._status_ptr(S_NROWS), self._status_ptr(S_ABORT), st))
-        # 1 scan + 6 order (run resolution, 3 scan kernels, gather, finish) + 5 segmentation + 1 quality
+        # 1 scan + 5 order (run resolution, 3 scan kernels, gather + finish) + 5 segmentation + 1 quality
         # + 7 windows (first-'M', 2 passes, 3 scan kernels, capacity check) + guard + carry
-        self.launches += 1 + 6 + 5 + 1 + 7 + 2
+        self.launches += 1 + 5 + 5 + 1 + 7 + 2
         if self.models is not None:
             cls_ws = self._buf("cls_ws", L.mc_classify_workspace_bytes(call_cap + 1))
             check(L.mc_classify(V(calls.data_ptr()), self._status_ptr(S_NROWS), call_cap + 1, self.models.array, V(cls_ws.data_ptr()), st))
