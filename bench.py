@@ -520,16 +520,21 @@ def main():
         return 0
 
     # ------------------------------------------------------------------------------------------------ our arm
-    scan_ms = []
+    scan_pairs = []
 
-    def step(record_scan=False):
-        """One pass over this rank's text: every stage of the chunk is queued back to back (one status read at the end),
-        then the slice-edge window is closed with the next rank's first kept line and the histograms are combined --
-        both consumed on the device, no host read."""
+    def step(record_scan=False, sync=True):
+        """One pass over this rank's text: every stage of the chunk is queued back to back, then the slice-edge window is
+        closed with the next rank's first kept line and the histograms are combined -- both consumed on the device, no host
+        read.  Warm-up steps read the chunk's status (buffer capacities are learned from it); timed steps do not read
+        anything back: K steps are K uninterrupted launch sequences, an overflow would raise the engine's sticky flag."""
         engine.reset_histogram(mdist.rank_row_base(rank))
         if record_scan:
             engine.scan_events = []
-        res = engine.run_chunk(d_text, nbytes)
+        res = None
+        if sync:
+            res = engine.run_chunk(d_text, nbytes)
+        else:
+            engine.launch_chunk(d_text, nbytes)
         if use_dist:
             mdist.close_and_reduce(engine, rank, fetch=False)
         else:
@@ -537,8 +542,7 @@ def main():
         if cfg["bed"]:
             engine.bed_select(BED_DEPTH, BED_THRESH)
         if record_scan and engine.scan_events:
-            torch.cuda.synchronize()
-            scan_ms.extend(a.elapsed_time(b) for a, b in engine.scan_events)
+            scan_pairs.extend(engine.scan_events)
             engine.scan_events = None
         return res
 
@@ -554,12 +558,15 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        res = step(record_scan=True)
+        step(record_scan=True, sync=False)
     ev1.record()
     torch.cuda.synchronize()
     if use_dist:
         dist.barrier()
+    if engine.overflowed():
+        raise RuntimeError("a timed step outgrew the buffers learned in the warm-up steps")
     elapsed_ms = ev0.elapsed_time(ev1)
+    scan_ms = [a.elapsed_time(b) for a, b in scan_pairs]
     launches = engine.launches - launches0
     clocks = sampler.summary()
     # calls of one step = mass of the (all-reduced) histogram + the rows keyed on the host (every step is the same pass)

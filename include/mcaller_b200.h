@@ -217,12 +217,15 @@ int64_t mc_workspace_bytes(int64_t n);
  * (MC_RF_RAW) and are finished here, one thread per record: event index, the float64 np.round(event_mean - model_mean, 4)
  * from exact decimal parsing, the k-mer equality flag (extract_contexts.py:150, :169, :286), the read-name span and the
  * target bits of the k-mer on both strands (kbits_fwd / kbits_rev, from `ref`); read-name changes between neighbouring
- * records of a run are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD), the others are left to mc_segment_reads.  d_scan_counters: the counter block mc_scan wrote
+ * records of a run are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD), the others are left to mc_segment_reads; d_seg_flags
+ * (optional) receives the same answer per ordered record as 0 / 1 / 2 = same read / new read / unknown, so that
+ * mc_segment_reads need not read the records again.  d_scan_counters: the counter block mc_scan wrote
  * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
  * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
 int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
                      uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
-                     mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws, void *stream);
+                     mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, uint32_t *d_seg_flags /* [rec_out_cap] or NULL */,
+                     void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the
@@ -233,7 +236,8 @@ int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *r
  * predecessor in the text and get MC_RF_SEGKNOWN / MC_RF_NEWREAD written back.
  */
 int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
-                     uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream);
+                     const uint32_t *d_seg_flags /* from mc_order_records, or NULL */, uint32_t *d_seg_start, uint64_t *d_nseg,
+                     void *d_ws, void *stream);
 
 /*
  * Stage 4 -- read quality per segment: read2qual[name] else read2qual[name.split(':')[0].split('_')[0]]
@@ -300,7 +304,7 @@ int mc_carry_rows(mc_call *d_rows, const uint64_t *d_ncalls, const mc_record *d_
  * chunk again without having synchronised in between. */
 int mc_chunk_guard(const uint64_t *d_counters, int64_t rec_cap, const uint64_t *d_n_records, int64_t rec_out_cap,
                    const uint64_t *d_nseg, int64_t seg_cap, const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort,
-                   void *stream);
+                   uint64_t *d_sticky /* may be NULL: set to 1 on overflow, never cleared here */, void *stream);
 int mc_carry_close(mc_carry *d_carry, int closing_contig, const int64_t *d_next_contigs, int from, int count, mc_call *d_row_out,
                    uint32_t *d_depth, uint32_t *d_meth, uint64_t *d_first, int64_t n_sites, uint64_t *d_row_base, void *stream);
 

@@ -88,11 +88,12 @@ _PROTOS = {
     "mc_num_tiles": (C.c_int64, [C.c_int64]),
     "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
     # d_text, nbytes, ref, d_tile_tab, n_tiles, d_run_tab, run_len, d_rec_in, rec_in_cap, d_scan_counters, d_rec_out, rec_out_cap,
-    # d_n_out, d_ws, stream
+    # d_n_out, d_seg_flags, d_ws, stream
     "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RefIndex), C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    # d_text, d_rec, d_n_records, rec_cap, d_seg_start, d_nseg, d_ws, stream
-    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # d_text, d_rec, d_n_records, rec_cap, d_seg_flags, d_seg_start, d_nseg, d_ws, stream
+    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     # d_text, d_rec, d_seg_start, d_nseg, seg_cap, d_table, table_size, d_seg_qual, d_err, stream
     "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
@@ -105,9 +106,9 @@ _PROTOS = {
     # d_rows, d_ncalls, d_rec, d_n_records, d_seg_start, d_nseg, d_seg_qual, qual_thresh, d_carry, d_nrows_out, d_abort, stream
     "mc_carry_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
-    # d_counters, rec_cap, d_n_records, rec_out_cap, d_nseg, seg_cap, d_ncalls, call_cap, d_abort, stream
+    # d_counters, rec_cap, d_n_records, rec_out_cap, d_nseg, seg_cap, d_ncalls, call_cap, d_abort, d_sticky, stream
     "mc_chunk_guard": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                 C.c_void_p]),
+                                 C.c_void_p, C.c_void_p]),
     # d_carry, closing_contig, d_next_contigs, from, count, d_row_out, d_depth, d_meth, d_first, n_sites, d_row_base, stream
     "mc_carry_close": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_void_p, C.c_void_p]),

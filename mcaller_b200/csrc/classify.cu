@@ -377,10 +377,11 @@ __global__ void k_chunk_guard(const unsigned long long *__restrict__ counters, u
                               const unsigned long long *__restrict__ d_n_records, unsigned long long rec_out_cap,
                               const unsigned long long *__restrict__ d_nseg, unsigned long long seg_cap,
                               const unsigned long long *__restrict__ d_ncalls, unsigned long long call_cap,
-                              unsigned long long *__restrict__ d_abort) {
+                              unsigned long long *__restrict__ d_abort, unsigned long long *__restrict__ d_sticky) {
     const bool bad = counters[MC_C_OVERFLOW] != 0ull || counters[MC_C_RECORDS] > rec_cap || *d_n_records > rec_out_cap ||
                      *d_nseg > seg_cap || d_ncalls[0] > call_cap || d_ncalls[1] != 0ull;
     *d_abort = bad ? 1ull : 0ull;
+    if (bad && d_sticky) *d_sticky = 1ull;                        // survives the next chunk's status reset (deferred status reads)
 }
 
 // row statistics without a D2H copy of the rows: [0] calls closed in this chunk, [1] calls still pending,
@@ -578,13 +579,13 @@ extern "C" int mc_bed_select(const uint32_t *d_depth, const uint32_t *d_meth, in
 
 extern "C" int mc_chunk_guard(const uint64_t *d_counters, int64_t rec_cap, const uint64_t *d_n_records, int64_t rec_out_cap,
                               const uint64_t *d_nseg, int64_t seg_cap, const uint64_t *d_ncalls, int64_t call_cap, uint64_t *d_abort,
-                              void *stream) {
+                              uint64_t *d_sticky, void *stream) {
     MC_REQUIRE(d_counters && d_n_records && d_nseg && d_ncalls && d_abort, "null pointer");
     k_chunk_guard<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(d_counters), (unsigned long long)rec_cap,
                                                     reinterpret_cast<const unsigned long long *>(d_n_records), (unsigned long long)rec_out_cap,
                                                     reinterpret_cast<const unsigned long long *>(d_nseg), (unsigned long long)seg_cap,
                                                     reinterpret_cast<const unsigned long long *>(d_ncalls), (unsigned long long)call_cap,
-                                                    reinterpret_cast<unsigned long long *>(d_abort));
+                                                    reinterpret_cast<unsigned long long *>(d_abort), reinterpret_cast<unsigned long long *>(d_sticky));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

@@ -305,13 +305,25 @@ __device__ __forceinline__ void mc_finish_record_win(const uint8_t *__restrict__
         mc_finish_record(text, limit, r);
         return;
     }
-    auto sel = [&](int k) {                                          // line offset at which column k + 1 starts
-        const int wi = (k >= c0) + (k >= c1) + (k >= c2);
-        const uint32_t m = wi == 0 ? W0 : wi == 1 ? W1 : wi == 2 ? W2 : W3;
-        const int base = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c1 : c2;
-        return 32 * wi + mc_nth_bit(m, k - base);
+    // columns start where the window has a set bit; they are needed in order, so walk the bits once: lowest set bit, clear
+    // it, move to the next word when the current one is used up
+    uint32_t m = W0;
+    int wi = 0;
+    auto next = [&]() {
+        while (m == 0u && wi < 3) {
+            ++wi;
+            m = wi == 1 ? W1 : wi == 2 ? W2 : W3;
+        }
+        const int q = 32 * wi + __ffs(m) - 1;
+        m &= m - 1u;
+        return q;
     };
-    const int f2 = sel(2), f3 = sel(3), f4 = sel(4), f5 = sel(5), f6 = sel(6), f9 = sel(9), f10 = sel(10);
+    next();                                                          // column 1 (contig)
+    next();                                                          // column 2 (position)
+    const int f2 = next(), f3 = next(), f4 = next(), f5 = next(), f6 = next();
+    next();                                                          // column 8 (event_stdv)
+    next();                                                          // column 9 (event_length)
+    const int f9 = next(), f10 = next();
     const uint8_t *lp = text + line;
     // end of the read name: the bytes before column 5 are whitespace; step back over them (one tab in nanopolish output)
     int name_end = f4 - 1;

@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(256) k_run_resolve(uint32_t *__restrict__ run_
 // strands (meth_ref[pos:pos+k], extract_contexts.py:176) and the read-change flag against the record before it in the
 // run (MC_RF_NEWREAD: one shuffle, both lines still in L1), and written to its place in file order.  The first record of
 // a run leaves the flag to stage 3 (its predecessor belongs to another warp).
-__global__ void __launch_bounds__(256) k_gather_finish(const uint8_t *__restrict__ text, int64_t limit, mc_refindex R,
+__global__ void __launch_bounds__(256, 4) k_gather_finish(const uint8_t *__restrict__ text, int64_t limit, mc_refindex R,
                                                       const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ run_tab,
                                                       const uint32_t *__restrict__ run_dst, int64_t n_tiles, int64_t n_runs, int run_len,
                                                       const mc_record *__restrict__ in, unsigned long long in_cap, mc_record *__restrict__ out,
-                                                      unsigned long long out_cap) {
+                                                      unsigned long long out_cap, uint32_t *__restrict__ seg_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (run >= n_runs) return;
@@ -265,12 +265,17 @@ __global__ void __launch_bounds__(256) k_gather_finish(const uint8_t *__restrict
             uint32_t ps = __shfl_up_sync(0xffffffffu, span, 1);
             if (lane == 0) { pl = carry_line; ps = carry_span; }
             if (ok) {
+                uint32_t sf = 2u;                                      // read-change flag for stage 3: 0 same read, 1 new read, 2 unknown
                 if (pl >= 0) {
                     uint32_t fl = r.flags | MC_RF_SEGKNOWN;
-                    if ((ps >> 16) != r.name_len || bytes_differ(text + pl + (ps & 0xFFFFu), text + line + r.name_off, r.name_len))
+                    sf = 0u;
+                    if ((ps >> 16) != r.name_len || bytes_differ(text + pl + (ps & 0xFFFFu), text + line + r.name_off, r.name_len)) {
                         fl |= MC_RF_NEWREAD;
+                        sf = 1u;
+                    }
                     r.flags = (uint8_t)fl;
                 }
+                if (seg_flags) seg_flags[dst] = sf;
                 uint4 *dp = reinterpret_cast<uint4 *>(out + dst);
                 const uint4 *sr = reinterpret_cast<const uint4 *>(&r);
                 dp[0] = sr[0];
@@ -288,10 +293,15 @@ __device__ __forceinline__ int64_t rec_line(const mc_record &r) { return ((int64
 
 // ---- stage 3: read segmentation ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ text, mc_record *__restrict__ rec, int64_t n_cap,
-                                                  const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ flags) {
+                                                  const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ flags,
+                                                  const uint32_t *__restrict__ known) {
     const int64_t n = dev_count(d_n, n_cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (known) {                                                  // stage 2 left the answer for all but the first record of a run
+        const uint32_t kf = known[i];
+        if (kf < 2u) { flags[i] = kf; return; }
+    }
     uint32_t f = 1u;
     const mc_record b = rec[i];
     if (b.flags & MC_RF_SEGKNOWN) {
@@ -357,8 +367,8 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 
 extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
                                 uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap,
-                                const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, void *d_ws,
-                                void *stream) {
+                                const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out,
+                                uint32_t *d_seg_flags, void *d_ws, void *stream) {
     MC_REQUIRE(d_text && ref && d_tile_tab && d_run_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     MC_REQUIRE(run_len >= 1, "run length must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
@@ -375,13 +385,13 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_
     if (rc) return rc;
     k_gather_finish<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, *ref, d_tile_tab, d_run_tab, dst, n_tiles,
                                                                           n_runs, run_len, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
-                                                                          (unsigned long long)rec_out_cap);
+                                                                          (unsigned long long)rec_out_cap, d_seg_flags);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
 extern "C" int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
-                                uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream) {
+                                const uint32_t *d_seg_flags, uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream) {
     MC_REQUIRE(d_text && d_rec && d_n_records && d_seg_start && d_nseg && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (rec_cap <= 0) {
@@ -392,7 +402,7 @@ extern "C" int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const u
     uint32_t *flags = ws_a(d_ws), *excl = ws_b(d_ws, rec_cap);
     const unsigned nb = (unsigned)((rec_cap + 255) / 256);
     const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n_records);
-    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, rec_cap, dn, flags);
+    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, rec_cap, dn, flags, d_seg_flags);
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32_dev(flags, excl, rec_cap, d_n_records, d_nseg, ws_s(d_ws, rec_cap), st);
     if (rc) return rc;

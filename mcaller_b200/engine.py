@@ -24,7 +24,7 @@ S_NSEG, S_MISSING_QUAL, S_NCALLS, S_CALL_OVERFLOW, S_ABORT, S_NREC, S_NROWS = 16
 S_STATS = 24                # 7 row statistics of mc_count_calls
 S_WORDS = 32
 # persistent device state (uint64 slots): global row index of the next chunk's slot 0, rows in the odd-row list
-P_ROW_BASE, P_N_ODD = 0, 1
+P_ROW_BASE, P_N_ODD, P_POISON = 0, 1, 2
 SPILL_CAP = 1 << 22         # doubles: values of columns with more than 128 events (a stalled read) while numpy's halving is replayed
 ODD_CAP = 1 << 16           # rows whose closing contig differs from their window's (reference quirk Q4); merged on the host
 
@@ -134,7 +134,7 @@ class Engine(object):
     def reset_stream_state(self, row_base=0):
         """Start of a byte range / file: no window carried in, first-seen row numbering restarts at row_base."""
         check(self.L.mc_carry_reset(C.c_void_p(self.d_carry.data_ptr()), self._sptr()))
-        self.d_persist.zero_()
+        self.d_persist[:2].zero_()                # row base, odd-row count (the sticky overflow flag stays)
         if row_base:
             self.d_persist[P_ROW_BASE] = int(row_base)
         self.launches += 1
@@ -178,6 +178,21 @@ class Engine(object):
         slack = 256 * min(n_tiles, 8192) + 4096
         return (nbytes // 24 + slack) if self.dense else (nbytes // 1024 + 2 * n_tiles + slack)
 
+    def _caps(self, nbytes, n_tiles):
+        """Capacities only size launches and buffers: heuristics for the first chunk, afterwards what the chunks so far needed
+        per byte of text (+25 %); a chunk that outgrows them is run again (mc_chunk_guard)."""
+        slack = 256 * min(n_tiles, 8192) + 4096
+        if self.rec_per_byte:
+            rec_cap = int(self.rec_per_byte * nbytes * 1.25) + slack
+            call_cap = int(self.call_per_byte * nbytes * 1.25) + 1024
+            seg_cap = int(self.seg_per_byte * nbytes * 1.5) + 1024
+        else:
+            rec_cap = self._default_rec_cap(nbytes, n_tiles)
+            call_cap = rec_cap // 8 + 1024
+            seg_cap = rec_cap
+        rec_cap = int(min(max(rec_cap, 1), 2 ** 32 - 2))
+        return rec_cap, int(max(call_cap, 1)), int(min(max(seg_cap, 1), rec_cap))
+
     def run_chunk(self, d_text, nbytes, rec_cap=None, call_cap=None):
         """d_text: uint8 device tensor, >= padded_capacity(nbytes) long, bytes past nbytes all '\\n'."""
         L = self.L
@@ -187,16 +202,13 @@ class Engine(object):
         res.nbytes = nbytes
         n_tiles = int(L.mc_num_tiles(nbytes))
         slack = 256 * min(n_tiles, 8192) + 4096
-        # capacities only size launches and buffers: heuristics for the first chunk, afterwards what the chunks so far needed
-        # per byte of text (+25 %); a chunk that outgrows them is run again (mc_chunk_guard)
-        if rec_cap is None:
-            rec_cap = (int(self.rec_per_byte * nbytes * 1.25) + slack) if self.rec_per_byte else self._default_rec_cap(nbytes, n_tiles)
-        if call_cap is None:
-            call_cap = (int(self.call_per_byte * nbytes * 1.25) + 1024) if self.rec_per_byte else rec_cap // 8 + 1024
-        seg_cap = (int(self.seg_per_byte * nbytes * 1.5) + 1024) if self.rec_per_byte else rec_cap
-        rec_cap = int(min(max(rec_cap, 1), 2 ** 32 - 2))
-        call_cap = int(max(call_cap, 1))
-        seg_cap = int(min(max(seg_cap, 1), rec_cap))
+        if rec_cap is None and call_cap is None:
+            rec_cap, call_cap, seg_cap = self._caps(nbytes, n_tiles)
+        else:
+            d_rec, d_call, d_seg = self._caps(nbytes, n_tiles)
+            rec_cap = int(min(max(rec_cap if rec_cap is not None else d_rec, 1), 2 ** 32 - 2))
+            call_cap = int(max(call_cap if call_cap is not None else d_call, 1))
+            seg_cap = int(min(d_seg, rec_cap))
         attempts = 0
         while True:
             cnt = self._launch_chunk(d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap)
@@ -231,7 +243,7 @@ class Engine(object):
                          pending_too_many_skips=int(v[6]))
         return res
 
-    def _launch_chunk(self, d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap):
+    def _launch_chunk(self, d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap, read_status=True):
         """All stages of one chunk, back to back on the current stream; one status read at the end."""
         L, st = self.L, self._sptr()
         V = C.c_void_p
@@ -242,6 +254,7 @@ class Engine(object):
         rec_b = self._buf("rec_b", 32 * rec_cap)
         ws = self._buf("ws", L.mc_workspace_bytes(max(rec_cap, n_tiles)))
         seg_start = self._buf("seg_start", 4 * (rec_cap + 2))
+        seg_flags = self._buf("seg_flags", 4 * rec_cap)
         seg_qual = self._buf("seg_qual", 8 * seg_cap)
         seg_count = self._buf("seg_count", 4 * seg_cap)
         calls = self._buf("calls", CALL_DTYPE.itemsize * (call_cap + 1))          # slot 0 + the chunk's rows
@@ -255,8 +268,9 @@ class Engine(object):
             e1.record()
             self.scan_events.append((e0, e1))
         check(L.mc_order_records(V(d_text.data_ptr()), nbytes, self.ref.ref(), V(tile_tab.data_ptr()), n_tiles, V(run_tab.data_ptr()), run_len, V(rec_a.data_ptr()), rec_cap,
-                                 V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(ws.data_ptr()), st))
-        check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_start.data_ptr()),
+                                 V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(seg_flags.data_ptr()),
+                                 V(ws.data_ptr()), st))
+        check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_flags.data_ptr()), V(seg_start.data_ptr()),
                                  self._status_ptr(S_NSEG), V(ws.data_ptr()), st))
         check(L.mc_segment_quality(V(d_text.data_ptr()), V(rec_b.data_ptr()), V(seg_start.data_ptr()), self._status_ptr(S_NSEG), seg_cap,
                                    V(self.d_qual.data_ptr()), self.qual_table_size, V(seg_qual.data_ptr()), self._status_ptr(S_MISSING_QUAL), st))
@@ -266,7 +280,7 @@ class Engine(object):
                                  rows1, call_cap, V(seg_count.data_ptr()), self._status_ptr(S_NCALLS), V(ws.data_ptr()),
                                  V(self.d_spill.data_ptr()), SPILL_CAP, st))
         check(L.mc_chunk_guard(V(self.d_small.data_ptr()), rec_cap, self._status_ptr(S_NREC), rec_cap, self._status_ptr(S_NSEG), seg_cap,
-                               self._status_ptr(S_NCALLS), call_cap, self._status_ptr(S_ABORT), st))
+                               self._status_ptr(S_NCALLS), call_cap, self._status_ptr(S_ABORT), self._persist_ptr(P_POISON), st))
         check(L.mc_carry_rows(V(calls.data_ptr()), self._status_ptr(S_NCALLS), V(rec_b.data_ptr()), self._status_ptr(S_NREC),
                               V(seg_start.data_ptr()), self._status_ptr(S_NSEG), V(seg_qual.data_ptr()), self.qual_thresh,
                               V(self.d_carry.data_ptr()), self._status_ptr(S_NROWS), self._status_ptr(S_ABORT), st))
@@ -284,7 +298,26 @@ class Engine(object):
                 self.launches += 2
         check(L.mc_count_calls(V(calls.data_ptr()), self._status_ptr(S_NROWS), call_cap + 1, self._status_ptr(S_STATS), st))
         self.launches += 1
+        if not read_status:
+            return None
         return self._read_status().copy()
+
+    def launch_chunk(self, d_text, nbytes):
+        """Queues every stage of a chunk WITHOUT reading its status: for back-to-back passes over inputs whose buffer needs are
+        already known (a repeated benchmark step).  Capacities come from the chunks seen so far; should one overflow anyway
+        the device keeps a sticky flag (`overflowed()`) and leaves all cross-chunk state untouched for that chunk."""
+        if not self.rec_per_byte:
+            raise _lib.McallerCudaError("launch_chunk needs a preceding run_chunk (capacities are learned from it)")
+        n_tiles = int(self.L.mc_num_tiles(nbytes))
+        rec_cap, call_cap, seg_cap = self._caps(nbytes, n_tiles)
+        self._launch_chunk(d_text, nbytes, n_tiles, rec_cap, call_cap, seg_cap, read_status=False)
+
+    def overflowed(self, clear=True):
+        """Did any chunk since the last check outgrow its buffers (8-byte D2H, synchronises)?"""
+        v = int(self.d_persist[P_POISON].item())
+        if clear and v:
+            self.d_persist[P_POISON] = 0
+        return bool(v)
 
     def count_rows(self, res):
         """Row statistics of a chunk (computed on the device as part of run_chunk)."""
