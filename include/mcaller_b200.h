@@ -217,15 +217,16 @@ int64_t mc_workspace_bytes(int64_t n);
  * (MC_RF_RAW) and are finished here, one thread per record: event index, the float64 np.round(event_mean - model_mean, 4)
  * from exact decimal parsing, the k-mer equality flag (extract_contexts.py:150, :169, :286), the read-name span and the
  * target bits of the k-mer on both strands (kbits_fwd / kbits_rev, from `ref`); read-name changes between neighbouring
- * records of a run are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD), the others are left to mc_segment_reads; d_seg_flags
- * (optional) receives the same answer per ordered record as 0 / 1 / 2 = same read / new read / unknown, so that
- * mc_segment_reads need not read the records again.  d_scan_counters: the counter block mc_scan wrote
+ * records of a run are flagged (MC_RF_SEGKNOWN / MC_RF_NEWREAD), the first record of a run is left to mc_segment_reads.
+ * d_seg_flags / d_run_first (optional, together): the read-change flag of every ordered record as 0 / 1 (placeholder 1 for the
+ * first record of a run) and, per run, the ordered index of its first record (0xFFFFFFFF: none) -- with them
+ * mc_segment_reads only has to look at one record per run.  d_scan_counters: the counter block mc_scan wrote
  * (may be NULL); when it shows that stage 1 ran out of record slots nothing is ordered and d_n_out[0] = 0, so every later
  * stage of the chunk is a no-op until the caller has grown the buffer and scanned again. */
 int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
                      uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap, const uint64_t *d_scan_counters,
                      mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out, uint32_t *d_seg_flags /* [rec_out_cap] or NULL */,
-                     void *d_ws, void *stream);
+                     uint32_t *d_run_first /* [n_runs] or NULL */, void *d_ws, void *stream);
 
 /*
  * Stage 3 -- read segmentation: a new segment starts where the read name (column 4) differs from the
@@ -236,8 +237,8 @@ int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *r
  * predecessor in the text and get MC_RF_SEGKNOWN / MC_RF_NEWREAD written back.
  */
 int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
-                     const uint32_t *d_seg_flags /* from mc_order_records, or NULL */, uint32_t *d_seg_start, uint64_t *d_nseg,
-                     void *d_ws, void *stream);
+                     uint32_t *d_seg_flags /* from mc_order_records, or NULL */, const uint32_t *d_run_first, int64_t n_runs,
+                     uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream);
 
 /*
  * Stage 4 -- read quality per segment: read2qual[name] else read2qual[name.split(':')[0].split('_')[0]]

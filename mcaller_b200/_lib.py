@@ -88,12 +88,12 @@ _PROTOS = {
     "mc_num_tiles": (C.c_int64, [C.c_int64]),
     "mc_workspace_bytes": (C.c_int64, [C.c_int64]),
     # d_text, nbytes, ref, d_tile_tab, n_tiles, d_run_tab, run_len, d_rec_in, rec_in_cap, d_scan_counters, d_rec_out, rec_out_cap,
-    # d_n_out, d_seg_flags, d_ws, stream
+    # d_n_out, d_seg_flags, d_run_first, d_ws, stream
     "mc_order_records": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RefIndex), C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    # d_text, d_rec, d_n_records, rec_cap, d_seg_flags, d_seg_start, d_nseg, d_ws, stream
-    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p]),
+                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # d_text, d_rec, d_n_records, rec_cap, d_seg_flags, d_run_first, n_runs, d_seg_start, d_nseg, d_ws, stream
+    "mc_segment_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
     # d_text, d_rec, d_seg_start, d_nseg, seg_cap, d_table, table_size, d_seg_qual, d_err, stream
     "mc_segment_quality": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),

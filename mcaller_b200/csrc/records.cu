@@ -196,11 +196,14 @@ __global__ void __launch_bounds__(256, 4) k_gather_finish(const uint8_t *__restr
                                                       const uint32_t *__restrict__ tile_tab, const uint32_t *__restrict__ run_tab,
                                                       const uint32_t *__restrict__ run_dst, int64_t n_tiles, int64_t n_runs, int run_len,
                                                       const mc_record *__restrict__ in, unsigned long long in_cap, mc_record *__restrict__ out,
-                                                      unsigned long long out_cap, uint32_t *__restrict__ seg_flags) {
+                                                      unsigned long long out_cap, uint32_t *__restrict__ seg_flags,
+                                                      uint32_t *__restrict__ run_first) {
     const int lane = threadIdx.x & 31;
     const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (run >= n_runs) return;
     const uint32_t rv = __ldg(run_tab + 2 * run + 1);
+    const bool empty_run = __ldg(run_dst + run) == __ldg(run_dst + run + 1);       // after the filler drop
+    if (run_first && lane == 0) run_first[run] = empty_run ? 0xFFFFFFFFu : __ldg(run_dst + run);
     if (__ldg(run_tab + 2 * run) == 0u) return;                  // nothing recorded in this run
     const bool drop = (rv >> 31) != 0u;
     unsigned long long d_run = __ldg(run_dst + run);
@@ -265,7 +268,8 @@ __global__ void __launch_bounds__(256, 4) k_gather_finish(const uint8_t *__restr
             uint32_t ps = __shfl_up_sync(0xffffffffu, span, 1);
             if (lane == 0) { pl = carry_line; ps = carry_span; }
             if (ok) {
-                uint32_t sf = 2u;                                      // read-change flag for stage 3: 0 same read, 1 new read, 2 unknown
+                uint32_t sf = 1u;                                      // read-change flag for stage 3 (the first record of a run is
+                                                                       // listed in run_first and decided there)
                 if (pl >= 0) {
                     uint32_t fl = r.flags | MC_RF_SEGKNOWN;
                     sf = 0u;
@@ -320,6 +324,25 @@ __global__ void __launch_bounds__(256) k_seg_flags(const uint8_t *__restrict__ t
     flags[i] = f;
 }
 
+// With the flags of stage 2: only the first record of every run is still undecided (its predecessor was finished by
+// another warp); one thread per run compares the two read names in the text and settles flag and record.
+__global__ void __launch_bounds__(256) k_seg_fix(const uint8_t *__restrict__ text, mc_record *__restrict__ rec, const unsigned long long *__restrict__ d_n,
+                                                int64_t n_cap, const uint32_t *__restrict__ run_first, int64_t n_runs, uint32_t *__restrict__ flags) {
+    const int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (run >= n_runs) return;
+    const uint32_t i = run_first[run];
+    if (i == 0xFFFFFFFFu || (int64_t)i >= dev_count(d_n, n_cap)) return;
+    uint32_t f = 1u;
+    const mc_record b = rec[i];
+    if (i > 0u) {
+        const mc_record a = rec[i - 1];
+        if (a.name_len == b.name_len)
+            f = bytes_differ(text + rec_line(a) + a.name_off, text + rec_line(b) + b.name_off, a.name_len) ? 1u : 0u;
+    }
+    rec[i].flags = (uint8_t)(b.flags | MC_RF_SEGKNOWN | (f ? MC_RF_NEWREAD : 0u));
+    flags[i] = f;
+}
+
 __global__ void __launch_bounds__(256) k_seg_starts(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ excl, int64_t n_cap,
                                                    const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ seg_start,
                                                    const unsigned long long *__restrict__ d_nseg) {
@@ -368,7 +391,8 @@ __global__ void __launch_bounds__(256) k_seg_quality(const uint8_t *__restrict__
 extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, const uint32_t *d_tile_tab, int64_t n_tiles,
                                 uint32_t *d_run_tab, int run_len, const mc_record *d_rec_in, int64_t rec_in_cap,
                                 const uint64_t *d_scan_counters, mc_record *d_rec_out, int64_t rec_out_cap, uint64_t *d_n_out,
-                                uint32_t *d_seg_flags, void *d_ws, void *stream) {
+                                uint32_t *d_seg_flags, uint32_t *d_run_first, void *d_ws, void *stream) {
+    MC_REQUIRE(!d_seg_flags == !d_run_first, "d_seg_flags and d_run_first go together");
     MC_REQUIRE(d_text && ref && d_tile_tab && d_run_tab && d_rec_in && d_rec_out && d_n_out && d_ws, "null pointer");
     MC_REQUIRE(run_len >= 1, "run length must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
@@ -377,21 +401,23 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_
         return MC_OK;
     }
     const int64_t n_runs = (n_tiles + run_len - 1) / run_len;
-    uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_runs);
+    uint32_t *cnt = ws_a(d_ws), *dst = ws_b(d_ws, n_runs + 1);
+    MC_CUDA_CHECK(cudaMemsetAsync(cnt + n_runs, 0, 4, st));
     k_run_resolve<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(d_run_tab, n_runs, cnt, reinterpret_cast<const unsigned long long *>(d_scan_counters),
                                                                    (unsigned long long)rec_in_cap);
     MC_LAUNCH_CHECK();
-    int rc = mc_exscan_u32(cnt, dst, n_runs, d_n_out, ws_s(d_ws, n_runs), st);
+    int rc = mc_exscan_u32(cnt, dst, n_runs + 1, d_n_out, ws_s(d_ws, n_runs + 1), st);     // entry n_runs (count 0) = the total
     if (rc) return rc;
     k_gather_finish<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, *ref, d_tile_tab, d_run_tab, dst, n_tiles,
                                                                           n_runs, run_len, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
-                                                                          (unsigned long long)rec_out_cap, d_seg_flags);
+                                                                          (unsigned long long)rec_out_cap, d_seg_flags, d_run_first);
     MC_LAUNCH_CHECK();
     return MC_OK;
 }
 
 extern "C" int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const uint64_t *d_n_records, int64_t rec_cap,
-                                const uint32_t *d_seg_flags, uint32_t *d_seg_start, uint64_t *d_nseg, void *d_ws, void *stream) {
+                                uint32_t *d_seg_flags, const uint32_t *d_run_first, int64_t n_runs, uint32_t *d_seg_start, uint64_t *d_nseg,
+                                void *d_ws, void *stream) {
     MC_REQUIRE(d_text && d_rec && d_n_records && d_seg_start && d_nseg && d_ws, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (rec_cap <= 0) {
@@ -402,7 +428,13 @@ extern "C" int mc_segment_reads(const uint8_t *d_text, mc_record *d_rec, const u
     uint32_t *flags = ws_a(d_ws), *excl = ws_b(d_ws, rec_cap);
     const unsigned nb = (unsigned)((rec_cap + 255) / 256);
     const unsigned long long *dn = reinterpret_cast<const unsigned long long *>(d_n_records);
-    k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, rec_cap, dn, flags, d_seg_flags);
+    if (d_seg_flags && d_run_first) {
+        // stage 2 decided every record but the first of each run: settle those, the flag array is then complete
+        flags = d_seg_flags;
+        if (n_runs > 0) k_seg_fix<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(d_text, d_rec, dn, rec_cap, d_run_first, n_runs, flags);
+    } else {
+        k_seg_flags<<<nb, 256, 0, st>>>(d_text, d_rec, rec_cap, dn, flags, nullptr);
+    }
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32_dev(flags, excl, rec_cap, d_n_records, d_nseg, ws_s(d_ws, rec_cap), st);
     if (rc) return rc;

@@ -249,7 +249,9 @@ class Engine(object):
         V = C.c_void_p
         tile_tab = self._buf("tile_tab", 8 * max(n_tiles, 1))
         run_len = max(int(L.mc_scan_run_len(nbytes)), 1)
-        run_tab = self._buf("run_tab", 8 * max((n_tiles + run_len - 1) // run_len, 1))
+        n_runs = max((n_tiles + run_len - 1) // run_len, 1)
+        run_tab = self._buf("run_tab", 8 * n_runs)
+        run_first = self._buf("run_first", 4 * n_runs)
         rec_a = self._buf("rec_a", 32 * rec_cap)
         rec_b = self._buf("rec_b", 32 * rec_cap)
         ws = self._buf("ws", L.mc_workspace_bytes(max(rec_cap, n_tiles)))
@@ -269,8 +271,9 @@ class Engine(object):
             self.scan_events.append((e0, e1))
         check(L.mc_order_records(V(d_text.data_ptr()), nbytes, self.ref.ref(), V(tile_tab.data_ptr()), n_tiles, V(run_tab.data_ptr()), run_len, V(rec_a.data_ptr()), rec_cap,
                                  V(self.d_small.data_ptr()), V(rec_b.data_ptr()), rec_cap, self._status_ptr(S_NREC), V(seg_flags.data_ptr()),
-                                 V(ws.data_ptr()), st))
-        check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_flags.data_ptr()), V(seg_start.data_ptr()),
+                                 V(run_first.data_ptr()), V(ws.data_ptr()), st))
+        check(L.mc_segment_reads(V(d_text.data_ptr()), V(rec_b.data_ptr()), self._status_ptr(S_NREC), rec_cap, V(seg_flags.data_ptr()), V(run_first.data_ptr()),
+                                 n_runs if n_tiles else 0, V(seg_start.data_ptr()),
                                  self._status_ptr(S_NSEG), V(ws.data_ptr()), st))
         check(L.mc_segment_quality(V(d_text.data_ptr()), V(rec_b.data_ptr()), V(seg_start.data_ptr()), self._status_ptr(S_NSEG), seg_cap,
                                    V(self.d_qual.data_ptr()), self.qual_table_size, V(seg_qual.data_ptr()), self._status_ptr(S_MISSING_QUAL), st))
