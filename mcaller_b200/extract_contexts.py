@@ -413,6 +413,7 @@ class RangeRun(object):
             with open(self.tsv_output, "ab") as outfi:
                 for res, text, n in fs.chunks(self.tsv_input, self.lo, self.hi):
                     _raise_on_counters(res)
+                    self._check_marking(text)
                     outfi.write(fmt.consume_bytes(res.calls(), text, res.n_segments))
                     self.bytes_done += n
             return
@@ -435,8 +436,22 @@ class RangeRun(object):
                     continue
                 res = eng.run_chunk(eng.upload(data), len(data))
                 _raise_on_counters(res)
+                self._check_marking(data)
                 self._write(fmt.consume(res.calls(), data, res.n_segments))
                 self.bytes_done += len(data)
+
+    def _check_marking(self, text):
+        """The reference marks a contig when the TSV first names it and quits on a bad positions row then
+        (extract_contexts.py:45-56, :154-160).  Contigs whose marking failed were kept without targets (ReferenceIndex):
+        the run stops as soon as one of them actually occurs in the text -- a rare path, searched on the host."""
+        if not self.ref.mark_errors:
+            return
+        buf = text.tobytes() if isinstance(text, np.ndarray) else bytes(text)
+        for nm, err in self.ref.mark_errors.items():
+            key = nm.encode()
+            if buf.startswith(key + b"\t") or buf.startswith(key + b" ") or (b"\n" + key + b"\t") in buf or (b"\n" + key + b" ") in buf:
+                print(str(err) + " - quitting thread now")
+                raise ReferenceAbort(str(err))
 
     def close_by_probe(self):
         """A window still open at the end of the range is closed by the first kept line after it, which lies in the next

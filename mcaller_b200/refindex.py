@@ -31,14 +31,24 @@ class ReferenceIndex(object):
         self.names = sorted(seqs, key=lambda s: s.encode())
         if len(self.names) >= 65535:
             raise ValueError("too many contigs")
-        self.marked = {}
-        self._marked_bytes = None
+        # one bytes copy of each 'M'-marked strand per contig, shared by every writer (native and Python)
+        self._marked_b = {}
+        # The reference marks a contig when it first meets it in the TSV (extract_contexts.py:154-160), so a bad positions
+        # row only stops a run that actually touches that contig.  Here all contigs are marked up front; a contig whose
+        # marking fails is kept without targets and remembered: extract_features raises if the run records a line on it.
+        self.mark_errors = {}
         bases_g, lens = [], []
         off = 0
         for nm in self.names:
             seq = seqs[nm]
-            fwd, rev = refmark.mark_reference(seq, base, motif=motif, positions_file=positions_file, contig=nm)
-            self.marked[nm] = (fwd, rev)
+            try:
+                fwd, rev = refmark.mark_reference(seq, base, motif=motif, positions_file=positions_file, contig=nm)
+            except refmark.MarkError as e:
+                if len(self.names) == 1:
+                    raise
+                self.mark_errors[nm] = e
+                fwd = rev = seq
+            self._marked_b[nm] = (fwd.encode("ascii"), rev.encode("ascii"))
             bases_g.append(off)
             lens.append(len(seq))
             off = ((off + len(seq) + 64 + 63) // 64) * 64
@@ -48,9 +58,9 @@ class ReferenceIndex(object):
         rev_b = np.zeros(n + 64, dtype=np.uint8)
         letters = np.full(n + 64, ord("N"), dtype=np.uint8)
         for nm, b0, ln in zip(self.names, bases_g, lens):
-            f, r = self.marked[nm]
-            fwd_b[b0:b0 + ln] = refmark.site_bitmap(f)
-            rev_b[b0:b0 + ln] = refmark.site_bitmap(r)
+            f, r = self._marked_b[nm]
+            fwd_b[b0:b0 + ln] = np.frombuffer(f, dtype=np.uint8) == ord("M")
+            rev_b[b0:b0 + ln] = np.frombuffer(r, dtype=np.uint8) == ord("M")
             letters[b0:b0 + ln] = np.frombuffer(seqs[nm].encode("ascii"), dtype=np.uint8)
         both = fwd_b | rev_b
         cand = both.copy()
@@ -104,12 +114,9 @@ class ReferenceIndex(object):
     def marked_bytes(self, strand):
         """The 'M'-marked copy of every contig (strand 0 = forward, 1 = reverse) as bytes, in index order; encoded once and
         shared by every writer (native and Python)."""
-        if self._marked_bytes is None:
-            self._marked_bytes = ([self.marked[nm][0].encode() for nm in self.names], [self.marked[nm][1].encode() for nm in self.names])
-        return self._marked_bytes[strand]
+        return [self._marked_b[nm][strand] for nm in self.names]
 
     def context(self, contig_index, mpos, rev):
         """revcomp(last_ref[mpos-k+1:mpos+k], last_rev) (extract_contexts.py:194)."""
-        f, r = self.marked[self.names[contig_index]]
-        src = r if rev else f
-        return refmark.revcomp(src[mpos - self.k + 1:mpos + self.k], bool(rev))
+        src = self._marked_b[self.names[contig_index]][1 if rev else 0]
+        return refmark.revcomp(src[mpos - self.k + 1:mpos + self.k].decode("ascii"), bool(rev))

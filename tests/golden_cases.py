@@ -53,6 +53,20 @@ CASES = {
     "bare_caay_p": dict(spec=_SPEC_P, positions="random", model=CAAY_BARE, base="A"),
     # cytosine targets
     "cg_c": dict(spec=_SPEC_G, motif="CG", model=R94, base="C", s=1),
+    # the reference's alternative classifiers (-c RF / LR / NBC; pickles fitted by tools/make_alt_models.py, the reference
+    # ships none): tree-walk, linear and naive-Bayes kernels pinned against the reference end to end
+    "rf_gatc": dict(spec=_SPEC3, motif="GATC", model="alt_RF_6_m6A.pkl", base="A", meth=True, s=1, classifier="RF"),
+    "lr_gatc": dict(spec=_SPEC3, motif="GATC", model="alt_LR_6_m6A.pkl", base="A", meth=True, classifier="LR"),
+    "nbc_gatc": dict(spec=_SPEC3, motif="GATC", model="alt_NBC_6_m6A.pkl", base="A", meth=True, classifier="NBC"),
+}
+
+
+# A case large enough for multi-chunk streaming (>= 10^3 reads, ~0.6 GB of TSV): the reference's outputs are stored as row
+# counts + sha256 (tools/make_golden.py), the inputs are regenerated on the GPU by the device generator (bit-identical to the
+# host generator, see test_device_generator_matches_numpy_generator)
+BIG_CASES = {
+    "gatc_1k_s1": dict(spec=dict(seed=21, contigs=[("ecoli", 600000)], n_reads=1200, len_min=1000, len_max=3000), motif="GATC",
+                       model=R95, base="A", meth=True, s=1, beds=[["-d", "2", "-t", "0.5"], ["-d", "3", "-t", "0.3", "--control"]]),
 }
 
 
@@ -202,6 +216,8 @@ def cli_args(case, inputs):
         a += ["-s", str(case["s"])]
     if case.get("q"):
         a += ["-q", str(case["q"])]
+    if case.get("classifier"):
+        a += ["-c", case["classifier"]]
     return a
 
 

@@ -277,3 +277,110 @@ def test_multi_gpu_product_path_nccl(tmp_path, cuda_lib):
     assert open(os.path.join(str(tmp_path), "syn.eventalign.diffs.6")).read() == gold["diffs"]
     want = [b for b in gold["beds"] if b["args"] == ["-d", "2", "-t", "0.5"]][0]["bed"]
     assert open(os.path.join(str(tmp_path), "syn.methylation.summary.bed")).read() == want
+
+
+def _build_big_inputs_on_device(case, outdir):
+    """Inputs of a BIG_CASES entry, the TSV written by the device generator (bit-identical to the host generator the golden
+    was made with -- the sha256 of the TSV is checked by the caller)."""
+    import numpy as np
+    from mcaller_b200 import synth, synth_device
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(**case["spec"])
+    genomes = [synth.genome(spec, ci) for ci in range(len(spec.contigs))]
+    seqs = {nm: genomes[ci].tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    ref = ReferenceIndex(seqs, case.get("base", "A"), motif=case.get("motif"), k=6)
+    meth = {}
+    for ci, (nm, ln) in enumerate(spec.contigs):
+        b0 = int(ref.contig_base[ref.names.index(nm)])
+        meth[ci] = (synth.meth_sites(spec, ci, ref.site_fwd_bits[b0:b0 + ln]), synth.meth_sites(spec, ci, ref.site_rev_bits[b0:b0 + ln]))
+    gen = synth_device.DeviceSynth(spec, ref, meth if case.get("meth") else None)
+    d_text, n, _ = gen.generate(0, spec.n_reads)
+    paths = {"tsv": os.path.join(outdir, "syn.eventalign.tsv"), "fasta": os.path.join(outdir, "ref.fasta"),
+             "fastq": os.path.join(outdir, "syn.fastq"), "model": os.path.join(gc.GOLD, "models", case["model"])}
+    d_text[:n].cpu().numpy().tofile(paths["tsv"])
+    with open(paths["fasta"], "w") as fh:
+        for nm, s in seqs.items():
+            fh.write(">%s\n" % nm)
+            fh.write("\n".join(s[j:j + 60] for j in range(0, len(s), 60)) + "\n")
+    with open(paths["fastq"], "w") as fh:
+        for i in range(spec.n_reads):
+            qs, _ = synth.read_quality_string(spec, i)
+            fh.write("@%s\n%s\n+\n%s\n" % (synth.read_name(spec, i), "A" * len(qs), qs))
+    return paths
+
+
+def test_thousand_read_case_matches_reference_hashes(tmp_path, capsys, cuda_lib):
+    """1 200 reads / ~0.6 GB of eventalign TSV streamed in 64 MB chunks: the `.diffs.6` file, the five stdout counters and the
+    BED files (make_bed drop-in on the text AND straight from the device histogram) hash to what the UNMODIFIED reference
+    produced on the same bytes (tests/golden/gatc_1k_s1.json, tools/make_golden.py) -- the reference, not only the oracle, at
+    a size where chunk edges, carried windows and multi-block kernels all occur."""
+    import hashlib
+    from mcaller_b200 import cli, extract_contexts as ec, make_bed as mb, read_qual
+    case = gc.BIG_CASES["gatc_1k_s1"]
+    gold = json.load(open(os.path.join(gc.GOLD, "gatc_1k_s1.json")))
+    inp = _build_big_inputs_on_device(case, str(tmp_path))
+    assert hashlib.sha256(open(inp["tsv"], "rb").read()).hexdigest() == gold["tsv_sha256"]
+    old = ec.CHUNK_BYTES
+    ec.CHUNK_BYTES = 64 << 20
+    try:
+        assert cli.mcaller_main(gc.cli_args(case, inp)) == 0
+        stdout = capsys.readouterr().out
+        diffs_path = os.path.join(str(tmp_path), "syn.eventalign.diffs.6")
+        diffs = open(diffs_path, "rb").read()
+        assert diffs.count(b"\n") == gold["diffs_rows"]
+        assert diffs.split(b"\n")[0].decode() == gold["diffs_first_row"] and diffs.split(b"\n")[-2].decode() == gold["diffs_last_row"]
+        assert hashlib.sha256(diffs).hexdigest() == gold["diffs_sha256"]
+        c = gold["counters"]
+        for line in ("%d observations\n" % c["observations"], "%d positions\n" % c["positions"],
+                     "%d regions with multiple methylated bases\n" % c["multi"], "%d observations with skips included\n" % c["with_skips"],
+                     "%d observations with too many skips\n" % c["too_many_skips"]):
+            assert line in stdout
+        # the fused route: histogram on the device while the rows are written
+        run = ec.RangeRun(inp["tsv"], inp["fasta"], read_qual.extract_read_quality(inp["fastq"]), 6, case["s"], 0.0, inp["model"], 0,
+                          endline=os.path.getsize(inp["tsv"]), base="A", motif=case["motif"], histogram=True)
+        os.remove(run.tsv_output) if os.path.exists(run.tsv_output) else None
+        run.stream()
+        run.eng.close_carry(-1)
+        assert hashlib.sha256(open(run.tsv_output, "rb").read()).hexdigest() == gold["diffs_sha256"]
+        depth, meth, first = run.eng.histogram_host()
+        assert int(depth.sum()) + len(run.eng.odd_rows()) == gold["diffs_rows"]
+    finally:
+        ec.CHUNK_BYTES = old
+    for b in gold["beds"]:
+        a = b["args"]
+        d_, t_ = int(a[a.index("-d") + 1]), float(a[a.index("-t") + 1])
+        out1, out2 = os.path.join(str(tmp_path), "t.bed"), os.path.join(str(tmp_path), "h.bed")
+        mb.aggregate_by_pos(diffs_path, out1, d_, t_, None, "--control" in a, False, False, None, False, "x", False)
+        mb.aggregate_from_histogram(run.ref, depth, meth, first, out2, d_, t_, control="--control" in a, odd_rows=run.eng.odd_rows())
+        for out in (out1, out2):
+            bed = open(out, "rb").read()
+            assert bed.count(b"\n") == b["rows"] and hashlib.sha256(bed).hexdigest() == b["sha256"], (a, out)
+    capsys.readouterr()
+
+
+def test_bad_positions_row_only_matters_for_contigs_in_the_tsv(tmp_path, capsys, cuda_lib):
+    """The reference marks a contig when the TSV first names it (extract_contexts.py:154-160): a positions row with the wrong
+    base on a contig that never occurs in the TSV is harmless (output == golden), on a contig that does occur it stops the
+    run (reference: print + sys.exit, here ReferenceAbort)."""
+    from mcaller_b200 import extract_contexts as ec, read_qual
+    case = gc.CASES["pos_p"]
+    gold = json.load(open(os.path.join(gc.GOLD, "pos_p.json")))
+    inp = gc.build_inputs(case, str(tmp_path))
+    with open(inp["fasta"], "a") as fh:
+        fh.write(">zz_unused\n" + "ACGT" * 50 + "\n")
+    with open(inp["positions"], "a") as fh:
+        fh.write("zz_unused\t1\t+\tm6A\n")                      # position 1 of zz_unused is 'C', not the target base
+    q = read_qual.extract_read_quality(inp["fastq"])
+    out = ".".join(inp["tsv"].split(".")[:-1]) + ".diffs.6.tmp0"
+    ec.extract_features(inp["tsv"], inp["fasta"], q, 6, case.get("s", 0), 0.0, inp["model"], "NN", 0, endline=os.path.getsize(inp["tsv"]),
+                        base="A", positions_list=inp["positions"])
+    assert open(out).read() == gold["diffs"]
+    os.remove(out)
+    seq = [ln for ln in open(inp["fasta"]).read().split(">") if ln.startswith("p1\n")][0].split("\n", 1)[1].replace("\n", "")
+    bad = next(i for i in range(20, 200) if seq[i] != "A")
+    with open(inp["positions"], "a") as fh:
+        fh.write("p1\t%d\t+\tm6A\n" % bad)
+    with pytest.raises(ec.ReferenceAbort):
+        ec.extract_features(inp["tsv"], inp["fasta"], q, 6, case.get("s", 0), 0.0, inp["model"], "NN", 0, endline=os.path.getsize(inp["tsv"]),
+                            base="A", positions_list=inp["positions"])
+    capsys.readouterr()

@@ -88,6 +88,37 @@ def make_case(name):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def make_big_case(name):
+    """Reference outputs of a BIG_CASES entry as counts + sha256 (the rows themselves would be tens of MB)."""
+    case = golden_cases.BIG_CASES[name]
+    tmp = tempfile.mkdtemp(prefix="gold_")
+    try:
+        inputs = golden_cases.build_inputs(case, tmp, models_dir=os.path.join(GOLD, "models"))
+        cmd = [sys.executable, os.path.join(REF, "mCaller.py")] + golden_cases.cli_args(case, inputs)
+        rc, so, se = run(cmd, tmp)
+        diffs_path = os.path.join(tmp, "syn.eventalign.diffs.6")
+        diffs = open(diffs_path, "rb").read()
+        rows = diffs.split(b"\n")
+        rec = {"case": name, "rc": rc, "tsv_sha256": hashlib.sha256(open(inputs["tsv"], "rb").read()).hexdigest(),
+               "tsv_bytes": os.path.getsize(inputs["tsv"]), "counters": counters(so), "diffs_rows": diffs.count(b"\n"),
+               "diffs_sha256": hashlib.sha256(diffs).hexdigest(), "diffs_first_row": rows[0].decode(), "diffs_last_row": rows[-2].decode(),
+               "beds": []}
+        for bed_args in case["beds"]:
+            for f in os.listdir(tmp):
+                if f.endswith(".bed") or f.endswith(".gff"):
+                    os.remove(os.path.join(tmp, f))
+            rc2, so2, se2 = run([sys.executable, os.path.join(REF, "make_bed.py"), "-f", "syn.eventalign.diffs.6"] + bed_args, tmp)
+            beds = [f for f in os.listdir(tmp) if f.endswith(".bed") or f.endswith(".gff")]
+            bed = open(os.path.join(tmp, beds[0]), "rb").read()
+            rec["beds"].append({"args": bed_args, "rc": rc2, "rows": bed.count(b"\n"), "sha256": hashlib.sha256(bed).hexdigest(),
+                                "first_row": bed.split(b"\n")[0].decode()})
+        with open(os.path.join(GOLD, name + ".json"), "w") as fh:
+            json.dump(rec, fh, indent=1, sort_keys=True)
+        print("%-18s rc=%d rows=%d counters=%s beds=%s" % (name, rc, rec["diffs_rows"], rec["counters"], [b["rows"] for b in rec["beds"]]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def make_bed_deep():
     """make_bed-only golden on a synthetic deep-coverage `.diffs.6` (golden_cases.deep_diffs_text)."""
     tmp = tempfile.mkdtemp(prefix="gold_")
@@ -140,9 +171,11 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if not os.path.exists(os.path.join(GOLD, "models", "CAAY_bare_model_6_m6A.pkl")):
         copy_fixtures()
-    names = sys.argv[1:] or (list(golden_cases.CASES) + ["bed_deep"])
+    names = sys.argv[1:] or (list(golden_cases.CASES) + ["bed_deep"] + list(golden_cases.BIG_CASES))
     for nm in names:
         if nm == "bed_deep":
             make_bed_deep()
+        elif nm in golden_cases.BIG_CASES:
+            make_big_case(nm)
         else:
             make_case(nm)
