@@ -551,6 +551,7 @@ def main():
     if use_dist:
         dist.barrier()
     torch.cuda.synchronize()
+    engine.overflowed()                 # clear the sticky flag: the warm-up steps grew the buffers where needed
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = engine.launches

@@ -232,6 +232,8 @@ class Engine(object):
                 seg_cap = min(n_seg + 1024, rec_cap)
             else:
                 call_cap = n_calls + 1024
+        if attempts:
+            self.d_persist[P_POISON] = 0              # the overflow was handled here: nothing is pending for overflowed()
         res.counters = {nm: int(cnt[i]) for i, nm in enumerate(_lib.COUNTER_NAMES)}
         res.n_records = n_rec
         res.n_segments = int(cnt[S_NSEG])
