@@ -60,7 +60,14 @@ def run_rank(rank, world, port, a, backend=None):
         run = ec.RangeRun(a["tsv"], a["reference"], read2qual, a["k"], a["skip"], a["qual"], a["modelfile"], start, endline=end,
                           base=a["base"], motif=a["motif"], positions_list=a["positions"], histogram=True,
                           row_base=mdist.rank_row_base(rank))
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         run.stream()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print("rank %d: %.2f GB of eventalign text -> %d rows in %.2f s (%.1f GB/s, %.0f calls/s) on cuda:%d"
+              % (rank, run.bytes_done / 1e9, run.fmt.n_obs, dt, run.bytes_done / 1e9 / max(dt, 1e-9), run.fmt.n_obs / max(dt, 1e-9), dev_index))
         eng = run.eng
         # (1) the window still open at the end of my range <- the first kept line of the next rank that has one
         first_kept = eng.first_kept_contig_dev()

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Throughput of the drop-in extract_features() on a FILE (page cache -> pinned buffers -> H2D -> kernels -> .diffs text on
-disk), i.e. what `mCaller.py -t 1` spends in its hot path.  usage: python tools/cli_throughput.py [--reads N]"""
+disk), i.e. what `mCaller.py -t 1` spends in its hot path -- and, with --gpus N, of the multi-GPU product path
+(`python -m mcaller_b200.cli mCaller ... --gpus N --bed`: N ranks, rows per rank, NCCL histogram, BED from the histogram).
+usage: python tools/cli_throughput.py [--reads N] [--gpus N] [--skip S]"""
 import argparse
 import os
 import sys
@@ -16,6 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=8000)
     ap.add_argument("--dir", default=None)
+    ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--skip", type=int, default=0)
     a = ap.parse_args()
     import io
     import contextlib
@@ -41,6 +45,29 @@ def main():
     del d_text, gen
     torch.cuda.empty_cache()
     model = os.path.join(ROOT, "tests", "golden", "models", "r95_twobase_model_NN_6_m6A.pkl")
+    if a.gpus:
+        import subprocess
+        fastq = os.path.join(d, "syn.fastq")
+        with open(fastq, "w") as fh:
+            for i in range(a.reads):
+                qs, _ = synth.read_quality_string(spec, i)
+                fh.write("@%s\n%s\n+\n%s\n" % (synth.read_name(spec, i), "A" * len(qs), qs))
+        cmd = [sys.executable, "-m", "mcaller_b200.cli", "mCaller", "-m", "GATC", "-r", fasta, "-e", tsv, "-f", fastq, "-d", model, "-b", "A",
+               "-s", str(a.skip), "--gpus", str(a.gpus), "--bed", "--bed_min_read_depth", "15", "--bed_mod_threshold", "0.5"]
+        env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        for rep in range(2):                   # first pass warms the page cache
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            dt = time.perf_counter() - t0
+            if p.returncode:
+                sys.exit(p.stdout[-3000:])
+        rows = sum(1 for _ in open(os.path.join(d, "syn.eventalign.diffs.6"), "rb"))
+        bed = sum(1 for _ in open(os.path.join(d, "syn.methylation.summary.bed"), "rb"))
+        stream = [ln for ln in p.stdout.split("\n") if ln.startswith("rank ")]
+        print("mCaller --gpus %d --bed on a %.2f GB file (%d reads, -s %d): %.2f s wall for the whole command (process start, CUDA / NCCL "
+              "init, FASTQ, reference marking included), %d rows -> %.0f calls/s, %d BED rows" % (a.gpus, n / 1e9, a.reads, a.skip, dt, rows, rows / dt, bed))
+        print("\n".join(stream))
+        return
     out = os.path.join(d, "syn.eventalign.diffs.6.tmp0")
     res = []
     for rep in range(2):                       # first pass warms the page cache, buffers and the CUDA context
