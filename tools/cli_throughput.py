@@ -35,6 +35,7 @@ def main():
     keys, q = synth_device.quality_table_for(spec, 0, a.reads)
     quals = dict(zip(keys, q.tolist()))
     d = a.dir or tempfile.mkdtemp(prefix="mc_cli_")
+    os.makedirs(d, exist_ok=True)
     tsv, fasta = os.path.join(d, "syn.eventalign.tsv"), os.path.join(d, "ref.fasta")
     with open(tsv, "wb") as fh:
         step = 1 << 28
