@@ -677,6 +677,7 @@ def main():
         e2e_pass()                                                 # warm-up (buffer growth, pinned result buffers)
         streamer.h2d_bytes = streamer.d2h_bytes = 0
         sink.text_bytes = 0
+        sink.render_seconds = 0.0
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -697,6 +698,7 @@ def main():
         h2d_rate = streamer.h2d_bytes / dt / 1e9
         e2e = {"value": e_calls / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // e_steps,
                "d2h_bytes_per_step": streamer.d2h_bytes // e_steps, "diffs_text_bytes_per_step": sink.text_bytes // e_steps,
+               "host_writer_ms_per_step": 1e3 * sink.render_seconds / e_steps, "ms_per_step": 1e3 * dt / e_steps,
                "h2d_gbs_per_gpu": h2d_rate, "h2d_ceiling_gbs_per_gpu": h2d_ceiling,
                "h2d_frac_of_ceiling": (h2d_rate / h2d_ceiling) if h2d_ceiling else None,
                "sample": "%d reads (%.2f GB TSV) per GPU streamed from pinned host memory in %d chunks, rows copied back and "

@@ -45,6 +45,7 @@ class TextSink(object):
         self.max_threads = int(max_threads)
         self.out = None
         self.text_bytes = 0
+        self.render_seconds = 0.0             # host time spent in the native writer
         self.carry_name = None                # read name of the window currently open across a chunk edge
         self.kept = [] if keep else None      # rendered text per chunk (tests)
 
@@ -68,9 +69,12 @@ class TextSink(object):
         cap = n_calls * (96 + 26 * (self.k + 1) + max(max_read_len, nlen)) + 4096
         if self.out is None or len(self.out) < cap:
             self.out = C.create_string_buffer(int(cap * 1.25))
+        import time as _time
+        t0 = _time.perf_counter()
         r = _lib.lib().mc_format_rows(C.c_void_p(rows.ctypes.data), n_calls, C.c_void_p(host_text_ptr), name, nlen, self.names, self.fwd,
                                       self.rev, self.lens, self.n, self.k, self.base, self.mod, self.with_prob, self.max_threads,
                                       self.out, len(self.out))
+        self.render_seconds += _time.perf_counter() - t0
         if r < 0:
             _lib.check(int(r) if r > -100 else -1)
         if rows[0]["kind"] != _lib.MC_NONE and rows[0]["read_off"] < 0:
