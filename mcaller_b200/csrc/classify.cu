@@ -41,7 +41,17 @@ __device__ __forceinline__ double mc_tanh(double x) {
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double t = p * __longlong_as_double((long long)(1023 + (int)n) << 52);
-    return copysign(__ddiv_rn(1.0 - t, 1.0 + t), x);
+    // (1 - t) / (1 + t) without the division routine: 1 + t lies in [1, 2], a single-precision reciprocal is refined by two
+    // Newton steps (24 -> 48 -> 96 bits) and the quotient gets one residual correction (<= 1 ulp)
+    const double d = 1.0 + t, u = 1.0 - t;
+    double rc = (double)__frcp_rn((float)d);
+    double e = fma(-d, rc, 1.0);
+    rc = fma(rc, e, rc);
+    e = fma(-d, rc, 1.0);
+    rc = fma(rc, e, rc);
+    double q = u * rc;
+    q = fma(fma(-d, q, u), rc, q);
+    return copysign(q, x);
 }
 
 __device__ __forceinline__ double activate(double v, int act) {
