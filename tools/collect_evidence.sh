@@ -15,12 +15,13 @@ timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_full_step.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/launches.log 2>&1
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k k_scan -c 1 --csv --log-file $O/k_scan_dram_full_size.csv \
-    python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/dram.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k k_scan -c 1 -f -o $O/k_scan_full \
-    python bench.py --reads 4000 --steps 1 --warmup 0 --no-e2e --no-cpu > $O/full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_finish_records|k_mlp|k_windows|k_gather|k_first_m' -c 6 -f \
-    -o $O/secondary_full python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/secondary.log 2>&1
+    -k k_scan --launch-skip 3 -c 1 --csv --log-file $O/k_scan_dram_full_size.csv \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/dram.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k k_scan --launch-skip 3 -c 1 -f -o $O/k_scan_full \
+    python bench.py --reads 4000 --steps 1 --warmup 3 --no-e2e --no-cpu > $O/full.log 2>&1
+# the launches of the step after the three warm-up steps (6 matching launches per step)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gather_finish|k_mlp|k_windows|k_seg_fix|k_first_m' \
+    --launch-skip 18 -c 6 -f -o $O/secondary_full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/secondary.log 2>&1
 CMD="compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_golden.py tests/test_gpu_kernels.py -x -q -k 'diffs_match and (gatc_s1 or adversarial or A_s2) or quiet_chunks and junk or odd_number_shapes'"
 ( timeout 1200 bash -c "$CMD" 2>&1 | tail -5; echo "command: $CMD" ) > $O/memcheck.txt
 ls -la $O
