@@ -56,6 +56,8 @@ def parse_args():
     p.add_argument("--cpu-reads", type=int, default=4000, help="reads in the bounded CPU-baseline sample")
     p.add_argument("--skip", type=int, default=-1, help="-s skip threshold (-1: the config's)")
     p.add_argument("--motif", default="", help="-m motif (default: the config's, GATC)")
+    p.add_argument("--qual", type=float, default=0.0, help="-q read-quality threshold (0: no filter; the synthetic read means spread around 9-13)")
+    p.add_argument("--scan-dense", action="store_true", help="record every kept line in the scan (round-1 behaviour under -q)")
     p.add_argument("--classifier", default="", choices=["", "NN", "RF"],
                    help="NN: the shipped MLP pickle; RF: a forest with the reference's -c RF hyper-parameters "
                         "(train_model.py:39-45) fitted on synthetic features (configs[3], tree-walk kernel)")
@@ -88,6 +90,8 @@ def resolve_config(args, world):
         c["classifier"] = args.classifier
     if args.reads:
         c["reads"] = args.reads
+    c["qual"] = float(args.qual)
+    c["scan_dense"] = bool(args.scan_dense)
     return c
 
 
@@ -96,6 +100,8 @@ def workload_text(c, nbytes=None, world=1):
         "RF model (50 trees, depth 10, reference hyper-parameters, fitted on synthetic features)"
     s = "%s: synthetic E. coli 4.6 Mb, %d reads per GPU%s, -m %s, %s, -n 6, -s %d" % (
         c["name"], c["reads"], (" (%.1f GB eventalign TSV)" % (nbytes / 1e9)) if nbytes else "", c["motif"], model, c["skip"])
+    if c.get("qual"):
+        s += ", -q %g%s" % (c["qual"], " (dense scan)" if c.get("scan_dense") else "")
     if c["bed"]:
         s += ", make_bed -d %d -t %s on the all-reduced histogram" % (BED_DEPTH, BED_THRESH)
     if c["index"] == 2:
@@ -266,7 +272,8 @@ def build_world(args, cfg, rank, world, n_generate=None):
     model = models.load_model_file(cfg["model"]) if cfg["classifier"] == "NN" else fit_reference_rf()
     e0, e1, two = models.select_models(model, base)
     dm = models.DeviceModels(e0, e1)
-    engine = eng_mod.Engine(ref, models=dm, qual_table=qt, skip_thresh=cfg["skip"], qual_thresh=0.0, two_models=two, histogram=True)
+    engine = eng_mod.Engine(ref, models=dm, qual_table=qt, skip_thresh=cfg["skip"], qual_thresh=cfg["qual"], two_models=two, histogram=True,
+                            dense=True if cfg["scan_dense"] else None)
     return dict(spec=spec, ref=ref, gen=gen, d_text=d_text, nbytes=nbytes, offs=offs, engine=engine, seqs=seqs, lo=lo, hi=hi,
                 quals=dict(zip(keys, q.tolist())), model=model, base=base, motif=motif)
 
@@ -331,7 +338,7 @@ def reference_pass(files, W, cfg, workdir, threads):
     """One run of the unmodified reference CLI on the sample -> (rows, seconds, path of its .diffs file)."""
     from oracle import ref_run
     r = ref_run.run_mcaller(workdir, files["tsv"], files["fasta"], files["fastq"], files["model"], threads=threads, base=W["base"],
-                            skip=cfg["skip"], classifier=cfg["classifier"], **files["motif_args"])
+                            skip=cfg["skip"], qual=cfg["qual"], classifier=cfg["classifier"], **files["motif_args"])
     if r["rc"] != 0 or r["diffs"] is None:
         raise RuntimeError("reference run failed (rc=%d): %s" % (r["rc"], (r["stdout"][-800:] + r["stderr"][-1500:])))
     with open(r["diffs"], "rb") as fh:
@@ -359,7 +366,7 @@ def cpu_oracle_pass(text_bytes, read_offsets, W, cfg, threads):
 
     def work(t):
         sl = bytes(mv[bounds[t]:bounds[t + 1]])
-        r = orc.extract(sl, None, None, k=6, skip_thresh=cfg["skip"], qual_thresh=0.0, cap=oracle_cap(cfg, len(sl)), count_only=True,
+        r = orc.extract(sl, None, None, k=6, skip_thresh=cfg["skip"], qual_thresh=cfg["qual"], cap=oracle_cap(cfg, len(sl)), count_only=True,
                         prepared=prep)
         return r["counters"]["observations"]
 
@@ -390,8 +397,8 @@ def parity_check(W, cfg, files, ref_diffs_path):
     unique lines).  Label / probability-text agreement is counted on the rows both sides have."""
     from oracle import oracle as orc
     gpu = gpu_rows_of_sample(W, cfg, files)
-    want = orc.extract(files["sample"], W["seqs"], W["quals"], k=6, skip_thresh=cfg["skip"], model=W["model"], base=W["base"],
-                       motif=W["motif"], cap=oracle_cap(cfg, len(files["sample"])))
+    want = orc.extract(files["sample"], W["seqs"], W["quals"], k=6, skip_thresh=cfg["skip"], qual_thresh=cfg["qual"], model=W["model"],
+                       base=W["base"], motif=W["motif"], cap=oracle_cap(cfg, len(files["sample"])))
     oracle_text = "".join(r + "\n" for r in want["rows"]).encode()
     gpu_rows = gpu.split(b"\n")[:-1]
     out = {"slice_reads": files["n_reads"], "gpu_calls": len(gpu_rows), "oracle_calls": len(want["rows"]),

@@ -179,16 +179,20 @@ int mc_read_u64(const uint64_t *d_src, int64_t n, uint64_t *h_dst, void *stream)
  * extract_contexts.py:140-176 (readlines, line.split()[:12], contig lookup, NNNNNN filter, k-mer
  * 'has M' test).  One warp per MC_TILE_BYTES chunk; a line belongs to the chunk holding its first byte.
  * Emits a record for every kept line that is a candidate (k-mer window touches a target on either
- * strand), that follows a candidate, or that is the first kept line of a run of chunks; with dense != 0 for
- * every kept line (needed with -q).  Records of one chunk are contiguous and in line order; warps reserve slots in
+ * strand), that follows a candidate, or that is the first kept line of a run of chunks; with dense == 1 for
+ * every kept line; with dense == 2 ("read-first", the mode for -q) additionally for the first kept line of every read
+ * (maximal block of lines with the same read name), so that whole reads can be dropped by quality later and a window left
+ * open at the end of a read still finds its closer: the first kept line of the next read that passes
+ * (extract_contexts.py:167 runs before :179).  Records of one chunk are contiguous and in line order; warps reserve slots in
  * blocks from d_counters[MC_C_RECORDS] (so that counter is an upper bound of the record count and the buffer has
  * holes); d_tile_tab[chunk] = {first record slot, count | flags} and d_run_tab[run] = {records of the run, flags} are consumed
  * by mc_order_records, which also drops the run-first records whose predecessor line turns out not to be a candidate.
  * Records leave this stage raw (MC_RF_RAW): line offset, position, contig, candidate flag and -- parked in the fields that are
  * still empty -- the first 128 field-start bits of the line; mc_order_records finishes them at full lane occupancy.
- * Without dense, groups of lines that all sit on non-candidate positions of the current contig are passed over after
+ * With dense != 1, groups of lines that all sit on non-candidate positions of the current contig (and, with dense == 2,
+ * all carry the read name of the line before them) are passed over after
  * a look at their first two columns, so MC_C_KEPT / MC_C_SHORT / MC_C_NNN / MC_C_BADPOS count only the lines that were
- * parsed in full: MC_C_KEPT is exact with dense != 0 and otherwise > 0 exactly when the range holds a kept line.
+ * parsed in full: MC_C_KEPT is exact with dense == 1 and otherwise > 0 exactly when the range holds a kept line.
  * d_counters (MC_C_COUNT uint64) must be zeroed by the caller; d_text must be 16-byte and d_tile_tab 8-byte aligned.
  */
 int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex *ref, int dense,

@@ -326,8 +326,18 @@ __device__ __forceinline__ void mc_finish_record_win(const uint8_t *__restrict__
     const int f9 = next(), f10 = next();
     const uint8_t *lp = text + line;
     // end of the read name: the bytes before column 5 are whitespace; step back over them (one tab in nanopolish output)
-    int name_end = f4 - 1;
-    while (name_end > f3 && __ldg(lp + name_end - 1) <= 0x20) --name_end;
+    // (the 8 bytes before column 5 in one load that does not depend on the others; a byte loop for anything unusual)
+    int name_end;
+    {
+        const unsigned long long t8 = f4 >= 8 ? load8_unaligned(lp + f4 - 8) : 0ull;
+        const uint32_t nh = fin_gt20((uint32_t)(t8 >> 32)), nlw = fin_gt20((uint32_t)t8);     // 0x80 per non-whitespace byte
+        const int tw = nh ? (__clz(nh) >> 3) : nlw ? 4 + (__clz(nlw) >> 3) : 8;               // whitespace bytes right before column 5
+        name_end = f4 - tw;
+        if (tw == 8 || name_end <= f3) {
+            name_end = f4 - 1;
+            while (name_end > f3 && __ldg(lp + name_end - 1) <= 0x20) --name_end;
+        }
+    }
     uint32_t fl = r.flags & ~MC_RF_RAW;
     int ev_idx = 0;
     double diff = 0.0;

@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(256, 4) k_gather_finish(const uint8_t *__restr
                                                       unsigned long long out_cap, uint32_t *__restrict__ seg_flags,
                                                       uint32_t *__restrict__ run_first) {
     const int lane = threadIdx.x & 31;
-    const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (run >= n_runs) return;
+    // warps stride over the runs (a resident grid): a warp whose run is empty moves on to its next run at once instead of
+    // leaving a hole in its CTA until the CTA's longest run is done
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t run = warp0; run < n_runs; run += n_warps) {
     const uint32_t rv = __ldg(run_tab + 2 * run + 1);
     const bool empty_run = __ldg(run_dst + run) == __ldg(run_dst + run + 1);       // after the filler drop
     if (run_first && lane == 0) run_first[run] = empty_run ? 0xFFFFFFFFu : __ldg(run_dst + run);
-    if (__ldg(run_tab + 2 * run) == 0u) return;                  // nothing recorded in this run
+    if (__ldg(run_tab + 2 * run) == 0u) continue;                // nothing recorded in this run
     const bool drop = (rv >> 31) != 0u;
     unsigned long long d_run = __ldg(run_dst + run);
     const int64_t c0 = run * run_len, c1 = min(c0 + (int64_t)run_len, n_tiles);
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(256, 4) k_gather_finish(const uint8_t *__restr
             carry_span = __shfl_sync(0xffffffffu, span, last);
         }
         d_run += tot;
+    }
     }
 }
 
@@ -408,7 +411,15 @@ extern "C" int mc_order_records(const uint8_t *d_text, int64_t nbytes, const mc_
     MC_LAUNCH_CHECK();
     int rc = mc_exscan_u32(cnt, dst, n_runs + 1, d_n_out, ws_s(d_ws, n_runs + 1), st);     // entry n_runs (count 0) = the total
     if (rc) return rc;
-    k_gather_finish<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, *ref, d_tile_tab, d_run_tab, dst, n_tiles,
+    int64_t gf_blocks = (n_runs * 32 + 255) / 256;
+    {
+        int dev = 0, sms = 0;
+        MC_CUDA_CHECK(cudaGetDevice(&dev));
+        MC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t resident = (int64_t)sms * 4;                 // __launch_bounds__(256, 4)
+        if (gf_blocks > resident) gf_blocks = resident;
+    }
+    k_gather_finish<<<(unsigned)gf_blocks, 256, 0, st>>>(d_text, nbytes + MC_TEXT_PAD - 64, *ref, d_tile_tab, d_run_tab, dst, n_tiles,
                                                                           n_runs, run_len, d_rec_in, (unsigned long long)rec_in_cap, d_rec_out,
                                                                           (unsigned long long)rec_out_cap, d_seg_flags, d_run_first);
     MC_LAUNCH_CHECK();

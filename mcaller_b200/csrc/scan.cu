@@ -51,6 +51,9 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_RUN
 #define MC_SCAN_RUN 32
 #endif
+#ifndef MC_SCAN_SWZ
+#define MC_SCAN_SWZ 0
+#endif
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int LCAP = 32;                      // lines per pass (one per lane)
@@ -67,6 +70,7 @@ struct WarpSmem {
     uint32_t cnt[8];                     // per-warp event counters (flushed once at the end)
     unsigned long long key[4];           // the hint contig's name in 8-byte pieces (quiet test; names of up to 31 bytes)
     alignas(8) unsigned long long bar[2];
+    unsigned long long rname[8];         // read-first mode: the read name of the last line seen, zero padded (names of up to 64 bytes)
 };
 
 // ---- TMA / mbarrier wrappers ---------------------------------------------------------------------------------------------
@@ -111,6 +115,12 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
     const uint32_t c = __dp4a(m5, hi, __dp4a(m4, lo, 0u));
     const uint32_t d = __dp4a(m7, hi, __dp4a(m6, lo, 0u));
     return (a >> 7) + b * 2u + c * 512u + d * 131072u;
+}
+
+// 4 msb-form words -> 16 flag bits
+__device__ __forceinline__ uint32_t pack16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    const uint32_t lo = 0x08040201u, hi = 0x80402010u;
+    return (__dp4a(m1, hi, __dp4a(m0, lo, 0u)) >> 7) + __dp4a(m3, hi, __dp4a(m2, lo, 0u)) * 2u;
 }
 
 // ---- generic field walk (rare: lines whose first 12 columns do not fit the 160-bit window) ------------------------------
@@ -223,6 +233,40 @@ __device__ __forceinline__ int parse_pos8(unsigned long long k8, int &pos) {
     return 1;
 }
 
+// ---- read-first mode (sparse scan with -q): read names of neighbouring lines ------------------------------------------
+// length of the token at smem offset q (bytes > 0x20), -1 when it is longer than 64 bytes
+__device__ __forceinline__ int token_len64(const uint8_t *text, int q) {
+    for (int j = 0; j < 9; ++j) {
+        const unsigned long long v = load8(text, q + 8 * j);
+        const uint32_t lo = gt20_msb((uint32_t)v) ^ 0x80808080u, hi = gt20_msb((uint32_t)(v >> 32)) ^ 0x80808080u;   // 0x80 = whitespace
+        if (lo) return 8 * j + ((__ffs(lo) - 1) >> 3);
+        if (hi) return 8 * j + 4 + ((__ffs(hi) - 1) >> 3);
+    }
+    return -1;
+}
+__device__ __forceinline__ unsigned long long low_bytes(unsigned long long v, int n) {          // first n (0..8) bytes of v
+    return n >= 8 ? v : (v & ((1ull << (8 * n)) - 1ull));
+}
+// token of `len` bytes at q equal to the zero-padded pieces key[]
+__device__ __forceinline__ bool token_is(const uint8_t *text, int q, int len, const unsigned long long *key) {
+    bool eq = true;
+    for (int j = 0; 8 * j < len; ++j) eq = eq && low_bytes(load8(text, q + 8 * j), len - 8 * j) == key[j];
+    return eq;
+}
+__device__ __forceinline__ bool tokens_equal(const uint8_t *text, int qa, int qb, int len) {
+    bool eq = true;
+    for (int j = 0; 8 * j < len; ++j) eq = eq && low_bytes(load8(text, qa + 8 * j) ^ load8(text, qb + 8 * j), len - 8 * j) == 0ull;
+    return eq;
+}
+// digits of a position column decoded by parse_pos8 (1..7)
+__device__ __forceinline__ int pos_digits8(unsigned long long k8) {
+    const uint32_t lo = (uint32_t)k8, hi = (uint32_t)(k8 >> 32);
+    const uint32_t xl = lo ^ 0x30303030u, xh = hi ^ 0x30303030u;
+    const uint32_t ndl = (((xl & 0x7f7f7f7fu) + 0x76767676u) | lo) & 0x80808080u;
+    const uint32_t ndh = (((xh & 0x7f7f7f7fu) + 0x76767676u) | hi) & 0x80808080u;
+    return ndl ? ((__ffs(ndl) - 1) >> 3) : 4 + ((__ffs(ndh) - 1) >> 3);
+}
+
 enum { ST_KEPT = 1u, ST_CAND = 2u, ST_SHORT = 4u, ST_UNKNOWN = 8u, ST_NNN = 16u, ST_BADPOS = 32u };
 
 // contig / NNNNNN / position / candidate test of one line whose columns 1, 2, 10 start at f0, f1, f9
@@ -264,6 +308,11 @@ __device__ __noinline__ uint32_t classify_from_global(const uint8_t *d_text, int
     return classify_line(t, f0, f1, f9, R, hint, hint_base, hint_len, -1, -1, -1, cid, pos);
 }
 
+// RF ("read-first" mode, the sparse scan under -q): the first kept line of every READ gets a record too, so that stage 4 can
+// filter whole reads by quality and still find the line that closes a window left open at the end of a read -- the first
+// kept line of the next read that passes (extract_contexts.py:167 runs before :179).  The warp carries the read name of
+// the last line it saw and "this read already has a kept line"; a chunk is quiet only if all its lines carry that name.
+template <bool RF>
 __global__ void __launch_bounds__(THREADS, MC_SCAN_MIN_CTAS)
 k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16, int64_t n_chunks64, int run_len, mc_refindex R,
        int dense, mc_record *__restrict__ d_rec, unsigned long long rec_cap, uint32_t *__restrict__ d_tile_tab,
@@ -276,6 +325,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     const int n_chunks = (int)n_chunks64;
     const int n_runs = (n_chunks + run_len - 1) / run_len;       // a run = run_len consecutive chunks parsed by one warp
     const uint32_t lt_mask = (1u << lane) - 1u;
+#if MC_SCAN_SWZ
+    const uint32_t swz = (lane & 4) ? 16u : 0u, swz_sel = (lane & 4) ? 0x1054u : 0x5410u;
+#endif
 
     // byte == 0x0a in three instructions per word: a LOP3 folds only one immediate, so the 0x7f mask is made a run-time
     // value (nbytes is never negative, which the compiler cannot know) and lives in a register: (w ^ imm) & reg is one LOP3
@@ -352,6 +404,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     int run_end = min(chunk + run_len, n_chunks);
     if (chunk < n_chunks) cur_async = stage(chunk, 0);
     int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
+    int rname_len = -1;            // RF: length of the read name in S.rname (-1: unknown / too long), warp-uniform
+    bool read_has_kept = false;    // RF: the read S.rname names already has a kept line in this run
     unsigned run_total = 0u, run_filler = 0u;                     // records / filler flag of the run so far
 
     while (chunk < n_chunks) {
@@ -385,10 +439,19 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int w = 32 * r + lane;
+#if MC_SCAN_SWZ
+            // lanes 4..7 of every eight read the two 16-byte halves of their 32 bytes in the other order: the eight 16-byte
+            // loads of a quarter warp then fall into eight different bank groups (32-byte stride alone hits four, twice)
+            const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w + swz);
+            const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + (16u - swz));
+            S.nl[w] = __byte_perm(pack16(eq0a_r(va.x), eq0a_r(va.y), eq0a_r(va.z), eq0a_r(va.w)),
+                                  pack16(eq0a_r(vb.x), eq0a_r(vb.y), eq0a_r(vb.z), eq0a_r(vb.w)), swz_sel);
+#else
             const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
             const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
             S.nl[w] = pack32(eq0a_r(va.x), eq0a_r(va.y), eq0a_r(va.z), eq0a_r(va.w), eq0a_r(vb.x), eq0a_r(vb.y), eq0a_r(vb.z),
                              eq0a_r(vb.w));
+#endif
         }
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
@@ -433,7 +496,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         // without the field-start map, the line list or the per-line parse.  Lanes test the lines that start inside their
         // own 128 bytes (usually one, so one round).
         bool quiet_chunk = false;
-        if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 31) {
+        if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 31 && (!RF || (read_has_kept && rname_len >= 1))) {
             uint32_t w0 = lsv.x, w1 = lsv.y, w2 = lsv.z, w3 = lsv.w;
             bool ok = true;
             while (__any_sync(0xffffffffu, (w0 | w1 | w2 | w3) != 0u)) {
@@ -454,11 +517,24 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                     ok = false;
                     if (name_ok) {
                         int p0 = 0;
-                        if (parse_pos8(load8(text, s0 + hint_nlen + 1), p0) == 1) {
+                        const unsigned long long p8 = load8(text, s0 + hint_nlen + 1);
+                        if (parse_pos8(p8, p0) == 1) {
                             ok = true;
                             if (p0 < hint_len) {
                                 const int64_t g = hint_base + p0;
                                 ok = ((__ldg(R.d_cand + (g >> 5)) >> (g & 31)) & 1u) == 0u;
+                            }
+                            if (RF && ok) {
+                                // "<ws><k-mer of up to 7 bytes><ws><the carried read name><ws>" right after the position
+                                const int km = s0 + hint_nlen + 1 + pos_digits8(p8) + 1;
+                                const unsigned long long k8 = load8(text, km);
+                                const uint32_t wl = gt20_msb((uint32_t)k8) ^ 0x80808080u, wh = gt20_msb((uint32_t)(k8 >> 32)) ^ 0x80808080u;
+                                const int klen = wl ? ((__ffs(wl) - 1) >> 3) : wh ? 4 + ((__ffs(wh) - 1) >> 3) : 8;
+                                ok = false;
+                                if (klen >= 1 && klen <= 7) {
+                                    const int nm = km + klen + 1;
+                                    ok = token_is(text, nm, rname_len, S.rname) && text[nm + rname_len] <= 0x20;
+                                }
                             }
                         }
                     }
@@ -541,10 +617,17 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int w = 32 * r + lane;
+#if MC_SCAN_SWZ
+                    const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w + swz);
+                    const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + (16u - swz));
+                    const uint32_t nonws = __byte_perm(pack16(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w)),
+                                                       pack16(gt20_msb(vb.x), gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w)), swz_sel);
+#else
                     const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
                     const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
                     const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x),
                                                   gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w));
+#endif
                     // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
                     const uint32_t top = nonws >> 31;
                     uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
@@ -607,13 +690,46 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             c_kept += (unsigned)__popc(kept_m);
             const uint32_t cand_m = __ballot_sync(0xffffffffu, (status & ST_CAND) != 0u);
             bool emit = false, filler_lane = false;
+            if (RF) {
+                // read name of every line of the pass against the line before it (bytes of column 4; anything unusual -- a
+                // line parsed from global memory, fewer than 4 columns, a name of more than 64 bytes -- counts as a change)
+                int nq = 0, nlen = -1;
+                if (lane < n_pass && staged) {
+                    nq = select_fs_walk(S.fs, s, 3);
+                    nlen = token_len64(text, nq);
+                    if (nlen == 0) nlen = -1;
+                }
+                const int pq = __shfl_up_sync(0xffffffffu, nq, 1), plen = __shfl_up_sync(0xffffffffu, nlen, 1);
+                bool same = false;
+                if (lane < n_pass && nlen > 0) {
+                    if (lane == 0) same = nlen == rname_len && token_is(text, nq, nlen, S.rname);
+                    else same = nlen == plen && tokens_equal(text, nq, pq, nlen);
+                }
+                const uint32_t pass_m = n_pass >= 32 ? 0xFFFFFFFFu : ((1u << n_pass) - 1u);
+                const uint32_t new_m = __ballot_sync(0xffffffffu, !same) & pass_m;
+                if (status & ST_KEPT) {
+                    const uint32_t nle = new_m & ((2u << lane) - 1u);           // read changes at or before this line
+                    bool had;
+                    if (nle == 0u) had = read_has_kept || (kept_m & lt_mask) != 0u;
+                    else had = (kept_m & lt_mask & ~((1u << (31 - __clz(nle))) - 1u)) != 0u;
+                    if (!had) emit = true;                                      // first kept line of its read
+                }
+                if (new_m == 0u) read_has_kept = read_has_kept || kept_m != 0u;
+                else read_has_kept = (kept_m >> (31 - __clz(new_m))) != 0u;
+                // the name of the pass's last line is what the next line is compared with
+                const int lq = __shfl_sync(0xffffffffu, nq, n_pass - 1), llen = __shfl_sync(0xffffffffu, nlen, n_pass - 1);
+                __syncwarp();
+                if (llen > 0 && lane < 8) S.rname[lane] = 8 * lane < llen ? low_bytes(load8(text, lq + 8 * lane), llen - 8 * lane) : 0ull;
+                rname_len = llen > 0 ? llen : -1;
+                __syncwarp();
+            }
             if (status & ST_KEPT) {
                 if (dense || (status & ST_CAND)) emit = true;
                 else {
                     const uint32_t below = kept_m & lt_mask;
                     const int st = below ? (int)((cand_m >> (31 - __clz(below))) & 1u) : prev_state;
-                    emit = (st != 0);            // predecessor is a candidate, or this is the first kept line of the run
-                    if (st < 0) filler_lane = true;
+                    if (st != 0) emit = true;    // predecessor is a candidate, or this is the first kept line of the run
+                    if (st < 0 && !RF) filler_lane = true;       // (RF: stage 2 keeps it, it may be the first kept line of its read)
                 }
             }
             const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
@@ -683,6 +799,8 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             run_total = 0u;
             run_filler = 0u;
             prev_state = -1;
+            rname_len = -1;
+            read_has_kept = false;
         }
         chunk = next;
         run_end = next_end;
@@ -755,7 +873,8 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     if (n_chunks == 0) return MC_OK;
     MC_REQUIRE(n_chunks < (1ll << 30), "too many chunks (chunk of text larger than 4 TB)");
     const size_t smem = sizeof(WarpSmem) * WARPS;
-    MC_CUDA_CHECK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool read_first = dense == 2;                           // sparse + the first kept line of every read (-q)
+    MC_CUDA_CHECK(cudaFuncSetAttribute(read_first ? k_scan<true> : k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = 0;
     int run_len = 1;
     {
@@ -766,9 +885,14 @@ extern "C" int mc_scan(const uint8_t *d_text, int64_t nbytes, const mc_refindex 
     const int64_t text_limit16 = ((nbytes + MC_TEXT_PAD) / 16) * 16;
     // the run cursor must start at zero whatever the caller did with the counter block
     MC_CUDA_CHECK(cudaMemsetAsync(d_counters + MC_C_RUN_CURSOR, 0, sizeof(uint64_t), (cudaStream_t)stream));
-    k_scan<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense, d_rec,
-                                                                     (unsigned long long)rec_cap, d_tile_tab, d_run_tab,
-                                                                     reinterpret_cast<unsigned long long *>(d_counters));
+    if (read_first)
+        k_scan<true><<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, 0, d_rec,
+                                                                               (unsigned long long)rec_cap, d_tile_tab, d_run_tab,
+                                                                               reinterpret_cast<unsigned long long *>(d_counters));
+    else
+        k_scan<false><<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(d_text, nbytes, text_limit16, n_chunks, run_len, *ref, dense ? 1 : 0,
+                                                                                d_rec, (unsigned long long)rec_cap, d_tile_tab, d_run_tab,
+                                                                                reinterpret_cast<unsigned long long *>(d_counters));
     MC_LAUNCH_CHECK();
     return MC_OK;
 }

@@ -64,8 +64,11 @@ class Engine(object):
         self.skip_thresh = int(skip_thresh)
         self.qual_thresh = float(qual_thresh)
         self.two_models = 1 if two_models else 0
-        # the -q filter drops whole reads, so window closers can be any kept line: record every kept line then
-        self.dense = bool(dense) if dense is not None else (self.qual_thresh > 0.0)
+        # scan mode: 1 = every kept line gets a record; 0 = candidates, their successors and run-first lines; 2 = mode 0 plus
+        # the first kept line of every read -- the -q filter drops whole reads, and a window left open at the end of a read
+        # is closed by the first kept line of the next read that passes (extract_contexts.py:167 before :179)
+        self.dense = bool(dense) if dense is not None else False
+        self.scan_mode = 1 if self.dense else (2 if self.qual_thresh > 0.0 else 0)
         with torch.cuda.device(self.device):
             if qual_table is None:
                 qual_table = np.zeros(16, dtype=_lib.QUAL_DTYPE)
@@ -266,7 +269,7 @@ class Engine(object):
         if self.scan_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(L.mc_scan(V(d_text.data_ptr()), nbytes, self.ref.ref(), 1 if self.dense else 0, V(rec_a.data_ptr()), rec_cap,
+        check(L.mc_scan(V(d_text.data_ptr()), nbytes, self.ref.ref(), self.scan_mode, V(rec_a.data_ptr()), rec_cap,
                         V(tile_tab.data_ptr()), V(run_tab.data_ptr()), V(self.d_small.data_ptr()), st))
         if self.scan_events is not None:
             e1.record()

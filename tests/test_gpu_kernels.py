@@ -475,6 +475,94 @@ def test_scan_runs_and_quiet_chunks_match_oracle(variant, run_len, cuda_lib, ora
         L.mc_scan_set_run_len(before)
 
 
+def _lead_junk(tsv, seed):
+    """Put 1-60 lines that are NOT kept (NNNNNN, or fewer than 12 columns) in front of the first line of about half of the
+    reads, under the read's own name: the read's first KEPT line is then not its first line, and may sit chunks later."""
+    import random
+    rnd = random.Random(seed)
+    out, last = [], None
+    for ln in tsv.decode().split("\n"):
+        f = ln.split("\t")
+        if len(f) >= 13 and f[3] != last:
+            last = f[3]
+            if rnd.random() < 0.5:
+                for _ in range(rnd.randint(1, 60)):
+                    if rnd.random() < 0.5:
+                        g = list(f)
+                        g[9], g[10], g[11], g[12] = "NNNNNN", "0.00", "0.00", "inf"
+                        out.append("\t".join(g))
+                    else:
+                        out.append("\t".join(f[:rnd.randint(4, 11)]))
+        out.append(ln)
+    return "\n".join(out).encode()
+
+
+@pytest.mark.parametrize("run_len", [0, 1, 5])
+@pytest.mark.parametrize("motif", ["GATCG", "GAT"])
+@pytest.mark.parametrize("variant", ["plain", "junk", "lead_junk", "names", "fuzz"])
+def test_quality_filter_with_sparse_scan_matches_oracle(variant, motif, run_len, cuda_lib, oracle):
+    """-q drops whole reads (extract_contexts.py:167) before the window logic sees their lines, so a window left open at the
+    end of a read is closed by the first kept line of the next read that PASSES, and the row takes that line's contig (:179,
+    :214).  The scan's read-first mode (mc_scan dense == 2) records the first kept line of every read for this; rows
+    (contig column included), features and counters must equal the oracle's with about half of the reads filtered, most
+    reads without any site of the rare motif (GATCG) or many windows open at read ends (GAT), reads of three contigs in
+    random order, and junk in front of / behind the lines that matter."""
+    import random
+    from mcaller_b200 import _lib, engine, models, read_qual, synth
+    from mcaller_b200.refindex import ReferenceIndex
+    spec = synth.SynthSpec(seed=77, contigs=[("NC_000913.3", 9000), ("c", 7000), ("plasmid_pB171_2", 5000)], n_reads=400, len_min=30, len_max=200)
+    order = list(range(spec.n_reads))
+    random.Random(5).shuffle(order)
+    tsv, fasta, fastq, quals = synth.generate(spec, reads=order)
+    quals = {k.split("_")[0]: v for k, v in quals.items()}
+    if variant == "junk":
+        tsv = _junk_blocks(tsv, 4)
+    elif variant == "lead_junk":
+        tsv = _lead_junk(tsv, 6)
+    elif variant == "names":
+        tsv, quals = _rename_reads(tsv, quals, "mixed", 8)
+    elif variant == "fuzz":
+        tsv = _mutate_layout(tsv, 3)
+    seqs = {nm: synth.genome(spec, ci).tobytes().decode() for ci, (nm, _) in enumerate(spec.contigs)}
+    ref = ReferenceIndex(seqs, "A", motif=motif, k=6)
+    model = models.load_model_file(os.path.join(gc.GOLD, "models", gc.R95))
+    dm = models.DeviceModels(model["MH"], model["MG"])
+    qt = float(np.median(list(quals.values())))
+    want = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=1, qual_thresh=qt, model=model, base="A", motif=motif, cap=100000)
+    all_rows = oracle.extract(tsv, seqs, quals, k=6, skip_thresh=1, model=model, base="A", motif=motif, cap=100000)
+    assert 10 < len(want["calls"]) < len(all_rows["calls"])
+    if motif == "GAT":
+        assert sum(1 for w in want["calls"] if w["chrom"] != w["win_contig"]) >= 2       # rows closed by a line of another contig
+    names = [nm for nm, _ in spec.contigs]
+    L = _lib.lib()
+    before = L.mc_scan_set_run_len(run_len)
+    try:
+        outs = []
+        for dense in (None, True):
+            eng = engine.Engine(ref, models=dm, qual_table=read_qual.build_quality_table(quals), skip_thresh=1, qual_thresh=qt,
+                                two_models=True, dense=dense)
+            assert eng.scan_mode == (1 if dense else 2)
+            res = eng.run_chunk(eng.upload(tsv), len(tsv))
+            assert res.missing_quality == 0
+            calls = res.calls()
+            mine = calls[(calls["kind"] == 0) & (calls["close_rec"] != 0xFFFFFFFF)]
+            assert len(mine) == len(want["calls"])
+            for c, w in zip(mine, want["calls"]):
+                assert names[int(c["chrom_contig"])] == w["chrom"] and names[int(c["win_contig"])] == w["win_contig"]
+                assert int(c["mpos"]) == w["mpos"] and bool(c["rev"]) == w["rev"] and int(c["empty_mask"]) == w["empty_mask"]
+                assert tsv[int(c["read_off"]):int(c["read_off"]) + int(c["read_len"])].decode() == w["read"]
+                assert [float(x) for x in c["feat"][:7]] == w["feat"]
+                assert abs(float(c["prob"]) - w["prob"]) < 1e-12
+            st = eng.count_rows(res)
+            assert st["too_many_skips"] == want["counters"]["too_many_skips"] and st["errors"] == 0
+            outs.append(res.n_records)
+        # (far) fewer records than one per kept line -- except that names of more than 64 bytes ("names") always count as a
+        # new read, so all their kept lines are recorded
+        assert outs[0] < outs[1] // (3 if (motif == "GATCG" and variant != "names") else 1)
+    finally:
+        L.mc_scan_set_run_len(before)
+
+
 @pytest.mark.parametrize("mode", ["A_dense", "p_one_strand"])
 def test_window_units_in_other_site_regimes(mode, tmp_path, cuda_lib, oracle):
     """The window builder cuts reads into units at non-candidate records; GATC gives short units.  Two other regimes against

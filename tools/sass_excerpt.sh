@@ -14,5 +14,6 @@ END {
     for (k in cnt) print cnt[k] "\t" k
 }' | sort -k2,2 -k1,1nr | awk -F'\t' '{ printf "%-8s %-34s %s\n", $1, $3, $2 }' | c++filt 2>/dev/null | sed 's/(anonymous namespace):://' | cut -c1-200
 echo
-echo "# first occurrences in k_scan"
-cuobjdump -sass "$LIB" | awk '/Function : /{f=($0 ~ /k_scanE/)} f && /UBLKCP|SYNCS\.ARRIVE|SYNCS\.PHASECHK|IDP\.4A/ {print}' | head -12
+echo "# first occurrences in k_scan (three of each kind)"
+cuobjdump -sass "$LIB" | awk '/Function : /{f=($0 ~ /6k_scan/); if (f) print} f && /UBLKCP|SYNCS\.ARRIVE|SYNCS\.PHASECHK|IDP\.4A/ {
+    k = ($0 ~ /UBLKCP/) ? "a" : ($0 ~ /ARRIVE/) ? "b" : ($0 ~ /PHASECHK/) ? "c" : "d"; if (++n[k] <= 3) print }' | cut -c1-160 | head -40
