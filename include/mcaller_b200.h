@@ -100,6 +100,7 @@ enum {
     MC_C_LONGLINE,         /* lines whose first 12 columns outran the look-ahead and took the byte-wise slow path (informational) */
     MC_C_OVERFLOW,         /* records dropped because rec_cap was too small */
     MC_C_RUN_CURSOR,       /* internal: next unclaimed run of chunks (dynamic work distribution of mc_scan) */
+    MC_C_QUIET,            /* chunks (MC_TILE_BYTES each) passed over after the look at their first columns (informational) */
     MC_C_COUNT = 16
 };
 
@@ -356,6 +357,7 @@ int mc_count_calls(const mc_call *d_calls, const uint64_t *d_nrows, int64_t row_
 typedef struct mc_locus_entry {
     unsigned long long hash;
     unsigned long long first_off;
+    unsigned long long check;   /* independent second hash of the locus key (0 = not set): two loci with one `hash` are counted in d_counters[7] */
     uint32_t depth;
     uint32_t meth;
 } mc_locus_entry;
@@ -369,7 +371,8 @@ int mc_diffs_aggregate(const uint8_t *d_text, int64_t nbytes, mc_locus_entry *d_
  *   streamed in line-aligned pieces into one table (first_off = base_off + offset inside the piece) -- d_posset (may be NULL) is an
  *   open-addressing set (power-of-two entries, 0 = empty) of FNV-1a hashes of "chrom\tpos\tstrand" built by the host from
  *   the positions file (entries whose end column is not start + 1 can never match and are left out).
- *   d_counters[8]: rows, malformed, centre-not-'M', table-full drops, rows outside the positions set, old-format rows
+ *   d_counters[8]: rows, malformed, centre-not-'M', table-full drops, rows outside the positions set, old-format rows,
+ *   [6] see mc_diffs_colstats, [7] rows whose 64-bit locus key matched a slot holding another locus (check hash differs)
  *   (7 fields), value tokens float() would not parse, value tokens outside the exactly-rounded range.
  * mc_diffs_rows: second pass; one mc_diffs_row per used row in arbitrary order (sort by line_off for file order):
  *   the locus slot in d_table, and the spans of the values (column 5) and stripped probability (column 8) fields.

@@ -15,7 +15,7 @@ MC_TILE_BYTES = 3840
 MC_TEXT_PAD = 4096
 MC_MAXK = 8
 MC_C_COUNT = 16
-COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor"]
+COUNTER_NAMES = ["lines", "kept", "records", "short", "unknown_contig", "nnn", "badpos", "longline", "overflow", "run_cursor", "quiet_chunks"]
 
 MC_ABI_VERSION = 2
 MC_CALL, MC_TOO_MANY_SKIPS, MC_MULTI_M, MC_NONE = 0, 1, 2, 3
@@ -58,7 +58,7 @@ CALL_DTYPE = np.dtype([("read_off", "<i8"), ("prob", "<f8"), ("feat", "<f8", (MC
 assert CALL_DTYPE.itemsize == 128
 
 class LocusEntry(C.Structure):
-    _fields_ = [("hash", C.c_uint64), ("first_off", C.c_uint64), ("depth", C.c_uint32), ("meth", C.c_uint32)]
+    _fields_ = [("hash", C.c_uint64), ("first_off", C.c_uint64), ("check", C.c_uint64), ("depth", C.c_uint32), ("meth", C.c_uint32)]
 
 
 CARRY_BYTES = 192          # sizeof(mc_carry): the row (128 B), valid, first_kept_contig, chunk count, padding

@@ -41,10 +41,20 @@ __device__ __forceinline__ unsigned long long fnv_span(const uint8_t *__restrict
     return h;
 }
 __device__ __forceinline__ unsigned long long fnv_sep(unsigned long long h) { return (h ^ 9ull) * 1099511628211ull; }
+// second, independent hash of the same bytes (other basis, other multiplier, extra shift-xor): stored next to the slot's key so
+// that two different loci with the same 64-bit key are noticed instead of merged
+__device__ __forceinline__ unsigned long long chk_span(const uint8_t *__restrict__ text, int64_t a, int64_t b, unsigned long long g) {
+    for (int64_t i = a; i < b; ++i) {
+        g = (g ^ __ldg(text + i)) * 0x9E3779B97F4A7C15ull;
+        g ^= g >> 29;
+    }
+    return g;
+}
+__device__ __forceinline__ unsigned long long chk_sep(unsigned long long g) { return ((g ^ 9ull) * 0x9E3779B97F4A7C15ull) ^ (g >> 31); }
 
 // 0 = use the row, 1 = malformed, 2 = centre of the context is not 'M' (:84), 3 = not in the positions set (:84)
 __device__ __forceinline__ int classify_row(const uint8_t *__restrict__ text, int64_t nbytes, int64_t p, const unsigned long long *posset,
-                                            unsigned long long posmask, DiffsRow &r, unsigned long long &h) {
+                                            unsigned long long posmask, DiffsRow &r, unsigned long long &h, unsigned long long *check = nullptr) {
     split_row(text, nbytes, p, r);
     if (r.nf != 8 && r.nf != 7) return 1;                        // reference: unpack error
     const int64_t c0 = r.f[0], c0e = r.f[1] - 1, p0 = r.f[2], p0e = r.f[3] - 1, x0 = r.f[3], x0e = r.f[4] - 1, s0 = r.f[5], s0e = r.f[6] - 1;
@@ -71,6 +81,13 @@ __device__ __forceinline__ int classify_row(const uint8_t *__restrict__ text, in
     h = fnv_span(text, x0, x0e, fnv_sep(h));
     h = fnv_span(text, s0, s0e, fnv_sep(h));
     if (h == 0ull) h = 1ull;
+    if (check) {
+        unsigned long long g = chk_span(text, c0, c0e, 0x243F6A8885A308D3ull);
+        g = chk_span(text, p0, p0e, chk_sep(g));
+        g = chk_span(text, x0, x0e, chk_sep(g));
+        g = chk_span(text, s0, s0e, chk_sep(g));
+        *check = g ? g : 1ull;
+    }
     return 0;
 }
 
@@ -82,8 +99,8 @@ k_diffs_aggregate(const uint8_t *__restrict__ text, int64_t nbytes, unsigned lon
     if (p >= nbytes) return;
     if (p > 0 && __ldg(text + p - 1) != '\n') return;          // not a line start
     DiffsRow r;
-    unsigned long long h = 0ull;
-    const int st = classify_row(text, nbytes, p, posset, posmask, r, h);
+    unsigned long long h = 0ull, chk = 0ull;
+    const int st = classify_row(text, nbytes, p, posset, posmask, r, h, &chk);
     atomicAdd(&counters[0], 1ull);                               // lines
     if (st == 1) { atomicAdd(&counters[1], 1ull); return; }
     if (st == 2) { atomicAdd(&counters[2], 1ull); return; }
@@ -102,6 +119,9 @@ k_diffs_aggregate(const uint8_t *__restrict__ text, int64_t nbytes, unsigned lon
             atomicAdd(&table[slot].depth, 1u);
             if (is_m) atomicAdd(&table[slot].meth, 1u);
             atomicMin(&table[slot].first_off, base_off + (unsigned long long)p);
+            // the first row of a locus leaves its check hash; a later row with the same key but other bytes is a collision
+            const unsigned long long seen = atomicCAS(&table[slot].check, 0ull, chk);
+            if (seen != 0ull && seen != chk) atomicAdd(&counters[7], 1ull);
             return;
         }
         slot = (slot + 1) & mask;
@@ -122,6 +142,7 @@ k_diffs_rehash(const mc_locus_entry *__restrict__ old_table, unsigned long long 
         const unsigned long long cur = atomicCAS(&table[slot].hash, 0ull, e.hash);
         if (cur == 0ull) {                                       // keys are distinct in the old table: the slot is ours
             table[slot].first_off = e.first_off;
+            table[slot].check = e.check;
             table[slot].depth = e.depth;
             table[slot].meth = e.meth;
             return;

@@ -51,9 +51,7 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #ifndef MC_SCAN_RUN
 #define MC_SCAN_RUN 32
 #endif
-#ifndef MC_SCAN_SWZ
-#define MC_SCAN_SWZ 0
-#endif
+
 constexpr int WARPS = MC_SCAN_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int LCAP = 32;                      // lines per pass (one per lane)
@@ -117,12 +115,6 @@ __device__ __forceinline__ uint32_t pack32(uint32_t m0, uint32_t m1, uint32_t m2
     return (a >> 7) + b * 2u + c * 512u + d * 131072u;
 }
 
-// 4 msb-form words -> 16 flag bits
-__device__ __forceinline__ uint32_t pack16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
-    const uint32_t lo = 0x08040201u, hi = 0x80402010u;
-    return (__dp4a(m1, hi, __dp4a(m0, lo, 0u)) >> 7) + __dp4a(m3, hi, __dp4a(m2, lo, 0u)) * 2u;
-}
-
 // ---- generic field walk (rare: lines whose first 12 columns do not fit the 160-bit window) ------------------------------
 // position of the n-th (0-based) field start at or after smem offset s; NW*32 when it lies beyond the staged bytes
 __device__ __noinline__ int select_fs_walk(const uint32_t *fs, int s, int n) {
@@ -156,7 +148,8 @@ __device__ __forceinline__ int nth_bit(uint32_t m, int j) {     // position of t
     for (int t = 6; t < j; ++t) m &= m - 1u;                     // words with more than 7 field starts: rare
     return __ffs(m) - 1;
 }
-__device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11) {
+template <bool WANT3>
+__device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, int &f1, int &f9, int &f11, int &f3) {
     const int w0 = s >> 5, sh = s & 31;
     const uint32_t a0 = S.fs[w0], a1 = S.fs[w0 + 1], a2 = S.fs[w0 + 2], a3 = S.fs[w0 + 3], a4 = S.fs[w0 + 4], a5 = S.fs[w0 + 5];
     const uint32_t W0 = __funnelshift_r(a0, a1, sh), W1 = __funnelshift_r(a1, a2, sh), W2 = __funnelshift_r(a2, a3, sh),
@@ -176,6 +169,7 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
             f0 = sel(0);
             f1 = sel(1);
         }
+        if (WANT3) f3 = c0 >= 4 ? s + nth_bit(W0, 3) : sel(3);      // column 4 (read name): inside the first 32 bytes as a rule
         if (c2 <= 9 && c3 > 11) {
             // usual layout (a ~128-byte line): columns 10 and 12 both start inside the fourth window word
             uint32_t m = W3;
@@ -198,6 +192,7 @@ __device__ __forceinline__ void line_fields(const WarpSmem &S, int s, int &f0, i
         f1 = select_fs_walk(S.fs, s, 1);
         f9 = select_fs_walk(S.fs, s, 9);
         f11 = select_fs_walk(S.fs, s, 11);
+        if (WANT3) f3 = select_fs_walk(S.fs, s, 3);
     }
 }
 
@@ -325,9 +320,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     const int n_chunks = (int)n_chunks64;
     const int n_runs = (n_chunks + run_len - 1) / run_len;       // a run = run_len consecutive chunks parsed by one warp
     const uint32_t lt_mask = (1u << lane) - 1u;
-#if MC_SCAN_SWZ
-    const uint32_t swz = (lane & 4) ? 16u : 0u, swz_sel = (lane & 4) ? 0x1054u : 0x5410u;
-#endif
 
     // byte == 0x0a in three instructions per word: a LOP3 folds only one immediate, so the 0x7f mask is made a run-time
     // value (nbytes is never negative, which the compiler cannot know) and lives in a register: (w ^ imm) & reg is one LOP3
@@ -395,6 +387,35 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         return false;
     };
 
+    // RF: does every lane's line carry the read name S.rname?  nm = where the lane's name starts in the staged bytes (-1: no
+    // line).  16 lanes x 4 bytes cover a name (<= 63 bytes) and the byte that must end it; two lines per step, one per half
+    // warp, so the shared-memory reads are free of bank conflicts.  Warp-uniform result.
+    int rname_len = -1;            // length of the read name in S.rname (-1: unknown / too long)
+    auto rf_all_match = [&](const uint8_t *text, int nm) -> bool {
+        const int j = lane & 15;
+        const uint32_t kw = reinterpret_cast<const uint32_t *>(S.rname)[j];
+        const int nb = rname_len - 4 * j;                                  // name bytes from this lane's word on
+        const uint32_t kmask = nb >= 4 ? 0xFFFFFFFFu : nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u);
+        const bool term_lane = j == (rname_len >> 2);
+        const int term_sh = 8 * (rname_len & 3);
+        const uint32_t *tw32 = reinterpret_cast<const uint32_t *>(text);
+        uint32_t have = __ballot_sync(0xffffffffu, nm >= 0);
+        while (have) {
+            const int oa = __ffs(have) - 1;
+            have &= have - 1u;
+            const int ob = have ? __ffs(have) - 1 : -1;
+            have &= have - 1u;                                             // (0 & anything stays 0)
+            const int o = lane < 16 ? oa : ob;
+            const int a = __shfl_sync(0xffffffffu, nm, o < 0 ? 0 : o) + 4 * j;
+            const uint32_t v = __funnelshift_r(tw32[a >> 2], tw32[(a >> 2) + 1], 8 * (a & 3));
+            bool bad = ((v ^ kw) & kmask) != 0u;
+            if (term_lane && ((v >> term_sh) & 0xFFu) > 0x20u) bad = true;
+            if (o < 0) bad = false;
+            if (__any_sync(0xffffffffu, bad)) return false;
+        }
+        return true;
+    };
+
     // Runs are claimed dynamically: run `warp_global` first, then one atomic per run on the run cursor.  Inside a run the
     // state of the last kept line (prev_state) carries from chunk to chunk, so only the first kept line of a RUN is a
     // "filler" record that stage 2 may have to drop.
@@ -404,7 +425,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     int run_end = min(chunk + run_len, n_chunks);
     if (chunk < n_chunks) cur_async = stage(chunk, 0);
     int prev_state = -1;           // -1: no kept line yet in this run, 0: last kept line not a candidate, 1: candidate
-    int rname_len = -1;            // RF: length of the read name in S.rname (-1: unknown / too long), warp-uniform
     bool read_has_kept = false;    // RF: the read S.rname names already has a kept line in this run
     unsigned run_total = 0u, run_filler = 0u;                     // records / filler flag of the run so far
 
@@ -439,19 +459,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int w = 32 * r + lane;
-#if MC_SCAN_SWZ
-            // lanes 4..7 of every eight read the two 16-byte halves of their 32 bytes in the other order: the eight 16-byte
-            // loads of a quarter warp then fall into eight different bank groups (32-byte stride alone hits four, twice)
-            const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w + swz);
-            const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + (16u - swz));
-            S.nl[w] = __byte_perm(pack16(eq0a_r(va.x), eq0a_r(va.y), eq0a_r(va.z), eq0a_r(va.w)),
-                                  pack16(eq0a_r(vb.x), eq0a_r(vb.y), eq0a_r(vb.z), eq0a_r(vb.w)), swz_sel);
-#else
             const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
             const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
             S.nl[w] = pack32(eq0a_r(va.x), eq0a_r(va.y), eq0a_r(va.z), eq0a_r(va.w), eq0a_r(vb.x), eq0a_r(vb.y), eq0a_r(vb.z),
                              eq0a_r(vb.w));
-#endif
         }
         if (lane == 0) S.nl[NW] = 0xFFFFFFFFu;
         __syncwarp();
@@ -499,7 +510,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
         if (!dense && prev_state == 0 && hint_nlen >= 1 && hint_nlen <= 31 && (!RF || (read_has_kept && rname_len >= 1))) {
             uint32_t w0 = lsv.x, w1 = lsv.y, w2 = lsv.z, w3 = lsv.w;
             bool ok = true;
-            while (__any_sync(0xffffffffu, (w0 | w1 | w2 | w3) != 0u)) {
+            int rf_round = 0, rf_nm1 = -1;                         // RF: where the read name of this lane's second line starts
+            for (;; ++rf_round) {
+                if (!__any_sync(0xffffffffu, (w0 | w1 | w2 | w3) != 0u)) break;
                 if ((w0 | w1 | w2 | w3) != 0u) {
                     const int jw = w0 ? 0 : w1 ? 1 : w2 ? 2 : 3;
                     const uint32_t m = w0 ? w0 : w1 ? w1 : w2 ? w2 : w3;
@@ -530,10 +543,26 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                                 const unsigned long long k8 = load8(text, km);
                                 const uint32_t wl = gt20_msb((uint32_t)k8) ^ 0x80808080u, wh = gt20_msb((uint32_t)(k8 >> 32)) ^ 0x80808080u;
                                 const int klen = wl ? ((__ffs(wl) - 1) >> 3) : wh ? 4 + ((__ffs(wh) - 1) >> 3) : 8;
-                                ok = false;
-                                if (klen >= 1 && klen <= 7) {
-                                    const int nm = km + klen + 1;
-                                    ok = token_is(text, nm, rname_len, S.rname) && text[nm + rname_len] <= 0x20;
+                                ok = klen >= 1 && klen <= 7 && rf_round < 2;
+                                const int nm = km + klen + 1;
+                                if (rf_round == 0) {
+                                    // first line of this lane (nearly every lane has one): the name against the carried one,
+                                    // 4 bytes at a time, then the byte that must end it; uniform trip count
+                                    const uint32_t *tw32 = reinterpret_cast<const uint32_t *>(text) + (nm >> 2);
+                                    const uint32_t *kw32 = reinterpret_cast<const uint32_t *>(S.rname);
+                                    const int sh = 8 * (nm & 3), nfull = rname_len >> 2;
+                                    uint32_t prev = tw32[0], acc = 0u;
+                                    for (int j = 0; j < nfull; ++j) {
+                                        const uint32_t nxt = tw32[j + 1];
+                                        acc |= __funnelshift_r(prev, nxt, sh) ^ kw32[j];
+                                        prev = nxt;
+                                    }
+                                    const uint32_t v = __funnelshift_r(prev, tw32[nfull + 1], sh);
+                                    const int nb = 8 * (rname_len & 3);
+                                    acc |= (v ^ kw32[nfull]) & ((1u << nb) - 1u);
+                                    ok = ok && acc == 0u && ((v >> nb) & 0xFFu) <= 0x20u;
+                                } else {
+                                    rf_nm1 = nm;       // second lines are few: compared below, a line per half warp
                                 }
                             }
                         }
@@ -541,7 +570,9 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 }
                 if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
             }
+            if (RF && ok) ok = rf_all_match(text, rf_nm1);         // ... and the carried read name
             quiet_chunk = ok;                                      // warp-uniform
+            if (ok && lane == 0) S.cnt[6] += 1u;
         }
 
         // ---- 2b. line list of a chunk that needs the full parse ---------------------------------------------------------------
@@ -617,17 +648,10 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int w = 32 * r + lane;
-#if MC_SCAN_SWZ
-                    const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w + swz);
-                    const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + (16u - swz));
-                    const uint32_t nonws = __byte_perm(pack16(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w)),
-                                                       pack16(gt20_msb(vb.x), gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w)), swz_sel);
-#else
                     const uint4 va = *reinterpret_cast<const uint4 *>(text + 32 * w);
                     const uint4 vb = *reinterpret_cast<const uint4 *>(text + 32 * w + 16);
                     const uint32_t nonws = pack32(gt20_msb(va.x), gt20_msb(va.y), gt20_msb(va.z), gt20_msb(va.w), gt20_msb(vb.x),
                                                   gt20_msb(vb.y), gt20_msb(vb.z), gt20_msb(vb.w));
-#endif
                     // top bit of the previous word: lane-1 of this round, or lane 31 of the previous round for lane 0
                     const uint32_t top = nonws >> 31;
                     uint32_t pt = __shfl_up_sync(0xffffffffu, top, 1);
@@ -654,12 +678,13 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             uint32_t status = 0u;
             int cid = -1, pos = 0, s = 0;
             bool staged = false;       // first 12 columns inside the staged bytes (else: classified from global memory)
+            int f3 = 0;                // RF: where column 4 (the read name) starts
             if (lane < n_pass) {
                 s = S.lstart[lane];
                 const int e = (pass0 + lane + 1 < total_lines) ? (int)S.lstart[lane + 1] - 1 : (e_last >= 0 ? e_last : next_bit(S.nl, s));
                 // columns 1, 2, 10, 12 from a 160-bit window of the field-start bits aligned at the line start
                 int f0, f1, f9, f11;
-                line_fields(S, s, f0, f1, f9, f11);
+                line_fields<RF>(S, s, f0, f1, f9, f11, f3);
                 if (f11 < e) {
                     staged = true;
                     // contig: compare the first bytes with the warp's hint in registers, full lookup on a miss
@@ -693,20 +718,32 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
             if (RF) {
                 // read name of every line of the pass against the line before it (bytes of column 4; anything unusual -- a
                 // line parsed from global memory, fewer than 4 columns, a name of more than 64 bytes -- counts as a change)
+                // usual case: every line of the pass carries the name the warp already holds (one cooperative compare)
+                const bool valid = lane < n_pass;
+                const uint32_t unusual = __ballot_sync(0xffffffffu, valid && !staged);
+                uint32_t new_m = 0u;
+                if (unusual != 0u || rname_len < 1 || !rf_all_match(text, valid ? f3 : -1)) {
                 int nq = 0, nlen = -1;
-                if (lane < n_pass && staged) {
-                    nq = select_fs_walk(S.fs, s, 3);
+                if (valid && staged) {
+                    nq = f3;
                     nlen = token_len64(text, nq);
                     if (nlen == 0) nlen = -1;
                 }
                 const int pq = __shfl_up_sync(0xffffffffu, nq, 1), plen = __shfl_up_sync(0xffffffffu, nlen, 1);
                 bool same = false;
-                if (lane < n_pass && nlen > 0) {
+                if (valid && nlen > 0) {
                     if (lane == 0) same = nlen == rname_len && token_is(text, nq, nlen, S.rname);
                     else same = nlen == plen && tokens_equal(text, nq, pq, nlen);
                 }
                 const uint32_t pass_m = n_pass >= 32 ? 0xFFFFFFFFu : ((1u << n_pass) - 1u);
-                const uint32_t new_m = __ballot_sync(0xffffffffu, !same) & pass_m;
+                new_m = __ballot_sync(0xffffffffu, !same) & pass_m;
+                // the name of the pass's last line is what the next line is compared with
+                const int lq = __shfl_sync(0xffffffffu, nq, n_pass - 1), llen = __shfl_sync(0xffffffffu, nlen, n_pass - 1);
+                __syncwarp();
+                if (llen > 0 && lane < 8) S.rname[lane] = 8 * lane < llen ? low_bytes(load8(text, lq + 8 * lane), llen - 8 * lane) : 0ull;
+                rname_len = (llen > 0 && llen <= 63) ? llen : -1;          // (the cooperative compare covers 63 bytes + the byte that ends the name)
+                __syncwarp();
+                }
                 if (status & ST_KEPT) {
                     const uint32_t nle = new_m & ((2u << lane) - 1u);           // read changes at or before this line
                     bool had;
@@ -716,12 +753,6 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
                 }
                 if (new_m == 0u) read_has_kept = read_has_kept || kept_m != 0u;
                 else read_has_kept = (kept_m >> (31 - __clz(new_m))) != 0u;
-                // the name of the pass's last line is what the next line is compared with
-                const int lq = __shfl_sync(0xffffffffu, nq, n_pass - 1), llen = __shfl_sync(0xffffffffu, nlen, n_pass - 1);
-                __syncwarp();
-                if (llen > 0 && lane < 8) S.rname[lane] = 8 * lane < llen ? low_bytes(load8(text, lq + 8 * lane), llen - 8 * lane) : 0ull;
-                rname_len = llen > 0 ? llen : -1;
-                __syncwarp();
             }
             if (status & ST_KEPT) {
                 if (dense || (status & ST_CAND)) emit = true;
@@ -814,6 +845,7 @@ k_scan(const uint8_t *__restrict__ d_text, int64_t nbytes, int64_t text_limit16,
     if (lane == 0) {
         if (c_lines) atomicAdd(&d_counters[MC_C_LINES], (unsigned long long)c_lines);
         if (c_kept) atomicAdd(&d_counters[MC_C_KEPT], (unsigned long long)c_kept);
+        if (S.cnt[6]) atomicAdd(&d_counters[MC_C_QUIET], (unsigned long long)S.cnt[6]);
     }
     if (lane < 6) {
         const int which = lane == 0 ? MC_C_SHORT : lane == 1 ? MC_C_UNKNOWN_CONTIG : lane == 2 ? MC_C_NNN : lane == 3 ? MC_C_BADPOS

@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-LOCUS_DTYPE = np.dtype([("hash", "<u8"), ("first_off", "<u8"), ("depth", "<u4"), ("meth", "<u4")])
+LOCUS_DTYPE = np.dtype([("hash", "<u8"), ("first_off", "<u8"), ("check", "<u8"), ("depth", "<u4"), ("meth", "<u4")])
 
 _FNV_OFF, _FNV_PRIME, _M64 = 14695981039346656037, 1099511628211, (1 << 64) - 1
 
@@ -153,7 +153,7 @@ class _Aggregation(object):
                     d_piece = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8, count=cut).copy()).to(self.dev)
                     _lib.check(self.L.mc_diffs_aggregate_ex(self._p(d_piece), cut, base, self._p(self.d_posset), self.posset_size,
                                                             self._p(self.d_table), self.table_size, self._p(self.d_cnt), self._stream()))
-                    n_loci = int((self.d_table.view(torch.int64).view(-1, 3)[:, 0] != 0).sum().item())
+                    n_loci = int((self.d_table.view(torch.int64).view(-1, 4)[:, 0] != 0).sum().item())
                     base += cut
                     carry = buf[cut:]
                     if not piece:
@@ -164,6 +164,8 @@ class _Aggregation(object):
             raise ValueError("%d rows of %s do not have 7 or 8 tab-separated fields" % (cnt[1], meth_fi))
         if cnt[3]:
             raise RuntimeError("locus table overflow")
+        if cnt[7]:
+            raise RuntimeError("%d rows of %s collide with another locus in the 64-bit key hash" % (cnt[7], meth_fi))
         table = self.d_table.cpu().numpy().view(LOCUS_DTYPE)
         used = np.nonzero(table["hash"] != 0)[0]
         order = np.argsort(table["first_off"][used], kind="stable")

@@ -169,7 +169,7 @@ def test_struct_sizes_match_abi():
     assert lib.mc_sizeof(0) == _lib.RECORD_DTYPE.itemsize and lib.mc_sizeof(1) == _lib.CALL_DTYPE.itemsize
     assert lib.mc_sizeof(2) == C.sizeof(_lib.RefIndex) and lib.mc_sizeof(3) == C.sizeof(_lib.Model)
     assert lib.mc_sizeof(4) == _lib.QUAL_DTYPE.itemsize and lib.mc_sizeof(5) == C.sizeof(_lib.SynthSpec)
-    assert lib.mc_sizeof(6) == C.sizeof(_lib.LocusEntry) == 24
+    assert lib.mc_sizeof(6) == C.sizeof(_lib.LocusEntry) == 32
     assert lib.mc_sizeof(7) == _lib.DIFFS_ROW_DTYPE.itemsize == 32
 
 
