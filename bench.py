@@ -661,10 +661,12 @@ def main():
         best = probe_reps * probe_n / (time.perf_counter() - t0) / 1e9
         del dst
         ceil_t = torch.tensor([best], dtype=torch.float64, device=dev)
+        ceil_min = ceil_t.clone()
         if use_dist:
             dist.all_reduce(ceil_t, op=dist.ReduceOp.SUM)
             ceil_t /= world
-        h2d_ceiling = float(ceil_t[0])
+            dist.all_reduce(ceil_min, op=dist.ReduceOp.MIN)
+        h2d_ceiling, h2d_ceiling_min = float(ceil_t[0]), float(ceil_min[0])
         streamer = stream_mod.HostStreamer(engine, chunk_bytes=min(args.e2e_chunk, max(end, 1 << 20)))
         cuts = stream_mod.plan_chunks(offs_all[:n_e], end, streamer.chunk_bytes)
         fmt_threads = binding.get("cores", 0) if binding.get("bound") else 0
@@ -695,10 +697,13 @@ def main():
             e_calls += e2e_pass()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        dt_fastest = dt
         if use_dist:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            tmin = t.clone()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dt, dt_fastest = float(t[0]), float(tmin[0])
             c = torch.tensor([e_calls], dtype=torch.int64, device=dev)
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             e_calls = int(c[0])
@@ -706,11 +711,12 @@ def main():
         e2e = {"value": e_calls / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // e_steps,
                "d2h_bytes_per_step": streamer.d2h_bytes // e_steps, "diffs_text_bytes_per_step": sink.text_bytes // e_steps,
                "host_writer_ms_per_step": 1e3 * sink.render_seconds / e_steps, "ms_per_step": 1e3 * dt / e_steps,
-               "h2d_gbs_per_gpu": h2d_rate, "h2d_ceiling_gbs_per_gpu": h2d_ceiling,
+               "ms_per_step_fastest_rank": 1e3 * dt_fastest / e_steps,
+               "h2d_gbs_per_gpu": h2d_rate, "h2d_ceiling_gbs_per_gpu": h2d_ceiling, "h2d_ceiling_slowest_rank_gbs": h2d_ceiling_min,
                "h2d_frac_of_ceiling": (h2d_rate / h2d_ceiling) if h2d_ceiling else None,
                "sample": "%d reads (%.2f GB TSV) per GPU streamed from pinned host memory in %d chunks, rows copied back and "
-                         "rendered as .diffs text by the native writer; ceiling = mean over ranks of %d back-to-back pinned->device copies of "
-                         "%.1f GB, all %d ranks copying at once" % (n_e, end / 1e9, len(cuts), probe_reps, probe_n / 1e9, world)}
+                         "rendered as .diffs text by the native writer; ceiling = mean (and slowest rank) over ranks of %d back-to-back "
+                         "pinned->device copies of %.1f GB, all %d ranks copying at once; the step ends with the slowest rank" % (n_e, end / 1e9, len(cuts), probe_reps, probe_n / 1e9, world)}
         del host
 
     # ------------------------------------------------------------------------------------------------ CPU baseline + parity

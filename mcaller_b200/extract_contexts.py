@@ -409,7 +409,10 @@ class RangeRun(object):
         if not self.train:
             # inference: pipelined path (reader thread -> pinned buffers -> H2D on a side stream -> kernels -> native writer)
             from . import stream as _stream
-            fs = _stream.FileStreamer(eng, CHUNK_BYTES, read_boundary_before, readers=READ_THREADS)
+            # chunk size: the configured one for long ranges; a short range (a rank's slice of a small file) is cut into ~6
+            # pieces so that reading, copying and computing still overlap and the pinned buffers stay small
+            chunk = min(CHUNK_BYTES, max(64 << 20, (self.hi - self.lo + 5) // 6))
+            fs = _stream.FileStreamer(eng, chunk, read_boundary_before, readers=READ_THREADS)
             with open(self.tsv_output, "ab") as outfi:
                 for res, text, n in fs.chunks(self.tsv_input, self.lo, self.hi):
                     _raise_on_counters(res)

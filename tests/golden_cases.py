@@ -46,6 +46,11 @@ CASES = {
     "pos_p": dict(spec=_SPEC_P, positions="random", model=R95, base="A", s=1),
     # read-quality filter
     "gatc_q": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, q=13.5),
+    # read-quality filter where it matters: reads of three contigs in random order, cut short so that windows stay open at read
+    # ends, half of the reads below the threshold -- a window is then closed by the first kept line of the next read that
+    # PASSES and takes that line's contig (extract_contexts.py:167 before :179, :214)
+    "gat_q_handoff": dict(spec=dict(seed=31, contigs=[("ctgA", 5000), ("ctgB", 4000), ("ctgC", 3000)], n_reads=90, len_min=40, len_max=160),
+                          motif="GAT", model=R95, base="A", s=1, q=13.5, post="truncate", shuffle=9),
     # malformed / odd lines
     "adversarial": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1, post="adversarial"),
     # bare estimator pickles -> 'general' model path
@@ -187,7 +192,11 @@ def build_inputs(case, outdir, models_dir=None):
             fwd, rev = refmark.mark_reference(seq, base, motif=case.get("motif"), positions_file=paths.get("positions"), contig=nm)
             site_maps[ci] = (synth.meth_sites(spec, ci, refmark.site_bitmap(fwd)),
                              synth.meth_sites(spec, ci, refmark.site_bitmap(rev)))
-    tsv, fasta, fastq, _ = synth.generate(spec, site_maps)
+    order = None
+    if case.get("shuffle") is not None:                      # reads in random order instead of contig by contig
+        order = list(range(spec.n_reads))
+        random.Random(case["shuffle"]).shuffle(order)
+    tsv, fasta, fastq, _ = synth.generate(spec, site_maps, reads=order)
     if case.get("post"):
         lines = tsv.decode().split("\n")
         if lines and lines[-1] == "":

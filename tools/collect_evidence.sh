@@ -22,8 +22,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k k_scan --l
 # the launches of the step after the three warm-up steps (6 matching launches per step)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gather_finish|k_mlp|k_windows|k_seg_fix|k_first_m' \
     --launch-skip 18 -c 6 -f -o $O/secondary_full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/secondary.log 2>&1
-CMD="compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_golden.py tests/test_gpu_kernels.py -x -q -k 'diffs_match and (gatc_s1 or adversarial or A_s2) or quiet_chunks and junk or odd_number_shapes'"
-( timeout 1200 bash -c "$CMD" 2>&1 | tail -5; echo "command: $CMD" ) > $O/memcheck.txt
+# compute-sanitizer (memcheck, racecheck, synccheck) over the golden, quiet-chunk / distant-closer, odd-shape, carry and -q read-first tests
+SEL="diffs_match and (gatc_s1 or adversarial or A_s2) or quiet_chunks and junk or odd_number_shapes or chunked_equals_whole and gatc_s1 or worker_ranges and gatc_s1 or quality_filter and (plain or names) and GAT-0"
+for tool in memcheck racecheck synccheck; do
+  ( timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_golden.py tests/test_gpu_kernels.py -x -q -k "$SEL" 2>&1 | tail -4
+    echo "exit=$?  command: compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_golden.py tests/test_gpu_kernels.py -x -q -k '$SEL'" ) > $O/sanitizer_$tool.txt
+done
 ls -la $O
 tail -c 600 $O/bench_default.json
-cat $O/memcheck.txt
+cat $O/sanitizer_*.txt
