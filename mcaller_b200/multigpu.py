@@ -124,10 +124,37 @@ def merge_outputs(tsv, k, world):
 
 
 def run(a, world):
-    """Spawn `world` ranks on this node (one per GPU) and merge their outputs."""
-    import torch.multiprocessing as mp
+    """Spawn `world` ranks on this node (one per GPU) and merge their outputs.  The parent never imports torch (that alone is
+    several seconds of a short run): plain `multiprocessing` with the spawn start method; a rank that fails takes the others
+    down with it."""
+    import multiprocessing
+    import time
+    ctx = multiprocessing.get_context("spawn")
     port = _free_port()
-    mp.spawn(run_rank, args=(world, port, a), nprocs=world, join=True)
+    procs = [ctx.Process(target=run_rank, args=(r, world, port, a)) for r in range(world)]
+    for p in procs:
+        p.start()
+    failed = None
+    while failed is None and any(p.is_alive() for p in procs):
+        for r, p in enumerate(procs):
+            p.join(0.05)
+            if p.exitcode not in (None, 0):
+                failed = (r, p.exitcode)
+                break
+    if failed is None:
+        for r, p in enumerate(procs):
+            p.join()
+            if p.exitcode != 0:
+                failed = (r, p.exitcode)
+                break
+    if failed is not None:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+        deadline = time.time() + 10
+        for p in procs:
+            p.join(max(0.0, deadline - time.time()))
+        raise RuntimeError("rank %d of %d exited with code %s" % (failed[0], world, failed[1]))
     return merge_outputs(a["tsv"], a["k"], world)
 
 
