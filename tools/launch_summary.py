@@ -17,7 +17,7 @@ for r in rows:
         except ValueError:
             continue
         seq.append((d["Kernel Name"][:72], v))
-idx = [i for i, (n, v) in enumerate(seq) if "k_scan(" in n]
+idx = [i for i, (n, v) in enumerate(seq) if "k_scan(" in n or "k_scan<" in n]
 step = seq[idx[-1]:] if idx else seq
 tot = sum(v for n, v in step)
 agg = {}
