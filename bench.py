@@ -714,6 +714,7 @@ def main():
                "ms_per_step_fastest_rank": 1e3 * dt_fastest / e_steps,
                "h2d_gbs_per_gpu": h2d_rate, "h2d_ceiling_gbs_per_gpu": h2d_ceiling, "h2d_ceiling_slowest_rank_gbs": h2d_ceiling_min,
                "h2d_frac_of_ceiling": (h2d_rate / h2d_ceiling) if h2d_ceiling else None,
+               "h2d_frac_of_slowest_rank_ceiling": (h2d_rate / h2d_ceiling_min) if h2d_ceiling_min else None,
                "sample": "%d reads (%.2f GB TSV) per GPU streamed from pinned host memory in %d chunks, rows copied back and "
                          "rendered as .diffs text by the native writer; ceiling = mean (and slowest rank) over ranks of %d back-to-back "
                          "pinned->device copies of %.1f GB, all %d ranks copying at once; the step ends with the slowest rank" % (n_e, end / 1e9, len(cuts), probe_reps, probe_n / 1e9, world)}
