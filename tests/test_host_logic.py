@@ -302,3 +302,11 @@ def test_tail_search_of_last_read_boundary_equals_full_search():
         want = ec.read_boundary_before(buf, len(buf))
         for span in (64, 1000, 50000, 1 << 22):
             assert stream.last_boundary(arr, len(buf), ec.read_boundary_before, span=span) == want, (trial, span)
+
+
+def test_multigpu_run_reports_a_failed_rank(tmp_path):
+    """`cli mCaller --gpus N` spawns its ranks with plain multiprocessing (the parent never imports torch); a rank that
+    dies -- here: no such TSV, or no CUDA device -- takes the others down and surfaces as one RuntimeError."""
+    from mcaller_b200 import multigpu
+    with pytest.raises(RuntimeError, match="rank [01] of 2 exited"):
+        multigpu.run(dict(tsv=str(tmp_path / "missing.eventalign.tsv"), k=6), 2)

@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""How often does the scan pass over a chunk?  Runs a 1 GB synthetic input through the engine in the three scan modes
+(0 sparse, 2 read-first = sparse under -q, 1 dense) and prints mc_scan's counters: chunks, chunks passed over after the
+look at their first columns (MC_C_QUIET), lines, kept lines seen by the full parse, records.
+usage (GPU box): python tools/scan_mode_counters.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
