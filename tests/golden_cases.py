@@ -51,6 +51,9 @@ CASES = {
     # PASSES and takes that line's contig (extract_contexts.py:167 before :179, :214)
     "gat_q_handoff": dict(spec=dict(seed=31, contigs=[("ctgA", 5000), ("ctgB", 4000), ("ctgC", 3000)], n_reads=90, len_min=40, len_max=160),
                           motif="GAT", model=R95, base="A", s=1, q=13.5, post="truncate", shuffle=9),
+    # the same with every A a target: each read ends inside an open window
+    "A_q_handoff": dict(spec=dict(seed=32, contigs=[("c1", 1500), ("c2", 1200), ("c3", 900)], n_reads=30, len_min=60, len_max=200),
+                        motif="A", model=R95, base="A", s=2, q=13.5, post="truncate", shuffle=4),
     # malformed / odd lines
     "adversarial": dict(spec=_SPEC3, motif="GATC", model=R95, base="A", meth=True, s=1, post="adversarial"),
     # bare estimator pickles -> 'general' model path

@@ -55,7 +55,7 @@ def test_diffs_match_reference(name, tmp_path, capsys, cuda_lib):
     assert "%d observations with too many skips\n" % c["too_many_skips"] in stdout
 
 
-@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q", "gat_q_handoff"])
+@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q", "gat_q_handoff", "A_q_handoff"])
 @pytest.mark.parametrize("chunk", [40000, 300000])
 def test_chunked_equals_whole(name, chunk, tmp_path, capsys, cuda_lib):
     """Streaming in small read-aligned chunks (window hand-off across chunk edges) must not change a byte."""
@@ -161,7 +161,7 @@ def _cli_args(case, inp):
     return gc.cli_args(case, inp)
 
 
-@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q", "gat_q_handoff", "pos_p"])
+@pytest.mark.parametrize("name", ["gatc_s1", "A_s2", "adversarial", "gatc_q", "gat_q_handoff", "A_q_handoff", "pos_p"])
 @pytest.mark.parametrize("workers", [3, 7])
 def test_worker_ranges_equal_single_worker(name, workers, tmp_path, capsys, cuda_lib):
     """`-t N` (mCaller.py:63-68 byte ranges, one extract_features call per range, worker i on GPU i mod n): each worker closes

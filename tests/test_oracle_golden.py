@@ -7,7 +7,7 @@ import pytest
 
 import golden_cases as gc
 
-FAST = ["masonread1_p", "masonread1_gatc", "masonread1_gatc_s2", "gatc_s0", "gatc_s2", "A_s0", "A_s2", "gaa_s1", "pos_p", "gatc_q", "gat_q_handoff",
+FAST = ["masonread1_p", "masonread1_gatc", "masonread1_gatc_s2", "gatc_s0", "gatc_s2", "A_s0", "A_s2", "gaa_s1", "pos_p", "gatc_q", "gat_q_handoff", "A_q_handoff",
         "adversarial", "bare_r94", "bare_caay_p", "cg_c", "gatc_s1", "gaa_s2", "rf_gatc", "lr_gatc", "nbc_gatc"]
 
 
