@@ -154,7 +154,7 @@ namespace {
 // ---- stage 2: gather records into file order ----------------------------------------------------------------
 // Stage 1 hands over two tables: per chunk {first record slot, count | filler flag << 16 | state << 17} and per RUN of
 // consecutive chunks (one warp parsed them in order) {records of the run, filler flag | state of the run's last kept
-// line << 1}.  The order of the records is fixed run by run: only the ~n_chunks / 32 run entries are prefix-summed, a
+// line << 1}.  The order of the records is fixed run by run: only the ~n_chunks / 128 run entries are prefix-summed, a
 // warp then walks its run's chunk entries (most are empty in sparse mode) and copies the records.
 //
 // Stage 1 records the first kept line of a run blindly because the line before it belongs to another warp.  With all

@@ -49,7 +49,7 @@ constexpr int NW = WB / 32;                   // 128 mask words = 4 per lane
 #define MC_SCAN_MIN_CTAS 1
 #endif
 #ifndef MC_SCAN_RUN
-#define MC_SCAN_RUN 32
+#define MC_SCAN_RUN 128
 #endif
 
 constexpr int WARPS = MC_SCAN_WARPS;

@@ -429,7 +429,7 @@ def _junk_blocks(tsv, seed):
     return "\n".join(out).encode()
 
 
-@pytest.mark.parametrize("run_len", [0, 1, 3, 64])
+@pytest.mark.parametrize("run_len", [0, 1, 3, 64, 200])
 @pytest.mark.parametrize("variant", ["junk", "fuzz", "plain"])
 def test_scan_runs_and_quiet_chunks_match_oracle(variant, run_len, cuda_lib, oracle):
     """The sparse scan passes over chunks whose lines all sit on non-candidate positions and carries the 'last kept line'
