@@ -11,6 +11,7 @@ synthetic eventalign text resident in HBM.  The workload follows BASELINE.json `
                     combined histogram -- all inside the timed region.
   --config 3        configs[3]: -c RF (tree-walk kernel).     --config 4: configs[4]: motif CAAYNNNNNRTAC + its model.
   --motif A         dense regime (every A is a target: no quiet chunks in the scan).
+  --qual Q          -q read-quality filter (sparse scan in read-first mode; --scan-dense: every kept line recorded, as round 1).
 
 `value` times the pass with the text already resident in HBM (CUDA events, max over ranks); `e2e` times the same metric
 through the public host-buffer path (pinned host memory -> H2D -> kernels -> rows D2H -> `.diffs` text); `roofline` is the
